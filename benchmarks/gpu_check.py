@@ -1,0 +1,348 @@
+"""Kernel-by-kernel numerics + timing checks on a real B200 (run through gpurun).
+
+    python benchmarks/gpu_check.py <case> [<case> ...]
+
+Every case compares a hand-written sm_100a kernel against a plain PyTorch fp32 reference of the same op and
+prints one ``CHECK <name> ... PASS|FAIL`` line; timing cases print ``TIME`` lines (CUDA events, warm-up, median).
+The shell driver (benchmarks/run_gpu_checks.sh) runs each case in its own process under ``timeout`` so that a
+hung kernel cannot take the whole GPU call down.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+import traceback
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+
+import b200ddl  # noqa: F401
+from b200ddl import ops
+from b200ddl.ops import conv as C
+
+DEV = "cuda"
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a = a.float()
+    b = b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def report(name: str, err: float, tol: float, extra: str = "") -> bool:
+    ok = err == err and err <= tol
+    print(f"CHECK {name} err={err:.3e} tol={tol:.1e} {extra} {'PASS' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
+def time_fn(fn, iters=20, warmup=5, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def make_conv_case(N, H, W, cin, cout, R, stride, pad, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    x = torch.randn(N, H, W, cin, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(R * R, cout, cin, device=DEV, generator=g) * (1.0 / (R * R * cin) ** 0.5))
+    Ho = (H + 2 * pad - R) // stride + 1
+    Wo = (W + 2 * pad - R) // stride + 1
+    return x, w, Ho, Wo
+
+
+CONV_SHAPES = [
+    # name, N, H, W, cin, cout, R, stride, pad
+    ("1x1_64_256_56", 8, 56, 56, 64, 256, 1, 1, 0),
+    ("1x1_256_64_56", 8, 56, 56, 256, 64, 1, 1, 0),
+    ("1x1_512_2048_7", 32, 7, 7, 512, 2048, 1, 1, 0),
+    ("1x1_1024_256_14", 16, 14, 14, 1024, 256, 1, 1, 0),
+    ("3x3_64_64_56", 4, 56, 56, 64, 64, 3, 1, 1),
+    ("3x3_128_128_28", 8, 28, 28, 128, 128, 3, 1, 1),
+    ("3x3_256_256_14", 8, 14, 14, 256, 256, 3, 1, 1),
+    ("3x3_512_512_7", 16, 7, 7, 512, 512, 3, 1, 1),
+    ("3x3s2_128_128_56", 4, 56, 56, 128, 128, 3, 2, 1),
+    ("3x3s2_512_512_14", 8, 14, 14, 512, 512, 3, 2, 1),
+    ("1x1s2_256_512_56", 4, 56, 56, 256, 512, 1, 2, 0),
+]
+
+
+def case_conv_fwd():
+    ok = True
+    for name, N, H, W, cin, cout, R, stride, pad in CONV_SHAPES:
+        try:
+            x, w, Ho, Wo = make_conv_case(N, H, W, cin, cout, R, stride, pad)
+            wk = w.to(torch.bfloat16).reshape(R * R * cout, cin).contiguous()
+            y = torch.empty(N, Ho, Wo, cout, device=DEV, dtype=torch.bfloat16)
+            ssum = torch.zeros(cout, device=DEV)
+            ssq = torch.zeros(cout, device=DEV)
+            op = C.ConvForward(x, wk, y, R, R, stride, pad, ssum, ssq)
+            op.run()
+            torch.cuda.synchronize()
+            ref = C.conv_reference(x, w.to(torch.bfloat16), R, R, stride, pad)
+            ok &= report(f"conv_fwd/{name}", rel_err(y, ref), 1.5e-2, f"box={op.box} grid={op.plan.grid} bn={op.plan.block_n}")
+            rs = ref.sum(dim=(0, 1, 2))
+            rq = (ref * ref).sum(dim=(0, 1, 2))
+            ok &= report(f"conv_fwd_stats_sum/{name}", float((ssum - rs).abs().max() / (rs.abs().max() + 1e-6)), 2e-2)
+            ok &= report(f"conv_fwd_stats_sq/{name}", float((ssq - rq).abs().max() / (rq.abs().max() + 1e-6)), 2e-2)
+        except Exception:
+            ok = False
+            print(f"CHECK conv_fwd/{name} EXCEPTION FAIL\n{traceback.format_exc()}", flush=True)
+    return ok
+
+
+def case_conv_dgrad():
+    ok = True
+    for name, N, H, W, cin, cout, R, stride, pad in CONV_SHAPES:
+        try:
+            x, w, Ho, Wo = make_conv_case(N, H, W, cin, cout, R, stride, pad)
+            g = torch.Generator(device=DEV).manual_seed(1)
+            dy = torch.randn(N, Ho, Wo, cout, device=DEV, generator=g).to(torch.bfloat16)
+            dx = torch.full((N, H, W, cin), 7.0, device=DEV, dtype=torch.bfloat16)
+            op = C.ConvDgrad(dy, w, dx, R, R, stride, pad)
+            op.run()
+            torch.cuda.synchronize()
+            wt = C.weight_from_kernel_layout(w.to(torch.bfloat16).float(), R, R)
+            ref = torch.nn.grad.conv2d_input((N, cin, H, W), wt, dy.float().permute(0, 3, 1, 2), stride=stride,
+                                             padding=pad).permute(0, 2, 3, 1)
+            ok &= report(f"conv_dgrad/{name}", rel_err(dx, ref), 1.5e-2, f"parts={len(op.parts)}")
+        except Exception:
+            ok = False
+            print(f"CHECK conv_dgrad/{name} EXCEPTION FAIL\n{traceback.format_exc()}", flush=True)
+    return ok
+
+
+def case_conv_wgrad():
+    ok = True
+    for name, N, H, W, cin, cout, R, stride, pad in CONV_SHAPES:
+        try:
+            x, w, Ho, Wo = make_conv_case(N, H, W, cin, cout, R, stride, pad)
+            g = torch.Generator(device=DEV).manual_seed(2)
+            dy = torch.randn(N, Ho, Wo, cout, device=DEV, generator=g).to(torch.bfloat16)
+            dw = torch.zeros(R * R * cout, cin, device=DEV)
+            op = C.ConvWgrad(dy, x, dw, R, R, stride, pad)
+            op.run()
+            torch.cuda.synchronize()
+            ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, R, R),
+                                              dy.float().permute(0, 3, 1, 2), stride=stride, padding=pad)
+            ref = C.weight_to_kernel_layout(ref).reshape(R * R * cout, cin)
+            ok &= report(f"conv_wgrad/{name}", rel_err(dw, ref), 1.0e-2,
+                         f"box={op.box} units={op.plan.units} stages={op.plan.stages}")
+        except Exception:
+            ok = False
+            print(f"CHECK conv_wgrad/{name} EXCEPTION FAIL\n{traceback.format_exc()}", flush=True)
+    return ok
+
+
+def case_elementwise():
+    e = ops.ext("_b200_ops")
+    ok = True
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for C_ in (64, 256, 2048):
+        M = 4096 + 64
+        y = torch.randn(M, C_, device=DEV, generator=g).to(torch.bfloat16)
+        res = torch.randn(M, C_, device=DEV, generator=g).to(torch.bfloat16)
+        gamma = torch.rand(C_, device=DEV, generator=g) + 0.5
+        beta = torch.randn(C_, device=DEV, generator=g)
+        s = torch.zeros(C_, device=DEV); q = torch.zeros(C_, device=DEV)
+        e.channel_stats(y, s, q)
+        yf = y.float()
+        ok &= report(f"channel_stats_sum/C{C_}", rel_err(s, yf.sum(0)), 1e-3)
+        ok &= report(f"channel_stats_sq/C{C_}", rel_err(q, (yf * yf).sum(0)), 1e-3)
+        rm = torch.zeros(C_, device=DEV); rv = torch.ones(C_, device=DEV)
+        mean = torch.empty(C_, device=DEV); invstd = torch.empty(C_, device=DEV)
+        scale = torch.empty(C_, device=DEV); shift = torch.empty(C_, device=DEV)
+        e.bn_finalize(s, q, float(M), gamma, beta, rm, rv, 0.1, 1e-5, mean, invstd, scale, shift, True)
+        mref = yf.mean(0); vref = yf.var(0, unbiased=False)
+        ok &= report(f"bn_finalize_mean/C{C_}", float((mean - mref).abs().max()), 1e-3)
+        ok &= report(f"bn_finalize_invstd/C{C_}", rel_err(invstd, (vref + 1e-5).rsqrt()), 2e-3)
+        ok &= report(f"bn_finalize_zeroed/C{C_}", float(s.abs().max() + q.abs().max()), 0.0)
+        out = torch.empty_like(y)
+        e.bn_apply(y, scale, shift, res, None, None, out, True)
+        ref = torch.relu((yf - mref) * (vref + 1e-5).rsqrt() * gamma + beta + res.float())
+        ok &= report(f"bn_apply_relu_res/C{C_}", rel_err(out, ref), 1.5e-2)
+        # backward
+        gout = torch.randn(M, C_, device=DEV, generator=g).to(torch.bfloat16)
+        sdz = torch.zeros(C_, device=DEV); sdzy = torch.zeros(C_, device=DEV)
+        e.bn_bwd_reduce(gout, None, out, y, sdz, sdzy)
+        dz_ref = gout.float() * (out.float() > 0)
+        ok &= report(f"bn_bwd_reduce_dz/C{C_}", rel_err(sdz, dz_ref.sum(0)), 2e-3)
+        ok &= report(f"bn_bwd_reduce_dzy/C{C_}", rel_err(sdzy, (dz_ref * yf).sum(0)), 2e-3)
+        dgamma = torch.empty(C_, device=DEV); dbeta = torch.empty(C_, device=DEV)
+        cA = torch.empty(C_, device=DEV); cB = torch.empty(C_, device=DEV); cC = torch.empty(C_, device=DEV)
+        e.bn_bwd_coeffs(sdz, sdzy, gamma, mean, invstd, float(M), dgamma, dbeta, cA, cB, cC)
+        dy = torch.empty_like(y); dz = torch.empty_like(y)
+        e.bn_bwd_apply(gout, None, out, y, cA, cB, cC, dy, dz)
+        # autograd reference
+        yr = yf.clone().requires_grad_(True)
+        gr = gamma.clone().requires_grad_(True); br = beta.clone().requires_grad_(True)
+        o = torch.relu(torch.nn.functional.batch_norm(yr, None, None, gr, br, True, 0.1, 1e-5) + res.float())
+        o.backward(gout.float())
+        ok &= report(f"bn_bwd_dy/C{C_}", rel_err(dy, yr.grad), 2e-2)
+        ok &= report(f"bn_bwd_dgamma/C{C_}", rel_err(dgamma, gr.grad), 1e-2)
+        ok &= report(f"bn_bwd_dbeta/C{C_}", rel_err(dbeta, br.grad), 1e-2)
+        ok &= report(f"bn_bwd_dz/C{C_}", rel_err(dz, dz_ref), 1e-2)
+    # maxpool
+    x = torch.relu(torch.randn(4, 16, 16, 64, device=DEV, generator=g)).to(torch.bfloat16)
+    out = torch.empty(4, 8, 8, 64, device=DEV, dtype=torch.bfloat16)
+    e.maxpool_fwd(x, out)
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    pr = torch.nn.functional.max_pool2d(xr, 3, 2, 1)
+    ok &= report("maxpool_fwd", rel_err(out, pr.permute(0, 2, 3, 1)), 0.0)
+    go = torch.randn(4, 8, 8, 64, device=DEV, generator=g).to(torch.bfloat16)
+    dx = torch.empty_like(x)
+    e.maxpool_bwd(x, out, go, dx)
+    pr.backward(go.float().permute(0, 3, 1, 2))
+    ok &= report("maxpool_bwd", rel_err(dx, xr.grad.permute(0, 2, 3, 1)), 1e-2)
+    # gap
+    x = torch.randn(8, 7, 7, 2048, device=DEV, generator=g).to(torch.bfloat16)
+    out = torch.empty(8, 2048, device=DEV, dtype=torch.bfloat16)
+    e.gap_fwd(x, out, 0.0, 0)
+    ok &= report("gap_fwd", rel_err(out, x.float().mean(dim=(1, 2))), 1e-2)
+    go = torch.randn(8, 2048, device=DEV, generator=g).to(torch.bfloat16)
+    dx = torch.empty_like(x)
+    e.gap_bwd(go, dx, 0.0, 0)
+    ok &= report("gap_bwd", rel_err(dx, (go.float() / 49)[:, None, None, :].expand(8, 7, 7, 2048)), 1e-2)
+    out_d = torch.empty_like(out)
+    e.gap_fwd(x, out_d, 0.5, 1234)
+    keep = (out_d.float() != 0).float().mean().item()
+    ok &= report("gap_dropout_keep_rate", abs(keep - 0.5), 0.05)
+    # softmax ce
+    for K in (5, 1000):
+        B = 256
+        logits = torch.randn(B, K, device=DEV, generator=g) * 3
+        labels = torch.randint(0, K, (B,), device=DEV, generator=g)
+        dl = torch.empty_like(logits); lr_ = torch.empty(B, device=DEV); st = torch.zeros(2, device=DEV)
+        e.softmax_ce(logits, labels, dl, lr_, st, 1.0 / B)
+        lg = logits.clone().requires_grad_(True)
+        loss = torch.nn.functional.cross_entropy(lg, labels)
+        loss.backward()
+        ok &= report(f"softmax_ce_loss/K{K}", abs(st[0].item() / B - loss.item()), 1e-4)
+        ok &= report(f"softmax_ce_grad/K{K}", rel_err(dl, lg.grad), 1e-3)
+        acc = (logits.argmax(1) == labels).float().sum().item()
+        ok &= report(f"softmax_ce_acc/K{K}", abs(st[1].item() - acc), 0.0)
+    # preprocess
+    xb = torch.randint(0, 256, (2, 32, 32, 3), device=DEV, dtype=torch.uint8, generator=g)
+    ob = torch.empty(2, 32, 32, 8, device=DEV, dtype=torch.bfloat16)
+    e.preprocess_u8(xb, ob, 1 / 127.5, -1.0)
+    ok &= report("preprocess_u8", rel_err(ob[..., :3], xb.float() / 127.5 - 1), 1e-2)
+    ok &= report("preprocess_u8_pad", float(ob[..., 3:].float().abs().max()), 0.0)
+    # optimizers
+    n = 4096 * 4
+    p = torch.randn(n, device=DEV, generator=g); gr = torch.randn(n, device=DEV, generator=g)
+    hyper = torch.tensor([0.1, 0.9, 0.999, 1e-8, 1e-4, 1.0, 1 - 0.9, 1 - 0.999], device=DEV)
+    pr_ = p.clone().requires_grad_(True)
+    opt = torch.optim.SGD([pr_], lr=0.1, momentum=0.9, weight_decay=1e-4)
+    mom = torch.zeros(n, device=DEV); p16 = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    pm = p.clone()
+    for _ in range(3):
+        pr_.grad = gr.clone(); opt.step()
+        e.sgd_step(pm, gr, mom, p16, hyper, False)
+    ok &= report("sgd_step", rel_err(pm, pr_.detach()), 1e-5)
+    ok &= report("sgd_step_bf16", rel_err(p16, pm), 1e-2)
+    pr_ = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr_], lr=0.1, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    pm = p.clone(); m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
+    for t in range(1, 4):
+        pr_.grad = gr.clone(); opt.step()
+        hyper[6] = 1 - 0.9 ** t; hyper[7] = 1 - 0.999 ** t
+        e.adam_step(pm, gr, m, v, None, hyper)
+    ok &= report("adam_step", rel_err(pm, pr_.detach()), 1e-3)
+    pr_ = p.clone().requires_grad_(True)
+    opt = torch.optim.Adadelta([pr_], lr=1.0, rho=0.9, eps=1e-6)
+    pm = p.clone(); sq = torch.zeros(n, device=DEV); ac = torch.zeros(n, device=DEV)
+    h2 = torch.tensor([1.0, 0.0, 0.9, 1e-6, 0.0, 1.0, 1.0, 1.0], device=DEV)
+    for t in range(3):
+        pr_.grad = gr.clone(); opt.step()
+        e.adadelta_step(pm, gr, sq, ac, None, h2)
+    ok &= report("adadelta_step", rel_err(pm, pr_.detach()), 1e-3)
+    return ok
+
+
+BIG_SHAPES = [
+    # ResNet-50 @ batch 256 layer shapes: name, N, H, W, cin, cout, R, stride, pad
+    ("s1_1x1_64_256", 256, 56, 56, 64, 256, 1, 1, 0),
+    ("s1_1x1_256_64", 256, 56, 56, 256, 64, 1, 1, 0),
+    ("s1_3x3_64", 256, 56, 56, 64, 64, 3, 1, 1),
+    ("s2_1x1_128_512", 256, 28, 28, 128, 512, 1, 1, 0),
+    ("s2_3x3_128", 256, 28, 28, 128, 128, 3, 1, 1),
+    ("s3_1x1_256_1024", 256, 14, 14, 256, 1024, 1, 1, 0),
+    ("s3_1x1_1024_256", 256, 14, 14, 1024, 256, 1, 1, 0),
+    ("s3_3x3_256", 256, 14, 14, 256, 256, 3, 1, 1),
+    ("s4_1x1_512_2048", 256, 7, 7, 512, 2048, 1, 1, 0),
+    ("s4_3x3_512", 256, 7, 7, 512, 512, 3, 1, 1),
+    ("s2_3x3s2_128", 256, 56, 56, 128, 128, 3, 2, 1),
+]
+
+
+def case_conv_time():
+    flush = torch.empty(256 * 1024 * 1024, device=DEV, dtype=torch.uint8)
+    for name, N, H, W, cin, cout, R, stride, pad in BIG_SHAPES:
+        try:
+            x, w, Ho, Wo = make_conv_case(N, H, W, cin, cout, R, stride, pad)
+            wk = w.to(torch.bfloat16).reshape(R * R * cout, cin).contiguous()
+            y = torch.empty(N, Ho, Wo, cout, device=DEV, dtype=torch.bfloat16)
+            ssum = torch.zeros(cout, device=DEV); ssq = torch.zeros(cout, device=DEV)
+            fwd = C.ConvForward(x, wk, y, R, R, stride, pad, ssum, ssq)
+            fwd_ns = C.ConvForward(x, wk, y, R, R, stride, pad)
+            dy = torch.randn_like(y)
+            dx = torch.empty_like(x)
+            dg = C.ConvDgrad(dy, w, dx, R, R, stride, pad)
+            dw = torch.zeros(R * R * cout, cin, device=DEV)
+            wg = C.ConvWgrad(dy, x, dw, R, R, stride, pad)
+            xc = x.permute(0, 3, 1, 2)  # channels_last NCHW view
+            wt = C.weight_from_kernel_layout(w.to(torch.bfloat16), R, R).contiguous(memory_format=torch.channels_last)
+            dyc = dy.permute(0, 3, 1, 2)
+            flops = 2.0 * N * Ho * Wo * cout * cin * R * R
+            t_f = time_fn(fwd.run, flush=flush)
+            t_fn = time_fn(fwd_ns.run, flush=flush)
+            t_d = time_fn(dg.run, flush=flush)
+            t_w = time_fn(wg.run, flush=flush)
+            t_cf = time_fn(lambda: torch.nn.functional.conv2d(xc, wt, stride=stride, padding=pad), flush=flush)
+            t_cd = time_fn(lambda: torch.nn.grad.conv2d_input(xc.shape, wt, dyc, stride=stride, padding=pad), flush=flush)
+            t_cw = time_fn(lambda: torch.nn.grad.conv2d_weight(xc, wt.shape, dyc, stride=stride, padding=pad), flush=flush)
+            bytes_f = (x.numel() + y.numel()) * 2
+            print(f"TIME {name} fwd+stats={t_f*1e3:.0f}us fwd={t_fn*1e3:.0f}us ({flops/t_fn/1e9:.0f} TF/s, "
+                  f"{bytes_f/t_fn/1e6:.0f} GB/s) cudnn_fwd={t_cf*1e3:.0f}us | dgrad={t_d*1e3:.0f}us cudnn={t_cd*1e3:.0f}us | "
+                  f"wgrad={t_w*1e3:.0f}us cudnn={t_cw*1e3:.0f}us", flush=True)
+        except Exception:
+            print(f"TIME {name} EXCEPTION\n{traceback.format_exc()}", flush=True)
+    return True
+
+
+CASES = {
+    "conv_fwd": case_conv_fwd,
+    "conv_dgrad": case_conv_dgrad,
+    "conv_wgrad": case_conv_wgrad,
+    "elementwise": case_elementwise,
+    "conv_time": case_conv_time,
+}
+
+if __name__ == "__main__":
+    torch.backends.cudnn.benchmark = True
+    names = sys.argv[1:] or list(CASES)
+    allok = True
+    for n in names:
+        t0 = time.time()
+        try:
+            ok = CASES[n]()
+        except Exception:
+            ok = False
+            print(f"CASE {n} EXCEPTION\n{traceback.format_exc()}", flush=True)
+        allok &= bool(ok)
+        print(f"CASE {n} {'PASS' if ok else 'FAIL'} ({time.time() - t0:.1f}s)", flush=True)
+    sys.exit(0 if allok else 1)

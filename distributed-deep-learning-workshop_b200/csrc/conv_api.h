@@ -1,0 +1,33 @@
+// Plain (torch-free) interface between the CUDA translation units and the pybind layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "conv_params.h"
+
+namespace b200 {
+
+struct ConvPlanRaw {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  CUtensorMap tmD;
+  ConvParams p;
+  int block_n;
+  int grid;
+  bool stats;
+};
+
+// dims/strides innermost first; strides in BYTES for dims 1..rank-1; SWIZZLE_128B, zero OOB fill.
+CUtensorMap encode_bf16(void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+void conv_plan_launch(const ConvPlanRaw& plan, cudaStream_t stream);
+
+struct WgradPlanRaw {
+  CUtensorMap tmDY;     // grad of conv output, NHWC view, box (64ch, bw, bh, bn)
+  CUtensorMap tmX[4];   // input views (parity views for strided convs)
+  WgradParams p;
+  int grid;
+};
+void wgrad_plan_launch(const WgradPlanRaw& plan, cudaStream_t stream);
+
+}  // namespace b200

@@ -1,0 +1,263 @@
+// pybind layer for the tcgen05 convolution kernels: validates tensors, derives the tiling, encodes the TMA
+// descriptors once, and exposes launchable plan objects (static buffers => plans are reused under CUDA graphs).
+#include <ATen/cuda/CUDAContext.h>
+#include <torch/extension.h>
+
+#include <cstring>
+#include <vector>
+
+#include "conv_api.h"
+
+namespace b200 {
+
+static void check_nhwc_view(const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kBFloat16, name, " must be bf16");
+  TORCH_CHECK(t.dim() == 4, name, " must be 4-D (N,H,W,C)");
+  TORCH_CHECK(t.stride(3) == 1, name, " must be channel-contiguous (NHWC)");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, name, " must be 16-byte aligned");
+  TORCH_CHECK((t.stride(2) * 2) % 16 == 0 && (t.stride(1) * 2) % 16 == 0 && (t.stride(0) * 2) % 16 == 0, name,
+              " strides must be multiples of 16 bytes");
+}
+
+// 4-D map over a (possibly strided) NHWC view: dims (C, W, H, N).
+static CUtensorMap map_nhwc(const at::Tensor& t, int box_c, int bw, int bh, int bn) {
+  uint64_t dims[4] = {(uint64_t)t.size(3), (uint64_t)t.size(2), (uint64_t)t.size(1), (uint64_t)t.size(0)};
+  uint64_t strides[3] = {(uint64_t)t.stride(2) * 2, (uint64_t)t.stride(1) * 2, (uint64_t)t.stride(0) * 2};
+  uint32_t box[4] = {(uint32_t)box_c, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  return encode_bf16(t.data_ptr(), 4, dims, strides, box);
+}
+// 2-D map over a row-major [rows, cols] matrix with given row pitch (elements).
+static CUtensorMap map_2d(void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_cols, int box_rows) {
+  uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  uint64_t strides[1] = {(uint64_t)pitch * 2};
+  uint32_t box[2] = {(uint32_t)box_cols, (uint32_t)box_rows};
+  return encode_bf16(ptr, 2, dims, strides, box);
+}
+
+static int sm_count() { return at::cuda::getCurrentDeviceProperties()->multiProcessorCount; }
+
+struct ConvPlan {
+  ConvPlanRaw raw;
+  std::vector<at::Tensor> keep;
+  int64_t launches = 0;
+
+  // views:  1..4 NHWC (possibly strided) input views on one pixel grid (N, Hv, Wv, Cin)
+  // weight: bf16 [taps*Cout, Cin];  out: NHWC view (N, Ho, Wo, Cout)
+  // tap_map/dw/dh: per tap view index + pixel offset;  bw/bh/bn: pixel box (0 => flat 1x1 mode)
+  ConvPlan(std::vector<at::Tensor> views, at::Tensor weight, at::Tensor out, std::vector<int64_t> tap_map,
+           std::vector<int64_t> tap_dw, std::vector<int64_t> tap_dh, int64_t bw, int64_t bh, int64_t bn,
+           c10::optional<at::Tensor> stat_sum, c10::optional<at::Tensor> stat_sqsum, int64_t max_ctas) {
+    TORCH_CHECK(!views.empty() && views.size() <= 4, "1..4 input views");
+    for (auto& v : views) check_nhwc_view(v, "input view");
+    check_nhwc_view(out, "out");
+    const int taps = (int)tap_map.size();
+    TORCH_CHECK(taps >= 1 && taps <= kMaxTaps, "1..16 taps");
+    TORCH_CHECK(tap_dw.size() == tap_map.size() && tap_dh.size() == tap_map.size());
+    const int64_t cin = views[0].size(3);
+    const int64_t cout = out.size(3);
+    TORCH_CHECK(cin % 64 == 0, "Cin must be a multiple of 64, got ", cin);
+    TORCH_CHECK(cout % 64 == 0, "Cout must be a multiple of 64, got ", cout);
+    TORCH_CHECK(weight.is_cuda() && weight.scalar_type() == at::kBFloat16 && weight.is_contiguous() &&
+                    weight.dim() == 2 && weight.size(0) == taps * cout && weight.size(1) == cin,
+                "weight must be bf16 [taps*Cout, Cin]");
+    ConvParams& p = raw.p;
+    std::memset(&p, 0, sizeof(p));
+    raw.block_n = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
+    p.taps = taps;
+    p.kblocks = (int)(cin / 64);
+    p.cout = (int)cout;
+    p.n_blocks = (int)(cout / raw.block_n);
+    for (int t = 0; t < taps; ++t) {
+      TORCH_CHECK(tap_map[t] >= 0 && tap_map[t] < (int64_t)views.size());
+      p.tap_map[t] = (int8_t)tap_map[t];
+      p.tap_dw[t] = (int8_t)tap_dw[t];
+      p.tap_dh[t] = (int8_t)tap_dh[t];
+    }
+    const int64_t N = out.size(0), Ho = out.size(1), Wo = out.size(2);
+    if (bw == 0) {
+      TORCH_CHECK(views.size() == 1 && taps == 1 && tap_dw[0] == 0 && tap_dh[0] == 0, "flat mode is 1x1 only");
+      TORCH_CHECK(views[0].is_contiguous() && out.is_contiguous(), "flat mode needs dense NHWC tensors");
+      TORCH_CHECK(views[0].size(0) == N && views[0].size(1) == Ho && views[0].size(2) == Wo);
+      const int64_t M = N * Ho * Wo;
+      p.mode = 0;
+      p.valid_rows = kBlockM;
+      p.m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+      raw.tmA[0] = map_2d(views[0].data_ptr(), M, cin, cin, 64, kBlockM);
+      for (int i = 1; i < 4; ++i) raw.tmA[i] = raw.tmA[0];
+      raw.tmD = map_2d(out.data_ptr(), M, cout, cout, 64, kBlockM);
+    } else {
+      TORCH_CHECK(bw * bh * bn <= kBlockM && bw * bh * bn >= 8, "box must hold 8..128 pixels");
+      TORCH_CHECK(Wo % bw == 0 && Ho % bh == 0 && N % bn == 0, "box must tile the output exactly: out ", N, "x", Ho,
+                  "x", Wo, " box ", bn, "x", bh, "x", bw);
+      p.mode = 1;
+      p.bw = (int)bw;
+      p.bh = (int)bh;
+      p.bn = (int)bn;
+      p.valid_rows = (int)(bw * bh * bn);
+      p.tiles_w = (int)(Wo / bw);
+      p.tiles_h = (int)(Ho / bh);
+      p.m_tiles = (int)(p.tiles_w * p.tiles_h * (N / bn));
+      for (size_t i = 0; i < 4; ++i) {
+        const at::Tensor& v = views[i < views.size() ? i : 0];
+        TORCH_CHECK(v.size(0) == N && v.size(3) == cin);
+        raw.tmA[i] = map_nhwc(v, 64, (int)bw, (int)bh, (int)bn);
+      }
+      raw.tmD = map_nhwc(out, 64, (int)bw, (int)bh, (int)bn);
+    }
+    raw.tmB = map_2d(weight.data_ptr(), taps * cout, cin, cin, 64, raw.block_n);
+    p.num_tiles = p.m_tiles * p.n_blocks;
+    raw.stats = stat_sum.has_value();
+    if (raw.stats) {
+      TORCH_CHECK(stat_sqsum.has_value());
+      TORCH_CHECK(stat_sum->is_cuda() && stat_sum->scalar_type() == at::kFloat && stat_sum->numel() >= cout);
+      TORCH_CHECK(stat_sqsum->is_cuda() && stat_sqsum->scalar_type() == at::kFloat && stat_sqsum->numel() >= cout);
+      p.stat_sum = stat_sum->data_ptr<float>();
+      p.stat_sqsum = stat_sqsum->data_ptr<float>();
+      keep.push_back(*stat_sum);
+      keep.push_back(*stat_sqsum);
+    }
+    const int cap = max_ctas > 0 ? (int)max_ctas : sm_count();
+    raw.grid = p.num_tiles < cap ? p.num_tiles : cap;
+    for (auto& v : views) keep.push_back(v);
+    keep.push_back(weight);
+    keep.push_back(out);
+  }
+  void run() {
+    conv_plan_launch(raw, at::cuda::getCurrentCUDAStream());
+    ++launches;
+  }
+  int grid() const { return raw.grid; }
+  int block_n() const { return raw.block_n; }
+};
+
+struct WgradPlan {
+  WgradPlanRaw raw;
+  std::vector<at::Tensor> keep;
+  int64_t launches = 0;
+
+  // dy: NHWC view (N, Ho, Wo, Cout) bf16;  views: input views on the same pixel grid;  dw: fp32 [taps*Cout, Cin]
+  WgradPlan(at::Tensor dy, std::vector<at::Tensor> views, at::Tensor dw, int64_t R, int64_t S,
+            std::vector<int64_t> tap_map, std::vector<int64_t> tap_dw, std::vector<int64_t> tap_dh, int64_t bw,
+            int64_t bh, int64_t bn, int64_t px_chunks, int64_t max_ctas) {
+    check_nhwc_view(dy, "dy");
+    TORCH_CHECK(!views.empty() && views.size() <= 4);
+    for (auto& v : views) check_nhwc_view(v, "input view");
+    const int taps = (int)(R * S);
+    TORCH_CHECK(taps >= 1 && taps <= kMaxTaps && (int)tap_map.size() == taps && (int)tap_dw.size() == taps &&
+                (int)tap_dh.size() == taps);
+    const int64_t cout = dy.size(3), cin = views[0].size(3);
+    TORCH_CHECK(cin % 64 == 0 && (cout == 64 || cout % 128 == 0), "wgrad: Cin % 64 == 0 and Cout == 64 or % 128 == 0");
+    TORCH_CHECK(dw.is_cuda() && dw.scalar_type() == at::kFloat && dw.is_contiguous() && dw.numel() == taps * cout * cin,
+                "dw must be fp32 [taps*Cout, Cin]");
+    TORCH_CHECK(S >= 1 && S <= 4, "filter width 1..4");
+    WgradParams& p = raw.p;
+    std::memset(&p, 0, sizeof(p));
+    p.cout = (int)cout;
+    p.cin = (int)cin;
+    p.S = (int)S;
+    p.a_chunks = cout == 64 ? 1 : 2;
+    p.co_blocks = (int)((cout + 127) / 128);
+    const int cin_blocks = (int)(cin / 64);
+    if (S == 1) {
+      p.cb_per_group = cin_blocks < 4 ? cin_blocks : 4;
+      while (cin_blocks % p.cb_per_group) --p.cb_per_group;
+      p.acc_chunks = p.cb_per_group;
+    } else {
+      p.cb_per_group = (cin_blocks >= 2 && S * 2 <= 6) ? 2 : 1;
+      p.acc_chunks = (int)S;
+    }
+    p.G = (int)S * p.cb_per_group;
+    p.cgroups = cin_blocks / p.cb_per_group;
+    p.groups = (int)R * p.cgroups;
+    for (int t = 0; t < taps; ++t) {
+      TORCH_CHECK(tap_map[t] >= 0 && tap_map[t] < (int64_t)views.size());
+      p.tap_map[t] = (int8_t)tap_map[t];
+      p.tap_dw[t] = (int8_t)tap_dw[t];
+      p.tap_dh[t] = (int8_t)tap_dh[t];
+    }
+    const int64_t N = dy.size(0), Ho = dy.size(1), Wo = dy.size(2);
+    if (bw == 0) {
+      TORCH_CHECK(views.size() == 1 && taps == 1 && dy.is_contiguous() && views[0].is_contiguous());
+      const int64_t M = N * Ho * Wo;
+      p.mode = 0;
+      p.P = 64;
+      TORCH_CHECK(M % p.P == 0, "flat wgrad needs pixels % 64 == 0");
+      p.iters_total = (int)(M / p.P);
+      raw.tmDY = map_2d(dy.data_ptr(), M, cout, cout, 64, p.P);
+      raw.tmX[0] = map_2d(views[0].data_ptr(), M, cin, cin, 64, p.P);
+      for (int i = 1; i < 4; ++i) raw.tmX[i] = raw.tmX[0];
+    } else {
+      const int64_t P = bw * bh * bn;
+      TORCH_CHECK(P % 16 == 0 && P <= 128, "wgrad pixel box must hold a multiple of 16 pixels (<= 128), got ", P);
+      TORCH_CHECK(Wo % bw == 0 && Ho % bh == 0 && N % bn == 0, "box must tile dy exactly");
+      p.mode = 1;
+      p.P = (int)P;
+      p.bw = (int)bw;
+      p.bh = (int)bh;
+      p.bn = (int)bn;
+      p.tiles_w = (int)(Wo / bw);
+      p.tiles_h = (int)(Ho / bh);
+      p.iters_total = (int)(p.tiles_w * p.tiles_h * (N / bn));
+      raw.tmDY = map_nhwc(dy, 64, (int)bw, (int)bh, (int)bn);
+      for (size_t i = 0; i < 4; ++i) {
+        const at::Tensor& v = views[i < views.size() ? i : 0];
+        TORCH_CHECK(v.size(0) == N && v.size(3) == cin);
+        raw.tmX[i] = map_nhwc(v, 64, (int)bw, (int)bh, (int)bn);
+      }
+    }
+    const int stage_bytes = (p.a_chunks + p.G) * p.P * 128;
+    p.stages = (232448 - 256) / stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    TORCH_CHECK(p.stages >= 2, "wgrad stage does not fit shared memory");
+    const int combos = p.co_blocks * p.groups;
+    const int cap = max_ctas > 0 ? (int)max_ctas : sm_count();
+    int64_t pc = px_chunks > 0 ? px_chunks : (2 * cap + combos - 1) / combos;
+    if (pc < 1) pc = 1;
+    if (pc > p.iters_total) pc = p.iters_total;
+    p.iters_per_chunk = (int)((p.iters_total + pc - 1) / pc);
+    p.px_chunks = (p.iters_total + p.iters_per_chunk - 1) / p.iters_per_chunk;
+    p.num_units = p.px_chunks * combos;
+    p.dw = dw.data_ptr<float>();
+    raw.grid = p.num_units < cap ? p.num_units : cap;
+    keep.push_back(dy);
+    for (auto& v : views) keep.push_back(v);
+    keep.push_back(dw);
+  }
+  void run() {
+    wgrad_plan_launch(raw, at::cuda::getCurrentCUDAStream());
+    ++launches;
+  }
+  int grid() const { return raw.grid; }
+  int units() const { return raw.p.num_units; }
+  int stages() const { return raw.p.stages; }
+};
+
+}  // namespace b200
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  namespace py = pybind11;
+  m.doc() = "b200ddl tcgen05/TMA implicit-GEMM convolution kernels (sm_100a)";
+  py::class_<b200::ConvPlan>(m, "ConvPlan")
+      .def(py::init<std::vector<at::Tensor>, at::Tensor, at::Tensor, std::vector<int64_t>, std::vector<int64_t>,
+                    std::vector<int64_t>, int64_t, int64_t, int64_t, c10::optional<at::Tensor>,
+                    c10::optional<at::Tensor>, int64_t>(),
+           py::arg("views"), py::arg("weight"), py::arg("out"), py::arg("tap_map"), py::arg("tap_dw"),
+           py::arg("tap_dh"), py::arg("bw"), py::arg("bh"), py::arg("bn"), py::arg("stat_sum") = c10::nullopt,
+           py::arg("stat_sqsum") = c10::nullopt, py::arg("max_ctas") = 0)
+      .def("run", &b200::ConvPlan::run)
+      .def_readonly("launches", &b200::ConvPlan::launches)
+      .def_property_readonly("grid", &b200::ConvPlan::grid)
+      .def_property_readonly("block_n", &b200::ConvPlan::block_n);
+  py::class_<b200::WgradPlan>(m, "WgradPlan")
+      .def(py::init<at::Tensor, std::vector<at::Tensor>, at::Tensor, int64_t, int64_t, std::vector<int64_t>,
+                    std::vector<int64_t>, std::vector<int64_t>, int64_t, int64_t, int64_t, int64_t, int64_t>(),
+           py::arg("dy"), py::arg("views"), py::arg("dw"), py::arg("R"), py::arg("S"), py::arg("tap_map"),
+           py::arg("tap_dw"), py::arg("tap_dh"), py::arg("bw"), py::arg("bh"), py::arg("bn"),
+           py::arg("px_chunks") = 0, py::arg("max_ctas") = 0)
+      .def("run", &b200::WgradPlan::run)
+      .def_readonly("launches", &b200::WgradPlan::launches)
+      .def_property_readonly("grid", &b200::WgradPlan::grid)
+      .def_property_readonly("units", &b200::WgradPlan::units)
+      .def_property_readonly("stages", &b200::WgradPlan::stages);
+}

@@ -1,0 +1,284 @@
+// Implicit-GEMM convolution (forward and data-gradient) for sm_100a.
+//
+//   D[m, n] = sum_{tap, c} A_tap[m, c] * B[tap][n][c]            (bf16 x bf16 -> fp32 in TMEM -> bf16)
+//
+// * A is an NHWC bf16 activation.  An M-tile is either 128 consecutive pixels of the flattened
+//   [N*H*W, C] view ("flat", 1x1 stride-1 convs) or a TMA box (bw x bh x bn pixels, <=128) of the 4-D tensor
+//   ("box", 3x3 / strided convs).  A filter tap is just a coordinate offset of the box; zero padding is the
+//   TMA out-of-bounds fill, so there is no im2col buffer and no halo handling in the kernel.
+//   Strided convs pass up to 4 "parity" views of the input (each a strided NHWC view) and a tap table that
+//   says which view + offset each tap reads.
+// * B is the filter as a [taps*Cout, Cin] K-major matrix.
+// * Warp-specialised, persistent: warp0 = TMA producer, warp1 = tcgen05.mma issuer, warp2 = TMEM allocator,
+//   warps4-7 = epilogue (tcgen05.ld -> bf16 -> swizzled smem -> TMA store), double-buffered TMEM accumulator
+//   so the epilogue of tile i overlaps the main loop of tile i+1.
+// * Optional fused BatchNorm statistics: per-output-channel sum and sum-of-squares of the fp32 accumulators
+//   are reduced in the epilogue (warp butterfly -> smem -> one global atomic per channel per CTA), which removes
+//   the separate statistics pass over the conv output.
+#pragma once
+#include "conv_params.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+template <int BLOCK_N>
+struct ConvSmem {
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 5 : 6);
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = 2 * kBlockM * 128;  // two 128x64 bf16 store buffers
+  static constexpr int kBarBytes = 256;
+  static constexpr int kStatBytes = 2 * BLOCK_N * 4;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + kStatBytes;
+  static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
+};
+
+template <int BLOCK_N, bool kStats>
+__global__ void __launch_bounds__(256, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                  const __grid_constant__ ConvParams p) {
+  using L = ConvSmem<BLOCK_N>;
+  constexpr int kStages = L::kStages;
+  constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * L::kABytes;
+  uint8_t* sStage = smem + kStages * L::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + L::kStagingBytes);
+  uint64_t* full_bar = bars;                     // [kStages]
+  uint64_t* empty_bar = bars + kStages;          // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;      // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* sStat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::kBarBytes);  // [2][BLOCK_N]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (kStats) {
+    for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) sStat[i] = 0.f;
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int k_iters = p.taps * p.kblocks;
+  const uint32_t a_bytes = (p.mode == 0 ? kBlockM : p.valid_rows) * 128;
+  const uint32_t stage_tx = a_bytes + L::kBBytes;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_blocks;
+      const int nb = tile - m_tile * p.n_blocks;
+      int w0 = 0, h0 = 0, n0 = 0;
+      if (p.mode == 1) {
+        const int tw = m_tile % p.tiles_w;
+        const int rest = m_tile / p.tiles_w;
+        const int th = rest % p.tiles_h;
+        w0 = tw * p.bw;
+        h0 = th * p.bh;
+        n0 = (rest / p.tiles_h) * p.bn;
+      }
+      for (int t = 0; t < p.taps; ++t) {
+        const CUtensorMap* am = &tmA0;
+        if (p.tap_map[t] == 1) am = &tmA1;
+        if (p.tap_map[t] == 2) am = &tmA2;
+        if (p.tap_map[t] == 3) am = &tmA3;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+          if (p.mode == 0)
+            tma_load_2d(sA + stage * L::kABytes, am, &full_bar[stage], kb * kBlockK, m_tile * kBlockM);
+          else
+            tma_load_4d(sA + stage * L::kABytes, am, &full_bar[stage], kb * kBlockK, w0 + p.tap_dw[t],
+                        h0 + p.tap_dh[t], n0);
+          tma_load_2d(sB + stage * L::kBBytes, &tmB, &full_bar[stage], kb * kBlockK, t * p.cout + nb * BLOCK_N);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * L::kABytes), 16, 1024);
+        const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * L::kBBytes), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int ew = warp - 4;           // TMEM lane quarter == warp_id % 4
+    const int row = ew * 32 + lane;    // tile row owned by this thread
+    const int etid = threadIdx.x - 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_blocks;
+      const int nb = tile - m_tile * p.n_blocks;
+      int w0 = 0, h0 = 0, n0 = 0;
+      if (p.mode == 1) {
+        const int tw = m_tile % p.tiles_w;
+        const int rest = m_tile / p.tiles_w;
+        const int th = rest % p.tiles_h;
+        w0 = tw * p.bw;
+        h0 = th * p.bh;
+        n0 = (rest / p.tiles_h) * p.bn;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
+      const bool row_valid = row < p.valid_rows;
+
+#pragma unroll 1
+      for (int c64 = 0; c64 < BLOCK_N / 64; ++c64, ++chunk_ctr) {
+        uint8_t* sbuf = sStage + (chunk_ctr & 1) * (kBlockM * 128);
+        if (etid == 0) tma_store_wait_read<1>();  // the store that used this buffer two chunks ago is done
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c64 * 64 + h * 32, r);
+          tmem_ld_wait();
+          if (c64 == BLOCK_N / 64 - 1 && h == 1) {
+            // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          // bf16 pack + swizzled smem write (16 B chunk j of row r lives at chunk j ^ (r & 7))
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+            v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+            v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+            v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+            const int chunk = (h * 4 + j) ^ (row & 7);
+            *reinterpret_cast<uint4*>(sbuf + row * 128 + chunk * 16) = v;
+          }
+          if (kStats) {
+            // column sums over this warp's 32 rows: butterfly transpose-reduce, lane j ends with column j.
+            float s[32], q[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x = row_valid ? __uint_as_float(r[i]) : 0.f;
+              s[i] = x;
+              q[i] = x * x;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send_s = up ? s[i] : s[i + off];
+                const float keep_s = up ? s[i + off] : s[i];
+                s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                const float send_q = up ? q[i] : q[i + off];
+                const float keep_q = up ? q[i + off] : q[i];
+                q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+              }
+            }
+            const int col = c64 * 64 + h * 32 + lane;
+            atomicAdd(&sStat[col], s[0]);
+            atomicAdd(&sStat[BLOCK_N + col], q[0]);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (etid == 0) {
+          const int ccol = nb * BLOCK_N + c64 * 64;
+          if (p.mode == 0)
+            tma_store_2d(&tmD, sbuf, ccol, m_tile * kBlockM);
+          else
+            tma_store_4d(&tmD, sbuf, ccol, w0, h0, n0);
+          tma_store_commit();
+        }
+      }
+      if (kStats) {
+        const int next = tile + gridDim.x;
+        const bool flush = (next >= p.num_tiles) || ((next % p.n_blocks) != nb);
+        if (flush) {
+          named_bar_sync(3, 128);  // all smem atomics of this tile landed
+          for (int i = etid; i < 2 * BLOCK_N; i += 128) {
+            const float v = sStat[i];
+            sStat[i] = 0.f;
+            float* dst = (i < BLOCK_N) ? (p.stat_sum + nb * BLOCK_N + i) : (p.stat_sqsum + nb * BLOCK_N + (i - BLOCK_N));
+            atomicAdd(dst, v);
+          }
+          // the next tile's first named_bar_sync(1) orders the zeroing before new atomics
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (etid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,54 @@
+// Kernel parameter blocks shared by device code and the (torch-facing) host code.
+#pragma once
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kMaxTaps = 16;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+
+struct ConvParams {
+  int mode;      // 0 = flat, 1 = box
+  int taps;      // number of filter taps (1, 9, ...)
+  int kblocks;   // Cin / 64
+  int n_blocks;  // Cout / BLOCK_N
+  int cout;
+  int m_tiles;
+  int num_tiles;   // m_tiles * n_blocks
+  int valid_rows;  // rows of the 128-row tile that hold real pixels (box mode may use < 128)
+  int bw, bh, bn;  // box extents
+  int tiles_w, tiles_h;
+  int8_t tap_map[kMaxTaps];  // which A tensor map the tap reads
+  int8_t tap_dw[kMaxTaps];   // coordinate offsets (in the view's pixel grid)
+  int8_t tap_dh[kMaxTaps];
+  float* stat_sum;    // [Cout] or nullptr
+  float* stat_sqsum;  // [Cout] or nullptr
+};
+
+// Weight-gradient GEMM:  dW[tap][co][ci] += sum_px dY[px, co] * X_tap[px, ci]
+struct WgradParams {
+  int mode;          // 0 = flat (2-D [M, C] maps), 1 = box (4-D NHWC maps)
+  int P;             // pixels per k-iteration (multiple of 16, <= 128)
+  int a_chunks;      // 64-channel chunks of dY per unit (1 if Cout == 64, else 2)
+  int G;             // 64-channel chunks of X per unit (1..6), ordered (ci-block, s)
+  int acc_chunks;    // chunks per accumulator: MMA N = 64 * acc_chunks
+  int S;             // filter width; a unit covers one filter row r (taps r*S .. r*S+S-1)
+  int cb_per_group;  // ci 64-blocks per unit
+  int cgroups;       // (Cin/64) / cb_per_group
+  int groups;        // R * cgroups
+  int co_blocks;     // ceil(Cout / 128)
+  int px_chunks;     // split-K factor over pixels
+  int iters_total;   // number of pixel boxes
+  int iters_per_chunk;
+  int stages;
+  int cout, cin;
+  int bw, bh, bn, tiles_w, tiles_h;
+  int num_units;
+  int8_t tap_map[kMaxTaps];
+  int8_t tap_dw[kMaxTaps];
+  int8_t tap_dh[kMaxTaps];
+  float* dw;  // [taps][Cout][Cin] fp32, accumulated with vector atomics
+};
+
+}  // namespace b200

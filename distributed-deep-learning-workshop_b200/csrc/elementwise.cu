@@ -1,0 +1,649 @@
+// Bandwidth-bound kernels of the image-classifier stack, NHWC bf16, fp32 math.
+// Every kernel moves 16 bytes per thread per access (8 bf16 channels) and is written so one pass does as much
+// as possible: BN-apply+ReLU+residual in one pass; BN-backward = one reduce pass + one apply pass that also
+// emits the masked gradient for the skip connection; softmax-CE forward+backward+accuracy in one kernel.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ops_api.h"
+
+namespace b200 {
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+__device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+__device__ __forceinline__ void ldf8(const float* p, float (&f)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+static inline int grid_for(int64_t work, int threads, int max_blocks = 148 * 16) {
+  int64_t b = (work + threads - 1) / threads;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------------ BN finalize
+// sum/sqsum (accumulated by the conv epilogue or channel_stats) -> mean, invstd, scale, shift; running stats
+// update; the accumulators are zeroed for the next step.
+__global__ void bn_finalize_kernel(float* __restrict__ sum, float* __restrict__ sqsum, float inv_count,
+                                   float unbias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                   float eps, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ scale, float* __restrict__ shift, int C, int training) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float m, var;
+  if (training) {
+    m = sum[c] * inv_count;
+    var = fmaxf(sqsum[c] * inv_count - m * m, 0.f);
+    sum[c] = 0.f;
+    sqsum[c] = 0.f;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
+  } else {
+    m = running_mean[c];
+    var = running_var[c];
+  }
+  float is = rsqrtf(var + eps);
+  mean[c] = m;
+  invstd[c] = is;
+  float sc = gamma[c] * is;
+  scale[c] = sc;
+  shift[c] = beta[c] - m * sc;
+}
+
+void bn_finalize(float* sum, float* sqsum, double count, const float* gamma, const float* beta, float* running_mean,
+                 float* running_var, float momentum, float eps, float* mean, float* invstd, float* scale,
+                 float* shift, int C, bool training, cudaStream_t s) {
+  float unbias = count > 1 ? (float)(count / (count - 1.0)) : 1.f;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum, sqsum, (float)(1.0 / count), unbias, gamma, beta,
+                                                      running_mean, running_var, momentum, eps, mean, invstd, scale,
+                                                      shift, C, training ? 1 : 0);
+}
+
+// ------------------------------------------------------------------------------------------------ BN apply
+// out = [relu]( y*scale + shift  [+ res | + res*res_scale + res_shift] )
+template <bool RELU, int RES>  // RES: 0 none, 1 identity residual, 2 residual with its own BN
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
+                                const float* __restrict__ res_scale, const float* __restrict__ res_shift,
+                                __nv_bfloat16* __restrict__ out, int64_t nvec, int cvec) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cvec) * 8;
+    float f[8], sc[8], sh[8];
+    unpack8(ld8(y + i * 8), f);
+    ldf8(scale + c, sc);
+    ldf8(shift + c, sh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
+    if (RES >= 1) {
+      float r[8];
+      unpack8(ld8(res + i * 8), r);
+      if (RES == 2) {
+        float rs[8], rh[8];
+        ldf8(res_scale + c, rs);
+        ldf8(res_shift + c, rh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = fmaf(r[k], rs[k], rh[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += r[k];
+    }
+    if (RELU) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+    }
+    st8(out + i * 8, pack8(f));
+  }
+}
+
+void bn_apply(const void* y, const float* scale, const float* shift, const void* res, const float* res_scale,
+              const float* res_shift, void* out, int64_t M, int C, bool relu, cudaStream_t s) {
+  const int64_t nvec = M * C / 8;
+  const int cvec = C / 8;
+  const int threads = 256;
+  const int blocks = grid_for(nvec, threads);
+  auto Y = (const __nv_bfloat16*)y;
+  auto R = (const __nv_bfloat16*)res;
+  auto O = (__nv_bfloat16*)out;
+  const int rmode = res == nullptr ? 0 : (res_scale == nullptr ? 1 : 2);
+#define LAUNCH(RL, RM) bn_apply_kernel<RL, RM><<<blocks, threads, 0, s>>>(Y, scale, shift, R, res_scale, res_shift, O, nvec, cvec)
+  if (relu) {
+    if (rmode == 0) LAUNCH(true, 0); else if (rmode == 1) LAUNCH(true, 1); else LAUNCH(true, 2);
+  } else {
+    if (rmode == 0) LAUNCH(false, 0); else if (rmode == 1) LAUNCH(false, 1); else LAUNCH(false, 2);
+  }
+#undef LAUNCH
+}
+
+// ------------------------------------------------------------------------------------------------ channel stats
+// per-channel sum / sum of squares of a [M, C] bf16 matrix (used for convs that do not run our fused epilogue)
+// and the BN-backward reductions  sum(dz), sum(dz*y)  with dz = (g1 [+ g2]) * (out > 0).
+template <int MODE>  // 0: stats of y;  1: bn backward reduce
+__global__ void col_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g2,
+                                  const __nv_bfloat16* __restrict__ outp, const __nv_bfloat16* __restrict__ y,
+                                  float* __restrict__ r0, float* __restrict__ r1, int64_t M, int C) {
+  extern __shared__ float red[];  // [rows_per_block][cvec*8][2]
+  const int cvec = C / 8;
+  const int lanes = cvec < (int)blockDim.x ? cvec : blockDim.x;   // threads along channels
+  const int rpb = blockDim.x / lanes;                             // rows processed concurrently
+  const int cx = threadIdx.x % lanes;
+  const int ry = threadIdx.x / lanes;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s0[k] = s1[k] = 0.f;
+  // a block owns a contiguous strip of rows
+  const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t r_begin = blockIdx.x * rows_per_block;
+  const int64_t r_end = r_begin + rows_per_block < M ? r_begin + rows_per_block : M;
+  if (ry < rpb) {
+    for (int cv = cx; cv < cvec; cv += lanes) {
+      float t0[8], t1[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t0[k] = t1[k] = 0.f;
+      for (int64_t r = r_begin + ry; r < r_end; r += rpb) {
+        const int64_t off = r * C + cv * 8;
+        float f[8];
+        unpack8(ld8(a + off), f);
+        if (MODE == 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            t0[k] += f[k];
+            t1[k] = fmaf(f[k], f[k], t1[k]);
+          }
+        } else {
+          if (g2 != nullptr) {
+            float h[8];
+            unpack8(ld8(g2 + off), h);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += h[k];
+          }
+          if (outp != nullptr) {
+            float o[8];
+            unpack8(ld8(outp + off), o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = o[k] > 0.f ? f[k] : 0.f;
+          }
+          float yy[8];
+          unpack8(ld8(y + off), yy);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            t0[k] += f[k];
+            t1[k] = fmaf(f[k], yy[k], t1[k]);
+          }
+        }
+      }
+      if (cvec <= lanes) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s0[k] = t0[k];
+          s1[k] = t1[k];
+        }
+      } else {
+        // more channel vectors than lanes (never for C <= 2048 with 256 threads); flush directly
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          atomicAdd(r0 + cv * 8 + k, t0[k]);
+          atomicAdd(r1 + cv * 8 + k, t1[k]);
+        }
+      }
+    }
+  }
+  if (cvec <= lanes) {
+    // reduce across the rpb row-lanes through shared memory, then one atomic per channel per block
+    float* sm0 = red;
+    float* sm1 = red + rpb * C;
+    if (ry < rpb) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        sm0[ry * C + cx * 8 + k] = s0[k];
+        sm1[ry * C + cx * 8 + k] = s1[k];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a0 = 0.f, a1 = 0.f;
+      for (int r = 0; r < rpb; ++r) {
+        a0 += sm0[r * C + c];
+        a1 += sm1[r * C + c];
+      }
+      atomicAdd(r0 + c, a0);
+      atomicAdd(r1 + c, a1);
+    }
+  }
+}
+
+static void col_reduce_launch(int mode, const void* a, const void* g2, const void* outp, const void* y, float* r0,
+                              float* r1, int64_t M, int C, cudaStream_t s) {
+  const int threads = 256;
+  int blocks = (int)((M + 63) / 64);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  const int cvec = C / 8;
+  const int lanes = cvec < threads ? cvec : threads;
+  const int rpb = threads / lanes;
+  const size_t smem = (size_t)2 * rpb * C * sizeof(float);
+  if (mode == 0)
+    col_reduce_kernel<0><<<blocks, threads, smem, s>>>((const __nv_bfloat16*)a, nullptr, nullptr, nullptr, r0, r1, M, C);
+  else
+    col_reduce_kernel<1><<<blocks, threads, smem, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)g2,
+                                                       (const __nv_bfloat16*)outp, (const __nv_bfloat16*)y, r0, r1, M, C);
+}
+
+void channel_stats(const void* y, float* sum, float* sqsum, int64_t M, int C, cudaStream_t s) {
+  col_reduce_launch(0, y, nullptr, nullptr, nullptr, sum, sqsum, M, C, s);
+}
+void bn_bwd_reduce(const void* g1, const void* g2, const void* outp, const void* y, float* sum_dz, float* sum_dzy,
+                   int64_t M, int C, cudaStream_t s) {
+  col_reduce_launch(1, g1, g2, outp, y, sum_dz, sum_dzy, M, C, s);
+}
+
+// ------------------------------------------------------------------------------------------------ BN bwd coeffs
+// dy = A*dz + B*y + Cc   with  A = gamma*invstd,  B = -A*invstd*dgamma/M,  Cc = -A*dbeta/M - B*mean
+__global__ void bn_bwd_coeffs_kernel(float* __restrict__ sum_dz, float* __restrict__ sum_dzy,
+                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, float inv_count, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, float* __restrict__ cA, float* __restrict__ cB,
+                                     float* __restrict__ cC, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float db = sum_dz[c];
+  const float dzy = sum_dzy[c];
+  sum_dz[c] = 0.f;
+  sum_dzy[c] = 0.f;
+  const float m = mean[c], is = invstd[c];
+  const float dg = is * (dzy - m * db);
+  dgamma[c] = dg;
+  dbeta[c] = db;
+  const float A = gamma[c] * is;
+  const float B = -A * is * dg * inv_count;
+  cA[c] = A;
+  cB[c] = B;
+  cC[c] = -A * db * inv_count - B * m;
+}
+void bn_bwd_coeffs(float* sum_dz, float* sum_dzy, const float* gamma, const float* mean, const float* invstd,
+                   double count, float* dgamma, float* dbeta, float* cA, float* cB, float* cC, int C,
+                   cudaStream_t s) {
+  bn_bwd_coeffs_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum_dz, sum_dzy, gamma, mean, invstd, (float)(1.0 / count),
+                                                        dgamma, dbeta, cA, cB, cC, C);
+}
+
+// dz = (g1 [+ g2]) * (out > 0);  dy = A*dz + B*y + Cc;  optionally dz is also written (skip-connection grad).
+template <bool HAS_G2, bool HAS_MASK, bool WRITE_DZ>
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
+                                    const __nv_bfloat16* __restrict__ outp, const __nv_bfloat16* __restrict__ y,
+                                    const float* __restrict__ cA, const float* __restrict__ cB,
+                                    const float* __restrict__ cC, __nv_bfloat16* __restrict__ dy,
+                                    __nv_bfloat16* __restrict__ dz, int64_t nvec, int cvec) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cvec) * 8;
+    float g[8], yy[8], A[8], B[8], Cc[8];
+    unpack8(ld8(g1 + i * 8), g);
+    if (HAS_G2) {
+      float h[8];
+      unpack8(ld8(g2 + i * 8), h);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] += h[k];
+    }
+    if (HAS_MASK) {
+      float o[8];
+      unpack8(ld8(outp + i * 8), o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = o[k] > 0.f ? g[k] : 0.f;
+    }
+    if (WRITE_DZ) st8(dz + i * 8, pack8(g));
+    unpack8(ld8(y + i * 8), yy);
+    ldf8(cA + c, A);
+    ldf8(cB + c, B);
+    ldf8(cC + c, Cc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = fmaf(A[k], g[k], fmaf(B[k], yy[k], Cc[k]));
+    st8(dy + i * 8, pack8(g));
+  }
+}
+void bn_bwd_apply(const void* g1, const void* g2, const void* outp, const void* y, const float* cA, const float* cB,
+                  const float* cC, void* dy, void* dz, int64_t M, int C, cudaStream_t s) {
+  const int64_t nvec = M * C / 8;
+  const int cvec = C / 8;
+  const int threads = 256;
+  const int blocks = grid_for(nvec, threads);
+  auto G1 = (const __nv_bfloat16*)g1;
+  auto G2 = (const __nv_bfloat16*)g2;
+  auto O = (const __nv_bfloat16*)outp;
+  auto Y = (const __nv_bfloat16*)y;
+  auto DY = (__nv_bfloat16*)dy;
+  auto DZ = (__nv_bfloat16*)dz;
+#define L(a, b, c) bn_bwd_apply_kernel<a, b, c><<<blocks, threads, 0, s>>>(G1, G2, O, Y, cA, cB, cC, DY, DZ, nvec, cvec)
+  const int key = (g2 ? 4 : 0) | (outp ? 2 : 0) | (dz ? 1 : 0);
+  switch (key) {
+    case 0: L(false, false, false); break;
+    case 1: L(false, false, true); break;
+    case 2: L(false, true, false); break;
+    case 3: L(false, true, true); break;
+    case 4: L(true, false, false); break;
+    case 5: L(true, false, true); break;
+    case 6: L(true, true, false); break;
+    default: L(true, true, true); break;
+  }
+#undef L
+}
+
+// ------------------------------------------------------------------------------------------------ max pool 3x3 s2 p1
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
+                                   int W, int C, int Ho, int Wo) {
+  const int cvec = C / 8;
+  const int64_t total = (int64_t)N * Ho * Wo * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    int64_t p = i / cvec;
+    const int wo = (int)(p % Wo);
+    p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -3.0e38f;
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * ho - 1 + r;
+      if (h < 0 || h >= H) continue;
+      for (int q = 0; q < 3; ++q) {
+        const int w = 2 * wo - 1 + q;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(ld8(x + (((int64_t)n * H + h) * W + w) * C + cv * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+      }
+    }
+    st8(out + i * 8, pack8(m));
+  }
+}
+void maxpool_fwd(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, C,
+                                                          Ho, Wo);
+}
+
+// Backward by gather: input pixel (h, w) receives dout of every window in which it is the FIRST maximum
+// (row-major scan order, torch's tie rule) - no atomics, no saved indices.
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ out,
+                                   const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int N,
+                                   int H, int W, int C, int Ho, int Wo) {
+  const int cvec = C / 8;
+  const int64_t total = (int64_t)N * H * W * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    int64_t p = i / cvec;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H);
+    const int n = (int)(p / H);
+    float xv[8], acc[8];
+    unpack8(ld8(x + i * 8), xv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    // windows (ho, wo) containing (h, w): 2*ho-1 <= h <= 2*ho+1  <=>  ho in [h/2, (h+1)/2]
+    for (int ho = h / 2; ho <= (h + 1) / 2; ++ho) {
+      if (ho < 0 || ho >= Ho) continue;
+      if (h < 2 * ho - 1 || h > 2 * ho + 1) continue;
+      for (int wo = w / 2; wo <= (w + 1) / 2; ++wo) {
+        if (wo < 0 || wo >= Wo) continue;
+        if (w < 2 * wo - 1 || w > 2 * wo + 1) continue;
+        const int64_t oidx = ((((int64_t)n * Ho + ho) * Wo + wo) * C) + cv * 8;
+        float ov[8], gv[8];
+        unpack8(ld8(out + oidx), ov);
+        unpack8(ld8(dout + oidx), gv);
+        // is (h, w) the first max of this window?  count earlier positions that also equal the max
+        bool first[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) first[k] = (xv[k] == ov[k]);
+        for (int r = 0; r < 3; ++r) {
+          const int hh = 2 * ho - 1 + r;
+          if (hh < 0 || hh >= H) continue;
+          for (int q = 0; q < 3; ++q) {
+            const int ww = 2 * wo - 1 + q;
+            if (ww < 0 || ww >= W) continue;
+            if (hh > h || (hh == h && ww >= w)) continue;  // only strictly earlier positions
+            float ev[8];
+            unpack8(ld8(x + (((int64_t)n * H + hh) * W + ww) * C + cv * 8), ev);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) first[k] = first[k] && !(ev[k] == ov[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += first[k] ? gv[k] : 0.f;
+      }
+    }
+    st8(dx + i * 8, pack8(acc));
+  }
+}
+void maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, int N, int H, int W, int C,
+                 cudaStream_t s) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)out,
+                                                          (const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, H, W, C,
+                                                          Ho, Wo);
+}
+
+// ------------------------------------------------------------------------------------------------ global avg pool
+// x [N, HW, C] -> out [N, C]  (optionally with inverted-dropout mask from a counter-based hash RNG)
+__device__ __forceinline__ uint32_t hash_u32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
+__global__ void gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int HW,
+                               int C, float keep_scale, uint32_t keep_thresh, uint32_t seed_lo, uint32_t seed_hi) {
+  const int cvec = C / 8;
+  const int64_t total = (int64_t)N * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    const int n = (int)(i / cvec);
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 0.f;
+    for (int p = 0; p < HW; ++p) {
+      float f[8];
+      unpack8(ld8(x + ((int64_t)n * HW + p) * C + cv * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += f[k];
+    }
+    const float inv = 1.f / HW;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = a[k] * inv;
+      if (keep_thresh != 0xFFFFFFFFu) {
+        const uint32_t r = hash_u32(seed_lo, seed_hi, (uint32_t)(i * 8 + k));
+        v = (r <= keep_thresh) ? v * keep_scale : 0.f;
+      }
+      a[k] = v;
+    }
+    st8(out + i * 8, pack8(a));
+  }
+}
+void gap_fwd(const void* x, void* out, int N, int HW, int C, float drop_p, uint64_t seed, cudaStream_t s) {
+  const int64_t total = (int64_t)N * (C / 8);
+  uint32_t thresh = 0xFFFFFFFFu;
+  float ks = 1.f;
+  if (drop_p > 0.f) {
+    thresh = (uint32_t)((1.0 - (double)drop_p) * 4294967295.0);
+    ks = 1.f / (1.f - drop_p);
+  }
+  gap_fwd_kernel<<<grid_for(total, 128), 128, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, HW, C, ks,
+                                                      thresh, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+__global__ void gap_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int N, int HW,
+                               int C, float keep_scale, uint32_t keep_thresh, uint32_t seed_lo, uint32_t seed_hi) {
+  const int cvec = C / 8;
+  const int64_t total = (int64_t)N * HW * cvec;
+  const float inv = 1.f / HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    const int n = (int)(i / ((int64_t)HW * cvec));
+    const int64_t j = (int64_t)n * cvec + cv;
+    float g[8];
+    unpack8(ld8(dout + j * 8), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = g[k] * inv;
+      if (keep_thresh != 0xFFFFFFFFu) {
+        const uint32_t r = hash_u32(seed_lo, seed_hi, (uint32_t)(j * 8 + k));
+        v = (r <= keep_thresh) ? v * keep_scale : 0.f;
+      }
+      g[k] = v;
+    }
+    st8(dx + i * 8, pack8(g));
+  }
+}
+void gap_bwd(const void* dout, void* dx, int N, int HW, int C, float drop_p, uint64_t seed, cudaStream_t s) {
+  const int64_t total = (int64_t)N * HW * (C / 8);
+  uint32_t thresh = 0xFFFFFFFFu;
+  float ks = 1.f;
+  if (drop_p > 0.f) {
+    thresh = (uint32_t)((1.0 - (double)drop_p) * 4294967295.0);
+    ks = 1.f / (1.f - drop_p);
+  }
+  gap_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, HW, C, ks,
+                                                      thresh, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// ------------------------------------------------------------------------------------------------ softmax CE
+// One warp per row.  logits fp32 [B, K] -> per-row loss, dlogits = (softmax - onehot) * grad_scale,
+// and the running (sum loss, correct count) pair in stats[0..1] via atomics.
+__global__ void softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                  float* __restrict__ dlogits, float* __restrict__ loss_rows,
+                                  float* __restrict__ stats, int B, int K, float grad_scale) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const float* row = logits + (int64_t)warp * K;
+  const int label = (int)labels[warp];
+  float mx = -3.0e38f;
+  int amax = 0;
+  for (int k = lane; k < K; k += 32) {
+    const float v = row[k];
+    if (v > mx) { mx = v; amax = k; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, amax, o);
+    if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
+  }
+  float se = 0.f;
+  for (int k = lane; k < K; k += 32) se += __expf(row[k] - mx);
+  for (int o = 16; o; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+  const float lse = mx + __logf(se);
+  const float inv = 1.f / se;
+  if (dlogits != nullptr) {
+    float* drow = dlogits + (int64_t)warp * K;
+    for (int k = lane; k < K; k += 32) {
+      const float pk = __expf(row[k] - mx) * inv;
+      drow[k] = (pk - (k == label ? 1.f : 0.f)) * grad_scale;
+    }
+  }
+  if (lane == 0) {
+    const float l = lse - row[label];
+    if (loss_rows != nullptr) loss_rows[warp] = l;
+    atomicAdd(stats, l);
+    atomicAdd(stats + 1, amax == label ? 1.f : 0.f);
+  }
+}
+void softmax_ce(const float* logits, const int64_t* labels, float* dlogits, float* loss_rows, float* stats, int B,
+                int K, float grad_scale, cudaStream_t s) {
+  const int threads = 128;
+  const int blocks = (B * 32 + threads - 1) / threads;
+  softmax_ce_kernel<<<blocks, threads, 0, s>>>(logits, labels, dlogits, loss_rows, stats, B, K, grad_scale);
+}
+
+// ------------------------------------------------------------------------------------------------ preprocess
+// uint8 NHWC [N,H,W,3] -> bf16 NHWC [N,H,W,Cpad] with x/127.5 - 1 (MobileNet/Keras "preprocess_input" rule, C13);
+// padded channels are zero so the stem can run as a tensor-core GEMM.
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t npix,
+                                     int cpad, float mul, float add) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* p = x + i * 3;
+    __nv_bfloat16* o = out + i * cpad;
+    o[0] = __float2bfloat16(fmaf((float)p[0], mul, add));
+    o[1] = __float2bfloat16(fmaf((float)p[1], mul, add));
+    o[2] = __float2bfloat16(fmaf((float)p[2], mul, add));
+    for (int c = 3; c < cpad; ++c) o[c] = __float2bfloat16(0.f);
+  }
+}
+void preprocess_u8(const uint8_t* x, void* out, int64_t npix, int cpad, float mul, float add, cudaStream_t s) {
+  preprocess_u8_kernel<<<grid_for(npix, 256), 256, 0, s>>>(x, (__nv_bfloat16*)out, npix, cpad, mul, add);
+}
+
+// Bilinear resize (half-pixel centres, like tf.image.resize) of one uint8 HWC image batch to [N, OH, OW, 3] uint8.
+__global__ void resize_bilinear_u8_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ out, int N, int H,
+                                          int W, int OH, int OW) {
+  const int64_t total = (int64_t)N * OH * OW;
+  const float sy = (float)H / OH, sx = (float)W / OW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % OW);
+    const int oh = (int)((i / OW) % OH);
+    const int n = (int)(i / ((int64_t)OW * OH));
+    float fy = (oh + 0.5f) * sy - 0.5f, fx = (ow + 0.5f) * sx - 0.5f;
+    fy = fminf(fmaxf(fy, 0.f), (float)(H - 1));
+    fx = fminf(fmaxf(fx, 0.f), (float)(W - 1));
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float wy = fy - y0, wx = fx - x0;
+    const uint8_t* b = x + (int64_t)n * H * W * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v00 = b[((int64_t)y0 * W + x0) * 3 + c], v01 = b[((int64_t)y0 * W + x1) * 3 + c];
+      const float v10 = b[((int64_t)y1 * W + x0) * 3 + c], v11 = b[((int64_t)y1 * W + x1) * 3 + c];
+      const float v = (v00 * (1 - wx) + v01 * wx) * (1 - wy) + (v10 * (1 - wx) + v11 * wx) * wy;
+      out[i * 3 + c] = (uint8_t)fminf(fmaxf(v + 0.5f, 0.f), 255.f);
+    }
+  }
+}
+void resize_bilinear_u8(const uint8_t* x, uint8_t* out, int N, int H, int W, int OH, int OW, cudaStream_t s) {
+  resize_bilinear_u8_kernel<<<grid_for((int64_t)N * OH * OW, 256), 256, 0, s>>>(x, out, N, H, W, OH, OW);
+}
+
+// ------------------------------------------------------------------------------------------------ weight layouts
+// fp32 master [taps][Cout][Cin] -> bf16 forward copy (same layout) and bf16 dgrad copy [taps'][Cin][Cout] with the
+// taps reversed (rotated 180 degrees).
+__global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                   __nv_bfloat16* __restrict__ wd, int taps, int cout, int cin) {
+  const int64_t total = (int64_t)taps * cout * cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int co = (int)((i / cin) % cout);
+    const int t = (int)(i / ((int64_t)cin * cout));
+    const __nv_bfloat16 v = __float2bfloat16(w[i]);
+    if (wf != nullptr) wf[i] = v;
+    if (wd != nullptr) wd[((int64_t)(taps - 1 - t) * cin + ci) * cout + co] = v;
+  }
+}
+void weight_prep(const float* w, void* wf, void* wd, int taps, int cout, int cin, cudaStream_t s) {
+  weight_prep_kernel<<<grid_for((int64_t)taps * cout * cin, 256, 148 * 4), 256, 0, s>>>(
+      w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, taps, cout, cin);
+}
+
+}  // namespace b200

@@ -1,0 +1,41 @@
+// Plain (torch-free) launch interface of the bandwidth-bound kernels and fused optimizers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+void bn_finalize(float* sum, float* sqsum, double count, const float* gamma, const float* beta, float* running_mean,
+                 float* running_var, float momentum, float eps, float* mean, float* invstd, float* scale,
+                 float* shift, int C, bool training, cudaStream_t s);
+void bn_apply(const void* y, const float* scale, const float* shift, const void* res, const float* res_scale,
+              const float* res_shift, void* out, int64_t M, int C, bool relu, cudaStream_t s);
+void channel_stats(const void* y, float* sum, float* sqsum, int64_t M, int C, cudaStream_t s);
+void bn_bwd_reduce(const void* g1, const void* g2, const void* outp, const void* y, float* sum_dz, float* sum_dzy,
+                   int64_t M, int C, cudaStream_t s);
+void bn_bwd_coeffs(float* sum_dz, float* sum_dzy, const float* gamma, const float* mean, const float* invstd,
+                   double count, float* dgamma, float* dbeta, float* cA, float* cB, float* cC, int C, cudaStream_t s);
+void bn_bwd_apply(const void* g1, const void* g2, const void* outp, const void* y, const float* cA, const float* cB,
+                  const float* cC, void* dy, void* dz, int64_t M, int C, cudaStream_t s);
+void maxpool_fwd(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s);
+void maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, int N, int H, int W, int C,
+                 cudaStream_t s);
+void gap_fwd(const void* x, void* out, int N, int HW, int C, float drop_p, uint64_t seed, cudaStream_t s);
+void gap_bwd(const void* dout, void* dx, int N, int HW, int C, float drop_p, uint64_t seed, cudaStream_t s);
+void softmax_ce(const float* logits, const int64_t* labels, float* dlogits, float* loss_rows, float* stats, int B,
+                int K, float grad_scale, cudaStream_t s);
+void preprocess_u8(const uint8_t* x, void* out, int64_t npix, int cpad, float mul, float add, cudaStream_t s);
+void resize_bilinear_u8(const uint8_t* x, uint8_t* out, int N, int H, int W, int OH, int OW, cudaStream_t s);
+void weight_prep(const float* w, void* wf, void* wd, int taps, int cout, int cin, cudaStream_t s);
+
+// Fused flat-buffer optimizers.  `hyper` is a DEVICE array (so LR schedules do not invalidate CUDA graphs):
+//   [0] lr  [1] momentum/beta1  [2] beta2/rho  [3] eps  [4] weight_decay  [5] grad_scale  [6] bias_corr1  [7] bias_corr2
+constexpr int kHyperLen = 8;
+void sgd_step(float* p, const float* g, float* mom, void* p16, int64_t n, const float* hyper, bool nesterov,
+              cudaStream_t s);
+void adam_step(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const float* hyper, cudaStream_t s);
+void adadelta_step(float* p, const float* g, float* sq, float* acc, void* p16, int64_t n, const float* hyper,
+                   cudaStream_t s);
+void cast_f32_to_bf16(const float* x, void* out, int64_t n, cudaStream_t s);
+
+}  // namespace b200

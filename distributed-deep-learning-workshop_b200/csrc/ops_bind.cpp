@@ -1,0 +1,201 @@
+// pybind layer for the bandwidth-bound kernels and fused optimizers (tensor checks + raw-pointer dispatch).
+#include <ATen/cuda/CUDAContext.h>
+#include <torch/extension.h>
+
+#include "ops_api.h"
+
+namespace {
+
+using at::Tensor;
+using OptT = c10::optional<at::Tensor>;
+
+int64_t g_launches = 0;  // number of kernels of ours launched through this module (bench.py reports it)
+
+inline cudaStream_t cur() { return at::cuda::getCurrentCUDAStream(); }
+inline void chk(const Tensor& t, at::ScalarType ty, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be CUDA");
+  TORCH_CHECK(t.scalar_type() == ty, name, " has wrong dtype");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+}
+inline const float* fp(const OptT& t) { return t.has_value() ? t->data_ptr<float>() : nullptr; }
+inline const void* vp(const OptT& t) { return t.has_value() ? t->data_ptr() : nullptr; }
+inline void after() {
+  ++g_launches;
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void bn_finalize(Tensor sum, Tensor sqsum, double count, Tensor gamma, Tensor beta, Tensor rmean, Tensor rvar,
+                 double momentum, double eps, Tensor mean, Tensor invstd, Tensor scale, Tensor shift, bool training) {
+  const int C = (int)gamma.numel();
+  for (auto* t : {&sum, &sqsum, &gamma, &beta, &rmean, &rvar, &mean, &invstd, &scale, &shift}) chk(*t, at::kFloat, "bn tensor");
+  b200::bn_finalize(sum.data_ptr<float>(), sqsum.data_ptr<float>(), count, gamma.data_ptr<float>(),
+                    beta.data_ptr<float>(), rmean.data_ptr<float>(), rvar.data_ptr<float>(), (float)momentum,
+                    (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(), scale.data_ptr<float>(),
+                    shift.data_ptr<float>(), C, training, cur());
+  after();
+}
+
+void bn_apply(Tensor y, Tensor scale, Tensor shift, OptT res, OptT res_scale, OptT res_shift, Tensor out, bool relu) {
+  chk(y, at::kBFloat16, "y");
+  chk(out, at::kBFloat16, "out");
+  const int C = (int)y.size(-1);
+  const int64_t M = y.numel() / C;
+  TORCH_CHECK(C % 8 == 0 && scale.numel() == C && shift.numel() == C && out.numel() == y.numel());
+  if (res.has_value()) { chk(*res, at::kBFloat16, "res"); TORCH_CHECK(res->numel() == y.numel()); }
+  b200::bn_apply(y.data_ptr(), scale.data_ptr<float>(), shift.data_ptr<float>(), vp(res), fp(res_scale),
+                 fp(res_shift), out.data_ptr(), M, C, relu, cur());
+  after();
+}
+
+void channel_stats(Tensor y, Tensor sum, Tensor sqsum) {
+  chk(y, at::kBFloat16, "y");
+  const int C = (int)y.size(-1);
+  TORCH_CHECK(C % 8 == 0 && C <= 2048);
+  b200::channel_stats(y.data_ptr(), sum.data_ptr<float>(), sqsum.data_ptr<float>(), y.numel() / C, C, cur());
+  after();
+}
+
+void bn_bwd_reduce(Tensor g1, OptT g2, OptT outp, Tensor y, Tensor sum_dz, Tensor sum_dzy) {
+  chk(g1, at::kBFloat16, "g1");
+  chk(y, at::kBFloat16, "y");
+  const int C = (int)y.size(-1);
+  TORCH_CHECK(C % 8 == 0 && C <= 2048 && g1.numel() == y.numel());
+  b200::bn_bwd_reduce(g1.data_ptr(), vp(g2), vp(outp), y.data_ptr(), sum_dz.data_ptr<float>(),
+                      sum_dzy.data_ptr<float>(), y.numel() / C, C, cur());
+  after();
+}
+
+void bn_bwd_coeffs(Tensor sum_dz, Tensor sum_dzy, Tensor gamma, Tensor mean, Tensor invstd, double count,
+                   Tensor dgamma, Tensor dbeta, Tensor cA, Tensor cB, Tensor cC) {
+  const int C = (int)gamma.numel();
+  b200::bn_bwd_coeffs(sum_dz.data_ptr<float>(), sum_dzy.data_ptr<float>(), gamma.data_ptr<float>(),
+                      mean.data_ptr<float>(), invstd.data_ptr<float>(), count, dgamma.data_ptr<float>(),
+                      dbeta.data_ptr<float>(), cA.data_ptr<float>(), cB.data_ptr<float>(), cC.data_ptr<float>(), C,
+                      cur());
+  after();
+}
+
+void bn_bwd_apply(Tensor g1, OptT g2, OptT outp, Tensor y, Tensor cA, Tensor cB, Tensor cC, Tensor dy, OptT dz) {
+  chk(g1, at::kBFloat16, "g1");
+  chk(y, at::kBFloat16, "y");
+  chk(dy, at::kBFloat16, "dy");
+  const int C = (int)y.size(-1);
+  b200::bn_bwd_apply(g1.data_ptr(), vp(g2), vp(outp), y.data_ptr(), cA.data_ptr<float>(), cB.data_ptr<float>(),
+                     cC.data_ptr<float>(), dy.data_ptr(), dz.has_value() ? dz->data_ptr() : nullptr, y.numel() / C, C,
+                     cur());
+  after();
+}
+
+void maxpool_fwd(Tensor x, Tensor out) {
+  chk(x, at::kBFloat16, "x");
+  chk(out, at::kBFloat16, "out");
+  b200::maxpool_fwd(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2), (int)x.size(3), cur());
+  after();
+}
+void maxpool_bwd(Tensor x, Tensor out, Tensor dout, Tensor dx) {
+  chk(x, at::kBFloat16, "x");
+  chk(dout, at::kBFloat16, "dout");
+  b200::maxpool_bwd(x.data_ptr(), out.data_ptr(), dout.data_ptr(), dx.data_ptr(), (int)x.size(0), (int)x.size(1),
+                    (int)x.size(2), (int)x.size(3), cur());
+  after();
+}
+void gap_fwd(Tensor x, Tensor out, double drop_p, int64_t seed) {
+  chk(x, at::kBFloat16, "x");
+  chk(out, at::kBFloat16, "out");
+  const int N = (int)x.size(0), C = (int)x.size(-1);
+  b200::gap_fwd(x.data_ptr(), out.data_ptr(), N, (int)(x.numel() / N / C), C, (float)drop_p, (uint64_t)seed, cur());
+  after();
+}
+void gap_bwd(Tensor dout, Tensor dx, double drop_p, int64_t seed) {
+  chk(dout, at::kBFloat16, "dout");
+  chk(dx, at::kBFloat16, "dx");
+  const int N = (int)dx.size(0), C = (int)dx.size(-1);
+  b200::gap_bwd(dout.data_ptr(), dx.data_ptr(), N, (int)(dx.numel() / N / C), C, (float)drop_p, (uint64_t)seed, cur());
+  after();
+}
+void softmax_ce(Tensor logits, Tensor labels, OptT dlogits, OptT loss_rows, Tensor stats, double grad_scale) {
+  chk(logits, at::kFloat, "logits");
+  chk(labels, at::kLong, "labels");
+  chk(stats, at::kFloat, "stats");
+  b200::softmax_ce(logits.data_ptr<float>(), labels.data_ptr<int64_t>(),
+                   dlogits.has_value() ? dlogits->data_ptr<float>() : nullptr,
+                   loss_rows.has_value() ? loss_rows->data_ptr<float>() : nullptr, stats.data_ptr<float>(),
+                   (int)logits.size(0), (int)logits.size(1), (float)grad_scale, cur());
+  after();
+}
+void preprocess_u8(Tensor x, Tensor out, double mul, double add) {
+  chk(x, at::kByte, "x");
+  chk(out, at::kBFloat16, "out");
+  TORCH_CHECK(x.size(-1) == 3);
+  b200::preprocess_u8(x.data_ptr<uint8_t>(), out.data_ptr(), x.numel() / 3, (int)out.size(-1), (float)mul, (float)add, cur());
+  after();
+}
+void resize_bilinear_u8(Tensor x, Tensor out) {
+  chk(x, at::kByte, "x");
+  chk(out, at::kByte, "out");
+  b200::resize_bilinear_u8(x.data_ptr<uint8_t>(), out.data_ptr<uint8_t>(), (int)x.size(0), (int)x.size(1),
+                           (int)x.size(2), (int)out.size(1), (int)out.size(2), cur());
+  after();
+}
+void weight_prep(Tensor w, OptT wf, OptT wd, int64_t taps, int64_t cout, int64_t cin) {
+  chk(w, at::kFloat, "w");
+  TORCH_CHECK(w.numel() == taps * cout * cin);
+  b200::weight_prep(w.data_ptr<float>(), wf.has_value() ? wf->data_ptr() : nullptr,
+                    wd.has_value() ? wd->data_ptr() : nullptr, (int)taps, (int)cout, (int)cin, cur());
+  after();
+}
+void sgd_step(Tensor p, Tensor g, Tensor mom, OptT p16, Tensor hyper, bool nesterov) {
+  chk(p, at::kFloat, "p"); chk(g, at::kFloat, "g"); chk(mom, at::kFloat, "mom"); chk(hyper, at::kFloat, "hyper");
+  TORCH_CHECK(p.numel() % 4 == 0 && g.numel() == p.numel() && mom.numel() == p.numel() && hyper.numel() >= b200::kHyperLen);
+  b200::sgd_step(p.data_ptr<float>(), g.data_ptr<float>(), mom.data_ptr<float>(),
+                 p16.has_value() ? p16->data_ptr() : nullptr, p.numel(), hyper.data_ptr<float>(), nesterov, cur());
+  after();
+}
+void adam_step(Tensor p, Tensor g, Tensor m, Tensor v, OptT p16, Tensor hyper) {
+  chk(p, at::kFloat, "p"); chk(g, at::kFloat, "g"); chk(m, at::kFloat, "m"); chk(v, at::kFloat, "v");
+  TORCH_CHECK(p.numel() % 4 == 0 && g.numel() == p.numel() && hyper.numel() >= b200::kHyperLen);
+  b200::adam_step(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
+                  p16.has_value() ? p16->data_ptr() : nullptr, p.numel(), hyper.data_ptr<float>(), cur());
+  after();
+}
+void adadelta_step(Tensor p, Tensor g, Tensor sq, Tensor acc, OptT p16, Tensor hyper) {
+  chk(p, at::kFloat, "p"); chk(g, at::kFloat, "g");
+  TORCH_CHECK(p.numel() % 4 == 0 && g.numel() == p.numel() && hyper.numel() >= b200::kHyperLen);
+  b200::adadelta_step(p.data_ptr<float>(), g.data_ptr<float>(), sq.data_ptr<float>(), acc.data_ptr<float>(),
+                      p16.has_value() ? p16->data_ptr() : nullptr, p.numel(), hyper.data_ptr<float>(), cur());
+  after();
+}
+void cast_bf16(Tensor x, Tensor out) {
+  chk(x, at::kFloat, "x"); chk(out, at::kBFloat16, "out");
+  TORCH_CHECK(x.numel() % 4 == 0 && out.numel() == x.numel());
+  b200::cast_f32_to_bf16(x.data_ptr<float>(), out.data_ptr(), x.numel(), cur());
+  after();
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  namespace py = pybind11;
+  m.doc() = "b200ddl bandwidth-bound sm_100a kernels and fused optimizers";
+  m.def("bn_finalize", &bn_finalize);
+  m.def("bn_apply", &bn_apply, py::arg("y"), py::arg("scale"), py::arg("shift"), py::arg("res") = c10::nullopt,
+        py::arg("res_scale") = c10::nullopt, py::arg("res_shift") = c10::nullopt, py::arg("out"), py::arg("relu") = true);
+  m.def("channel_stats", &channel_stats);
+  m.def("bn_bwd_reduce", &bn_bwd_reduce);
+  m.def("bn_bwd_coeffs", &bn_bwd_coeffs);
+  m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("maxpool_fwd", &maxpool_fwd);
+  m.def("maxpool_bwd", &maxpool_bwd);
+  m.def("gap_fwd", &gap_fwd);
+  m.def("gap_bwd", &gap_bwd);
+  m.def("softmax_ce", &softmax_ce);
+  m.def("preprocess_u8", &preprocess_u8);
+  m.def("resize_bilinear_u8", &resize_bilinear_u8);
+  m.def("weight_prep", &weight_prep);
+  m.def("sgd_step", &sgd_step);
+  m.def("adam_step", &adam_step);
+  m.def("adadelta_step", &adadelta_step);
+  m.def("cast_bf16", &cast_bf16);
+  m.def("launch_count", [] { return g_launches; });
+  m.def("reset_launch_count", [] { g_launches = 0; });
+}

@@ -1,0 +1,229 @@
+"""Planning layer of the tcgen05 implicit-GEMM convolution (kernels: csrc/conv_igemm.cuh, csrc/conv_wgrad.cu).
+
+A convolution on NHWC bf16 tensors is described to the kernels as
+  * 1..4 *views* of the input that share one pixel grid (for stride 2 these are the four parity sub-grids
+    ``x[:, ph::2, pw::2, :]`` - plain strided views, no copies),
+  * a *tap table*: for every filter tap the view it reads and the pixel offset inside that view,
+  * a pixel *box* (bw, bh, bn) with bw*bh*bn <= 128 that tiles the output exactly (or "flat" for dense 1x1).
+Zero padding is the TMA out-of-bounds fill.  The reference delegates all of this to TF/cuDNN.
+"""
+from __future__ import annotations
+
+import weakref
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _build
+
+_plans: "weakref.WeakSet" = weakref.WeakSet()
+_retired_launches = 0
+
+
+def plan_launches() -> int:
+    return _retired_launches + sum(int(p.launches) for p in list(_plans))
+
+
+def _divisors(n: int) -> List[int]:
+    return [d for d in range(1, n + 1) if n % d == 0]
+
+
+def pick_box(n: int, h: int, w: int, rows: int = 128, multiple_of: int = 1) -> Tuple[int, int, int]:
+    """Largest pixel box (bw, bh, bn) <= rows that tiles an (n, h, w) grid exactly.
+
+    Preference: most pixels, then widest along W (longer contiguous runs for TMA), then H."""
+    best = None
+    for bw in _divisors(w):
+        if bw > rows:
+            continue
+        for bh in _divisors(h):
+            if bw * bh > rows:
+                continue
+            for bn in _divisors(n):
+                p = bw * bh * bn
+                if p > rows or p % multiple_of:
+                    continue
+                key = (p, bw, bh)
+                if best is None or key > best[0]:
+                    best = (key, (bw, bh, bn))
+    if best is None:
+        raise ValueError(f"no pixel box for grid {(n, h, w)} rows<={rows} multiple_of={multiple_of}")
+    return best[1]
+
+
+@dataclass
+class TapTable:
+    views: List[torch.Tensor]
+    tap_map: List[int]
+    tap_dw: List[int]
+    tap_dh: List[int]
+
+
+def make_taps(x: torch.Tensor, R: int, S: int, stride: int, pad: int) -> TapTable:
+    """Views + tap table for a forward conv / wgrad over NHWC ``x`` (N, H, W, C)."""
+    if stride == 1:
+        tm, dw, dh = [], [], []
+        for r in range(R):
+            for s in range(S):
+                tm.append(0)
+                dw.append(s - pad)
+                dh.append(r - pad)
+        return TapTable([x], tm, dw, dh)
+    if stride != 2:
+        raise ValueError("stride must be 1 or 2")
+    N, H, W, C = x.shape
+    if H % 2 or W % 2:
+        raise ValueError("stride-2 convs need even H and W")
+    used = {}
+    views: List[torch.Tensor] = []
+    tm, dw, dh = [], [], []
+    for r in range(R):
+        for s in range(S):
+            oh, ow = r - pad, s - pad
+            ph, pw = oh % 2, ow % 2
+            key = (ph, pw)
+            if key not in used:
+                used[key] = len(views)
+                views.append(x[:, ph::2, pw::2, :])
+            tm.append(used[key])
+            dh.append((oh - ph) // 2)
+            dw.append((ow - pw) // 2)
+    return TapTable(views, tm, dw, dh)
+
+
+class ConvForward:
+    """y = conv(x, w) [+ per-channel sum / sum-of-squares of y for BatchNorm] on the tensor cores.
+
+    ``w`` is the bf16 filter in kernel layout ``[R*S*Cout, Cin]`` (tap-major)."""
+
+    def __init__(self, x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, R: int, S: int, stride: int = 1,
+                 pad: int = 0, stat_sum: Optional[torch.Tensor] = None, stat_sqsum: Optional[torch.Tensor] = None,
+                 max_ctas: int = 0):
+        ext = _build.load("_b200_conv")
+        taps = make_taps(x, R, S, stride, pad)
+        N, Ho, Wo, _ = y.shape
+        flat = (R == 1 and S == 1 and stride == 1 and pad == 0 and x.is_contiguous() and y.is_contiguous())
+        if flat:
+            bw = bh = bn = 0
+        else:
+            bw, bh, bn = pick_box(N, Ho, Wo)
+        self.box = (bw, bh, bn)
+        self.plan = ext.ConvPlan(taps.views, w, y, taps.tap_map, taps.tap_dw, taps.tap_dh, bw, bh, bn,
+                                 stat_sum, stat_sqsum, max_ctas)
+        _plans.add(self.plan)
+
+    def run(self) -> None:
+        self.plan.run()
+
+
+class ConvDgrad:
+    """dx = conv_transpose(dy, w) for the same geometry, as one or more forward-style implicit GEMMs.
+
+    ``w_master`` is the fp32 (or bf16) filter ``[R*S, Cout, Cin]``; the transposed/rotated bf16 copies the kernel
+    needs are (re)built by :meth:`refresh_weights` (cheap: filters are tiny next to activations)."""
+
+    def __init__(self, dy: torch.Tensor, w_master: torch.Tensor, dx: torch.Tensor, R: int, S: int, stride: int = 1,
+                 pad: int = 0, max_ctas: int = 0):
+        ext = _build.load("_b200_conv")
+        self.R, self.S, self.stride, self.pad = R, S, stride, pad
+        self.w_master = w_master
+        taps_total, cout, cin = w_master.shape
+        assert taps_total == R * S
+        self.parts = []  # (plan, weight buffer, tap index list)
+        self.needs_zero = False
+        self.dx = dx
+        N, Ho, Wo, _ = dy.shape
+        if stride == 1:
+            # dx[h] = sum_r dy[h + pad - r] w[r]  -> forward conv with taps reversed and pad' = R-1-pad
+            idx = [r * S + s for r in range(R) for s in range(S)]
+            tm, dw, dh = [], [], []
+            for r in range(R):
+                for s in range(S):
+                    tm.append(0)
+                    dh.append(pad - r)
+                    dw.append(pad - s)
+            wbuf = torch.empty(len(idx) * cin, cout, dtype=torch.bfloat16, device=dy.device)
+            flat = (R == 1 and S == 1 and pad == 0 and dy.is_contiguous() and dx.is_contiguous())
+            box = (0, 0, 0) if flat else pick_box(N, dx.shape[1], dx.shape[2])
+            plan = ext.ConvPlan([dy], wbuf, dx, tm, dw, dh, box[0], box[1], box[2], None, None, max_ctas)
+            _plans.add(plan)
+            self.parts.append((plan, wbuf, idx))
+        else:
+            # output parity classes: dx[2i+ph, 2j+pw] = sum_{taps with (r-pad)%2==ph, (s-pad)%2==pw} dy[i-dh, j-dw] w[r,s]
+            for ph in range(2):
+                for pw in range(2):
+                    idx, tm, dw, dh = [], [], [], []
+                    for r in range(R):
+                        for s in range(S):
+                            oh, ow = r - pad, s - pad
+                            if oh % 2 == ph and ow % 2 == pw:
+                                idx.append(r * S + s)
+                                tm.append(0)
+                                dh.append(-((oh - ph) // 2))
+                                dw.append(-((ow - pw) // 2))
+                    out_view = dx[:, ph::2, pw::2, :]
+                    if not idx:
+                        self.needs_zero = True
+                        continue
+                    wbuf = torch.empty(len(idx) * cin, cout, dtype=torch.bfloat16, device=dy.device)
+                    box = pick_box(N, out_view.shape[1], out_view.shape[2])
+                    plan = ext.ConvPlan([dy], wbuf, out_view, tm, dw, dh, box[0], box[1], box[2], None, None, max_ctas)
+                    _plans.add(plan)
+                    self.parts.append((plan, wbuf, idx))
+        self.refresh_weights()
+
+    def refresh_weights(self) -> None:
+        w = self.w_master
+        for _, wbuf, idx in self.parts:
+            sel = w[idx] if len(idx) != w.shape[0] or idx != list(range(w.shape[0])) else w
+            # [t, Cout, Cin] -> [t, Cin, Cout]
+            wbuf.view(len(idx), w.shape[2], w.shape[1]).copy_(sel.transpose(1, 2))
+
+    def run(self) -> None:
+        if self.needs_zero:
+            self.dx.zero_()
+        for plan, _, _ in self.parts:
+            plan.run()
+
+
+class ConvWgrad:
+    """dw[t, co, ci] += sum_px dy[px, co] * x_t[px, ci]  (fp32 accumulation with vector atomics; zero dw first)."""
+
+    def __init__(self, dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, R: int, S: int, stride: int = 1,
+                 pad: int = 0, px_chunks: int = 0, max_ctas: int = 0):
+        ext = _build.load("_b200_conv")
+        taps = make_taps(x, R, S, stride, pad)
+        N, Ho, Wo, _ = dy.shape
+        flat = (R == 1 and S == 1 and stride == 1 and pad == 0 and x.is_contiguous() and dy.is_contiguous()
+                and (N * Ho * Wo) % 64 == 0)
+        if flat:
+            bw = bh = bn = 0
+        else:
+            bw, bh, bn = pick_box(N, Ho, Wo, rows=128, multiple_of=16)
+        self.box = (bw, bh, bn)
+        self.plan = ext.WgradPlan(dy, taps.views, dw, R, S, taps.tap_map, taps.tap_dw, taps.tap_dh, bw, bh, bn,
+                                  px_chunks, max_ctas)
+        _plans.add(self.plan)
+
+    def run(self) -> None:
+        self.plan.run()
+
+
+# ------------------------------------------------------------------------------------------- references (tests)
+def weight_to_kernel_layout(w_oihw: torch.Tensor) -> torch.Tensor:
+    """torch [Cout, Cin, R, S] -> kernel layout [R*S, Cout, Cin]."""
+    co, ci, R, S = w_oihw.shape
+    return w_oihw.permute(2, 3, 0, 1).reshape(R * S, co, ci).contiguous()
+
+
+def weight_from_kernel_layout(w_tck: torch.Tensor, R: int, S: int) -> torch.Tensor:
+    t, co, ci = w_tck.shape
+    return w_tck.view(R, S, co, ci).permute(2, 3, 0, 1).contiguous()
+
+
+def conv_reference(x_nhwc: torch.Tensor, w_tck: torch.Tensor, R: int, S: int, stride: int, pad: int) -> torch.Tensor:
+    """fp32 reference of the forward conv (NHWC in, NHWC out)."""
+    w = weight_from_kernel_layout(w_tck.float(), R, S)
+    y = torch.nn.functional.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w, stride=stride, padding=pad)
+    return y.permute(0, 2, 3, 1).contiguous()
