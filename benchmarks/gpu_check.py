@@ -324,12 +324,89 @@ def case_conv_time():
     return True
 
 
+def case_engine():
+    """ResNet-50 engine forward/backward vs torchvision (same weights, fp32 reference and bf16-autocast reference)."""
+    import torchvision
+    from b200ddl.models.resnet_engine import ResNet50Engine, EngineTrainStep
+    from b200ddl import optim
+
+    ok = True
+    N, K = 32, 10
+    eng = ResNet50Engine(batch=N, num_classes=K, zero_init_residual=False, seed=1)
+    opt = optim.SGD(learning_rate=0.1, momentum=0.9)
+    step = EngineTrainStep(eng, opt, use_graph=False)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randint(0, 256, (N, 224, 224, 3), device=DEV, dtype=torch.uint8, generator=g)
+    y = torch.randint(0, K, (N,), device=DEV, generator=g)
+    eng.set_input(x, y)
+    ref = torchvision.models.resnet50(weights=None, num_classes=K).to(DEV)
+    ref.load_state_dict({k: v.to(DEV) for k, v in eng.state_dict().items()}, strict=False)
+    ref.train()
+    xin = (x.permute(0, 3, 1, 2).float() / 127.5 - 1.0)
+    eng.forward(training=True)
+    eng.backward()
+    torch.cuda.synchronize()
+    loss_e, acc_e = eng.loss_and_acc()
+    out = ref(xin)
+    loss_r = torch.nn.functional.cross_entropy(out, y)
+    loss_r.backward()
+    ok &= report("engine/loss_vs_fp32", abs(loss_e - loss_r.item()) / abs(loss_r.item()), 3e-2, f"engine={loss_e:.4f} ref={loss_r.item():.4f}")
+    ok &= report("engine/logits_vs_fp32", rel_err(eng.logits, out), 8e-2)
+    ref16 = torchvision.models.resnet50(weights=None, num_classes=K).to(DEV)
+    ref16.load_state_dict({k: v.to(DEV) for k, v in eng.state_dict().items()}, strict=False)
+    ref16.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out16 = ref16(xin)
+    loss16 = torch.nn.functional.cross_entropy(out16.float(), y)
+    loss16.backward()
+    print(f"INFO torch-bf16-autocast loss={loss16.item():.4f} logits_err_vs_fp32={rel_err(out16, out):.3e}", flush=True)
+    pr = dict(ref.named_parameters())
+    p16 = dict(ref16.named_parameters())
+    import math
+    for name in ["fc.weight", "fc.bias", "layer4.2.conv3.weight", "layer4.2.bn3.weight", "layer4.0.downsample.0.weight",
+                 "layer3.0.conv2.weight", "layer2.0.conv2.weight", "layer2.1.conv1.weight", "layer1.0.conv1.weight",
+                 "layer1.0.conv2.weight", "layer1.0.bn1.bias", "bn1.weight", "conv1.weight"]:
+        ge = eng.g(name).detach().float()
+        if name.endswith("conv1.weight") or "conv" in name or "downsample.0" in name:
+            k = int(round(math.sqrt(ge.shape[0])))
+            ge = C.weight_from_kernel_layout(ge, k, k)
+        gr = pr[name].grad.float()
+        g16 = p16[name].grad.float()
+        cos = torch.nn.functional.cosine_similarity(ge.flatten(), gr.flatten(), dim=0).item()
+        cos16 = torch.nn.functional.cosine_similarity(g16.flatten(), gr.flatten(), dim=0).item()
+        nr = (ge.norm() / (gr.norm() + 1e-12)).item()
+        ok &= report(f"engine/grad_cos/{name}", 1.0 - cos, 3e-2, f"norm_ratio={nr:.3f} torch_bf16_cos_gap={1-cos16:.2e}")
+    # running stats
+    rm = dict(ref.named_buffers())
+    ok &= report("engine/running_mean/bn1", rel_err(eng.running_mean["bn1"], rm["bn1.running_mean"]), 3e-2)
+    ok &= report("engine/running_var/layer3.0.bn2", rel_err(eng.running_var["layer3.0.bn2"], rm["layer3.0.bn2.running_var"]), 5e-2)
+    # a few optimisation steps must reduce the loss on a fixed batch (graph path)
+    eng2 = ResNet50Engine(batch=N, num_classes=K, seed=2)
+    step2 = EngineTrainStep(eng2, optim.SGD(learning_rate=0.05, momentum=0.9), use_graph=True)
+    losses = []
+    for i in range(12):
+        step2.load(x, y)
+        step2.run()
+        losses.append(step2.result()[0])
+    print("INFO graph-step losses", " ".join(f"{l:.3f}" for l in losses), flush=True)
+    ok &= report("engine/loss_decreases", float(losses[-1] >= losses[0]), 0.0, f"{losses[0]:.3f}->{losses[-1]:.3f}")
+    ok &= report("engine/loss_finite", float(not all(l == l and abs(l) < 1e4 for l in losses)), 0.0)
+    # eval-mode forward runs and is finite
+    from b200ddl.models.resnet_engine import EngineEvalStep
+    ev = EngineEvalStep(eng2)
+    ev.run()
+    le, ae = ev.result()
+    ok &= report("engine/eval_finite", float(not (le == le and le < 1e4)), 0.0, f"eval loss={le:.3f} acc={ae:.3f}")
+    return ok
+
+
 CASES = {
     "conv_fwd": case_conv_fwd,
     "conv_dgrad": case_conv_dgrad,
     "conv_wgrad": case_conv_wgrad,
     "elementwise": case_elementwise,
     "conv_time": case_conv_time,
+    "engine": case_engine,
 }
 
 if __name__ == "__main__":

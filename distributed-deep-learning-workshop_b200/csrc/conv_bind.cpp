@@ -88,8 +88,10 @@ struct ConvPlan {
       raw.tmD = map_2d(out.data_ptr(), M, cout, cout, 64, kBlockM);
     } else {
       TORCH_CHECK(bw * bh * bn <= kBlockM && bw * bh * bn >= 8, "box must hold 8..128 pixels");
-      TORCH_CHECK(Wo % bw == 0 && Ho % bh == 0 && N % bn == 0, "box must tile the output exactly: out ", N, "x", Ho,
-                  "x", Wo, " box ", bn, "x", bh, "x", bw);
+      // W and H must tile exactly (a partial spatial box would pick up halo pixels); the image dimension may
+      // overhang: out-of-range images are zero-filled on load and clipped on store.
+      TORCH_CHECK(Wo % bw == 0 && Ho % bh == 0, "box must tile the output plane exactly: out ", N, "x", Ho, "x", Wo,
+                  " box ", bn, "x", bh, "x", bw);
       p.mode = 1;
       p.bw = (int)bw;
       p.bh = (int)bh;
@@ -97,7 +99,7 @@ struct ConvPlan {
       p.valid_rows = (int)(bw * bh * bn);
       p.tiles_w = (int)(Wo / bw);
       p.tiles_h = (int)(Ho / bh);
-      p.m_tiles = (int)(p.tiles_w * p.tiles_h * (N / bn));
+      p.m_tiles = (int)(p.tiles_w * p.tiles_h * ((N + bn - 1) / bn));
       for (size_t i = 0; i < 4; ++i) {
         const at::Tensor& v = views[i < views.size() ? i : 0];
         TORCH_CHECK(v.size(0) == N && v.size(3) == cin);
@@ -190,7 +192,7 @@ struct WgradPlan {
     } else {
       const int64_t P = bw * bh * bn;
       TORCH_CHECK(P % 16 == 0 && P <= 128, "wgrad pixel box must hold a multiple of 16 pixels (<= 128), got ", P);
-      TORCH_CHECK(Wo % bw == 0 && Ho % bh == 0 && N % bn == 0, "box must tile dy exactly");
+      TORCH_CHECK(Wo % bw == 0 && Ho % bh == 0, "box must tile the dy plane exactly");
       p.mode = 1;
       p.P = (int)P;
       p.bw = (int)bw;
@@ -198,7 +200,7 @@ struct WgradPlan {
       p.bn = (int)bn;
       p.tiles_w = (int)(Wo / bw);
       p.tiles_h = (int)(Ho / bh);
-      p.iters_total = (int)(p.tiles_w * p.tiles_h * (N / bn));
+      p.iters_total = (int)(p.tiles_w * p.tiles_h * ((N + bn - 1) / bn));
       raw.tmDY = map_nhwc(dy, 64, (int)bw, (int)bh, (int)bn);
       for (size_t i = 0; i < 4; ++i) {
         const at::Tensor& v = views[i < views.size() ? i : 0];

@@ -12,8 +12,9 @@
 // * Warp-specialised, persistent: warp0 = TMA producer, warp1 = tcgen05.mma issuer, warp2 = TMEM allocator,
 //   warps4-7 = epilogue (tcgen05.ld -> bf16 -> swizzled smem -> TMA store), double-buffered TMEM accumulator
 //   so the epilogue of tile i overlaps the main loop of tile i+1.
-// * Optional fused BatchNorm statistics: per-output-channel sum and sum-of-squares of the fp32 accumulators
-//   are reduced in the epilogue (warp butterfly -> smem -> one global atomic per channel per CTA), which removes
+// * Optional fused BatchNorm statistics: per-output-channel sum and sum-of-squares of the bf16 output tile
+//   are reduced in the epilogue (staged smem tile -> per-CTA smem accumulators -> one global atomic per channel per
+//   CTA), which removes
 //   the separate statistics pass over the conv output.
 #pragma once
 #include "conv_params.h"
@@ -184,7 +185,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
-      const bool row_valid = row < p.valid_rows;
 
 #pragma unroll 1
       for (int c64 = 0; c64 < BLOCK_N / 64; ++c64, ++chunk_ctr) {
@@ -213,32 +213,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             const int chunk = (h * 4 + j) ^ (row & 7);
             *reinterpret_cast<uint4*>(sbuf + row * 128 + chunk * 16) = v;
           }
-          if (kStats) {
-            // column sums over this warp's 32 rows: butterfly transpose-reduce, lane j ends with column j.
-            float s[32], q[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = row_valid ? __uint_as_float(r[i]) : 0.f;
-              s[i] = x;
-              q[i] = x * x;
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-              const bool up = (lane & off) != 0;
-#pragma unroll
-              for (int i = 0; i < off; ++i) {
-                const float send_s = up ? s[i] : s[i + off];
-                const float keep_s = up ? s[i + off] : s[i];
-                s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-                const float send_q = up ? q[i] : q[i + off];
-                const float keep_q = up ? q[i + off] : q[i];
-                q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-              }
-            }
-            const int col = c64 * 64 + h * 32 + lane;
-            atomicAdd(&sStat[col], s[0]);
-            atomicAdd(&sStat[BLOCK_N + col], q[0]);
-          }
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
@@ -249,6 +223,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           else
             tma_store_4d(&tmD, sbuf, ccol, w0, h0, n0);
           tma_store_commit();
+        }
+        if (kStats) {
+          // Column statistics from the bf16 tile that was just staged (exactly the values BatchNorm will read):
+          // thread = (column pair cp, 32-row group rg); one conflict-free LDS.32 per row, no shuffles.
+          const int cp = etid & 31;
+          const int rg = etid >> 5;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const int r_end = min(rg * 32 + 32, p.valid_rows);
+#pragma unroll 8
+          for (int r = rg * 32; r < r_end; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+            s0 += f.x;
+            s1 += f.y;
+            q0 = fmaf(f.x, f.x, q0);
+            q1 = fmaf(f.y, f.y, q1);
+          }
+          const int col = c64 * 64 + cp * 2;
+          atomicAdd(&sStat[col], s0);
+          atomicAdd(&sStat[col + 1], s1);
+          atomicAdd(&sStat[BLOCK_N + col], q0);
+          atomicAdd(&sStat[BLOCK_N + col + 1], q1);
         }
       }
       if (kStats) {

@@ -58,14 +58,14 @@ __global__ void bn_finalize_kernel(float* __restrict__ sum, float* __restrict__ 
   if (training) {
     m = sum[c] * inv_count;
     var = fmaxf(sqsum[c] * inv_count - m * m, 0.f);
-    sum[c] = 0.f;
-    sqsum[c] = 0.f;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
   } else {
     m = running_mean[c];
     var = running_var[c];
   }
+  sum[c] = 0.f;  // the conv epilogue accumulates into these in both modes
+  sqsum[c] = 0.f;
   float is = rsqrtf(var + eps);
   mean[c] = m;
   invstd[c] = is;
@@ -627,8 +627,8 @@ void resize_bilinear_u8(const uint8_t* x, uint8_t* out, int N, int H, int W, int
 }
 
 // ------------------------------------------------------------------------------------------------ weight layouts
-// fp32 master [taps][Cout][Cin] -> bf16 forward copy (same layout) and bf16 dgrad copy [taps'][Cin][Cout] with the
-// taps reversed (rotated 180 degrees).
+// fp32 master [taps][Cout][Cin] -> bf16 forward copy (same layout) and bf16 dgrad copy [taps][Cin][Cout]
+// (per-tap transpose; the dgrad plan pairs tap t with the mirrored pixel offset).
 __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                    __nv_bfloat16* __restrict__ wd, int taps, int cout, int cin) {
   const int64_t total = (int64_t)taps * cout * cin;
@@ -638,7 +638,7 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int t = (int)(i / ((int64_t)cin * cout));
     const __nv_bfloat16 v = __float2bfloat16(w[i]);
     if (wf != nullptr) wf[i] = v;
-    if (wd != nullptr) wd[((int64_t)(taps - 1 - t) * cin + ci) * cout + co] = v;
+    if (wd != nullptr) wd[((int64_t)t * cin + ci) * cout + co] = v;
   }
 }
 void weight_prep(const float* w, void* wf, void* wd, int taps, int cout, int cin, cudaStream_t s) {

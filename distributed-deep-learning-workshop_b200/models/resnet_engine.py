@@ -1,0 +1,613 @@
+"""ResNet-50 as a hand-scheduled B200 engine (the TARGET model of BASELINE.json; reference model = C14).
+
+No autograd and no tracing compiler: forward and backward are explicit sequences of our sm_100a kernels over
+*static* NHWC bf16 buffers, so the whole training step is one CUDA graph.
+
+  conv            tcgen05/TMEM/TMA implicit GEMM (ops.conv.ConvForward) with the BatchNorm statistics reduced in
+                  the epilogue
+  BN+ReLU(+add)   one bandwidth-bound pass (bn_apply); backward = reduce pass + apply pass (also emits the masked
+                  skip-connection gradient)
+  dgrad / wgrad   the same implicit-GEMM kernel with transposed filters / the MN-major wgrad kernel accumulating
+                  fp32 straight into the flat gradient buffer the all-reduce consumes
+  optimizer       one fused launch over the flat fp32 master / state buffers (see optim.fused)
+
+Parameters live in ONE flat fp32 buffer laid out in *backward completion order*, so gradient buckets become
+ready front-to-back and `DistributedOptimizer` can all-reduce bucket k while bucket k+1 is still being computed.
+Conv filters use the kernel layout ``[R*S, Cout, Cin]``; `state_dict()` converts to torch's OIHW.
+
+Reference call sites this replaces: `build_model` (P1/03:159-178), `model.fit` inner step (P1/03:353-358).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from .. import ops
+from ..ops import conv as C
+
+
+@dataclass
+class ParamSpec:
+    name: str
+    shape: Tuple[int, ...]
+    kind: str  # 'conv' | 'gamma' | 'beta' | 'fc_w' | 'fc_b'
+    offset: int = 0
+    numel: int = 0
+
+
+@dataclass
+class ConvSpec:
+    name: str
+    cin: int
+    cout: int
+    k: int
+    stride: int
+    pad: int
+
+
+@dataclass
+class BlockSpec:
+    name: str
+    cin: int
+    mid: int
+    stride: int
+    downsample: bool
+    h_in: int
+    h_out: int
+
+
+def _align(n: int, a: int = 64) -> int:
+    return (n + a - 1) // a * a
+
+
+def resnet50_blocks(image_size: int = 224) -> List[BlockSpec]:
+    cfg = [(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)]
+    blocks = []
+    cin = 64
+    h = image_size // 4
+    for si, (mid, n, stride) in enumerate(cfg):
+        for bi in range(n):
+            s = stride if bi == 0 else 1
+            blocks.append(BlockSpec(f"layer{si + 1}.{bi}", cin, mid, s, bi == 0, h, h // s))
+            h //= s
+            cin = mid * 4
+    return blocks
+
+
+class ResNet50Engine:
+    """Static-shape ResNet-50 training / inference engine for one GPU."""
+
+    arch = "resnet50"
+
+    def __init__(self, batch: int, num_classes: int = 1000, device: Optional[torch.device] = None,
+                 image_size: int = 224, dropout: float = 0.0, bn_momentum: float = 0.1, bn_eps: float = 1e-5,
+                 seed: int = 0, max_ctas: int = 0, zero_init_residual: bool = True):
+        ops.require_native()
+        self.zero_init_residual = zero_init_residual
+        if image_size % 32:
+            raise ValueError("image_size must be a multiple of 32")
+        self.batch = int(batch)
+        self.num_classes = int(num_classes)
+        self.image_size = int(image_size)
+        self.dropout = float(dropout)
+        self.bn_momentum = bn_momentum
+        self.bn_eps = bn_eps
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.max_ctas = int(max_ctas)
+        self.seed = seed
+        self.blocks = resnet50_blocks(image_size)
+        self._e = ops.ext("_b200_ops")
+        self._built = False
+        self.grad_hook: Optional[Callable[[int, int], None]] = None  # called with flat [lo, hi) when grads are final
+        self._step_count = 0
+        self._layout_params()
+        self._alloc_params(seed)
+
+    # ------------------------------------------------------------------------------------------------ parameters
+    def _layout_params(self) -> None:
+        specs: List[ParamSpec] = []
+
+        def conv(name, cin, cout, k):
+            specs.append(ParamSpec(name + ".weight", (k * k, cout, cin), "conv"))
+
+        def bn(name, c):
+            specs.append(ParamSpec(name + ".weight", (c,), "gamma"))
+            specs.append(ParamSpec(name + ".bias", (c,), "beta"))
+
+        # backward completion order: fc, blocks reversed (bn3, [bn_ds], conv3, bn2, conv2, bn1, conv1, [conv_ds]), stem
+        specs.append(ParamSpec("fc.weight", (self.num_classes, 2048), "fc_w"))
+        specs.append(ParamSpec("fc.bias", (self.num_classes,), "fc_b"))
+        for b in reversed(self.blocks):
+            bn(b.name + ".bn3", b.mid * 4)
+            if b.downsample:
+                bn(b.name + ".downsample.1", b.mid * 4)
+            conv(b.name + ".conv3", b.mid, b.mid * 4, 1)
+            bn(b.name + ".bn2", b.mid)
+            conv(b.name + ".conv2", b.mid, b.mid, 3)
+            bn(b.name + ".bn1", b.mid)
+            conv(b.name + ".conv1", b.cin, b.mid, 1)
+            if b.downsample:
+                conv(b.name + ".downsample.0", b.cin, b.mid * 4, 1)
+        bn("bn1", 64)
+        specs.append(ParamSpec("conv1.weight", (49, 64, 3), "conv"))
+        off = 0
+        for s in specs:
+            s.numel = int(math.prod(s.shape))
+            s.offset = off
+            off += _align(s.numel)
+        self.param_specs = specs
+        self.spec = {s.name: s for s in specs}
+        self.flat_numel = off
+
+    def _alloc_params(self, seed: int) -> None:
+        dev = self.device
+        self.params = torch.zeros(self.flat_numel, device=dev, dtype=torch.float32)
+        self.w16 = torch.zeros(self.flat_numel, device=dev, dtype=torch.bfloat16)
+        self.grads: Optional[torch.Tensor] = None  # bound later (may be symmetric memory)
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for s in self.param_specs:
+            v = self.params[s.offset:s.offset + s.numel].view(s.shape)
+            if s.kind == "conv":
+                taps, cout, cin = s.shape
+                std = math.sqrt(2.0 / (cout * taps))  # kaiming normal, fan_out (torchvision)
+                v.copy_(torch.randn(s.shape, generator=g) * std)
+            elif s.kind == "gamma":
+                # zero-init the last BN of every residual branch (Goyal et al., cited by the reference P1/03:315)
+                v.fill_(0.0 if (self.zero_init_residual and s.name.endswith("bn3.weight")) else 1.0)
+            elif s.kind == "fc_w":
+                bound = 1.0 / math.sqrt(2048)
+                v.copy_((torch.rand(s.shape, generator=g) * 2 - 1) * bound)
+            elif s.kind == "fc_b":
+                bound = 1.0 / math.sqrt(2048)
+                v.copy_((torch.rand(s.shape, generator=g) * 2 - 1) * bound)
+        # running statistics (not optimised): one flat buffer, mean then var per BN
+        self.bn_names = [s.name[:-len(".weight")] for s in self.param_specs if s.kind == "gamma"]
+        self.bn_channels = {n: self.spec[n + ".weight"].numel for n in self.bn_names}
+        tot = sum(self.bn_channels.values())
+        self.running = torch.zeros(2 * tot, device=dev)
+        self.running_mean: Dict[str, torch.Tensor] = {}
+        self.running_var: Dict[str, torch.Tensor] = {}
+        o = 0
+        for n in self.bn_names:
+            c = self.bn_channels[n]
+            self.running_mean[n] = self.running[o:o + c]
+            self.running_var[n] = self.running[tot + o:tot + o + c]
+            o += c
+        self.running[tot:].fill_(1.0)
+        self.sync_weights()
+
+    def p(self, name: str) -> torch.Tensor:
+        s = self.spec[name]
+        return self.params[s.offset:s.offset + s.numel].view(s.shape)
+
+    def g(self, name: str) -> torch.Tensor:
+        s = self.spec[name]
+        return self.grads[s.offset:s.offset + s.numel].view(s.shape)
+
+    def w16v(self, name: str) -> torch.Tensor:
+        s = self.spec[name]
+        return self.w16[s.offset:s.offset + s.numel].view(s.shape)
+
+    def sync_weights(self) -> None:
+        """Refresh every bf16 working copy from the fp32 master (after an optimizer step or a weight load)."""
+        self._e.cast_bf16(self.params, self.w16)
+        if self._built:
+            for d in self._dgrads:
+                d.refresh_weights()
+            self._stem_w.copy_(self._stem_oihw_from_flat())
+
+    def _stem_oihw_from_flat(self) -> torch.Tensor:
+        return self.p("conv1.weight").view(7, 7, 64, 3).permute(2, 3, 0, 1)
+
+    # ------------------------------------------------------------------------------------------------ build
+    def bind_grad_buffer(self, grads: Optional[torch.Tensor] = None) -> None:
+        if grads is None:
+            grads = torch.zeros(self.flat_numel, device=self.device, dtype=torch.float32)
+        assert grads.numel() >= self.flat_numel and grads.dtype == torch.float32
+        self.grads = grads
+
+    def build(self, training: bool = True) -> "ResNet50Engine":
+        """Allocate activations / scratch and encode every TMA descriptor (once; buffers are static)."""
+        if self._built:
+            return self
+        if self.grads is None and training:
+            self.bind_grad_buffer()
+        dev, N, e = self.device, self.batch, self._e
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        f32 = dict(device=dev, dtype=torch.float32)
+        S = self.image_size
+        self.x_u8 = torch.zeros(N, S, S, 3, device=dev, dtype=torch.uint8)
+        self.labels = torch.zeros(N, device=dev, dtype=torch.int64)
+        self.x16 = torch.zeros(N, S, S, 3, **bf)
+        self.stats = torch.zeros(2, **f32)          # [sum loss, correct]
+        self.logits = torch.zeros(N, self.num_classes, **f32)
+        self.dlogits = torch.zeros(N, self.num_classes, **f32)
+        self.loss_rows = torch.zeros(N, **f32)
+
+        # BN work buffers (per BN): sum, sqsum, mean, invstd, scale, shift, sum_dz, sum_dzy, cA, cB, cC
+        self.bnw: Dict[str, Dict[str, torch.Tensor]] = {}
+        for n in self.bn_names:
+            c = self.bn_channels[n]
+            buf = torch.zeros(11, c, **f32)
+            keys = ["sum", "sqsum", "mean", "invstd", "scale", "shift", "sum_dz", "sum_dzy", "cA", "cB", "cC"]
+            self.bnw[n] = {k: buf[i] for i, k in enumerate(keys)}
+
+        H0 = S // 2
+        self.y0 = torch.zeros(N, H0, H0, 64, **bf)
+        self.a0 = torch.zeros(N, H0, H0, 64, **bf)
+        self.p0 = torch.zeros(N, H0 // 2, H0 // 2, 64, **bf)
+        self._stem_w = torch.zeros(64, 3, 7, 7, **bf).contiguous(memory_format=torch.channels_last)
+        self._stem_w.copy_(self._stem_oihw_from_flat())
+
+        max_act = N * (S // 4) * (S // 4) * 256
+        max_act = max(max_act, N * H0 * H0 * 64)
+        if training:
+            self._scr = {k: torch.zeros(max_act, **bf) for k in ("dy", "da", "dds", "dzA", "dzB")}
+
+        self.act: Dict[str, torch.Tensor] = {}
+        self._fwd: Dict[str, C.ConvForward] = {}
+        self._dg: Dict[str, C.ConvDgrad] = {}
+        self._wg: Dict[str, C.ConvWgrad] = {}
+        self._dgrads: List[C.ConvDgrad] = []
+        mc = self.max_ctas
+
+        def scr(key, shape):
+            n = int(math.prod(shape))
+            return self._scr[key][:n].view(shape)
+
+        x_in = self.p0
+        for b in self.blocks:
+            Hi, Ho, mid, cout = b.h_in, b.h_out, b.mid, b.mid * 4
+            A = self.act
+            A[b.name + ".y1"] = torch.zeros(N, Hi, Hi, mid, **bf)
+            A[b.name + ".a1"] = torch.zeros(N, Hi, Hi, mid, **bf)
+            A[b.name + ".y2"] = torch.zeros(N, Ho, Ho, mid, **bf)
+            A[b.name + ".a2"] = torch.zeros(N, Ho, Ho, mid, **bf)
+            A[b.name + ".y3"] = torch.zeros(N, Ho, Ho, cout, **bf)
+            A[b.name + ".out"] = torch.zeros(N, Ho, Ho, cout, **bf)
+            if b.downsample:
+                A[b.name + ".yd"] = torch.zeros(N, Ho, Ho, cout, **bf)
+            convs = [("conv1", x_in, "y1", "bn1", 1, 1, 0), ("conv2", A[b.name + ".a1"], "y2", "bn2", 3, b.stride, 1),
+                     ("conv3", A[b.name + ".a2"], "y3", "bn3", 1, 1, 0)]
+            if b.downsample:
+                convs.append(("downsample.0", x_in, "yd", "downsample.1", 1, b.stride, 0))
+            for cname, xin, yk, bnk, k, stride, pad in convs:
+                full = b.name + "." + cname
+                w = self.w16v(full + ".weight")
+                w2d = w.view(w.shape[0] * w.shape[1], w.shape[2])
+                bw_ = self.bnw[b.name + "." + bnk]
+                y = A[b.name + "." + yk]
+                self._fwd[full] = C.ConvForward(xin, w2d, y, k, k, stride, pad, bw_["sum"], bw_["sqsum"], mc)
+                if training:
+                    dy = scr("dy", y.shape)
+                    gw = self.g(full + ".weight")
+                    self._wg[full] = C.ConvWgrad(dy, xin, gw.view(gw.shape[0] * gw.shape[1], gw.shape[2]), k, k,
+                                                 stride, pad, 0, mc)
+                    dx = scr("dds" if cname == "downsample.0" else "da", xin.shape)
+                    dgr = C.ConvDgrad(dy, self.p(full + ".weight"), dx, k, k, stride, pad, mc)
+                    self._dg[full] = dgr
+                    self._dgrads.append(dgr)
+            x_in = A[b.name + ".out"]
+        self.feat = x_in  # [N, 7, 7, 2048]
+        self.pooled = torch.zeros(N, 2048, **bf)
+        if training:
+            self.dpooled = torch.zeros(N, 2048, **bf)
+        self._training_built = training
+        self._built = True
+        self.sync_weights()
+        return self
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def _bn_fwd(self, bn: str, count: float, training: bool) -> Dict[str, torch.Tensor]:
+        w = self.bnw[bn]
+        self._e.bn_finalize(w["sum"], w["sqsum"], float(count), self.p(bn + ".weight"), self.p(bn + ".bias"),
+                            self.running_mean[bn], self.running_var[bn], self.bn_momentum, self.bn_eps, w["mean"],
+                            w["invstd"], w["scale"], w["shift"], training)
+        return w
+
+    def forward(self, training: bool = True) -> None:
+        """x_u8 / labels (static inputs) -> logits, loss stats.  All launches go to the current stream."""
+        e, N, A = self._e, self.batch, self.act
+        e.preprocess_u8(self.x_u8, self.x16, 1.0 / 127.5, -1.0)
+        # stem: 7x7/2 conv, 3 input channels (library conv; K=147 is below the TMA 16-byte channel granule)
+        y0 = torch.nn.functional.conv2d(self.x16.permute(0, 3, 1, 2), self._stem_w, stride=2, padding=3)
+        self.y0.copy_(y0.permute(0, 2, 3, 1))
+        w0 = self.bnw["bn1"]
+        e.channel_stats(self.y0, w0["sum"], w0["sqsum"])
+        cnt0 = N * self.y0.shape[1] * self.y0.shape[2]
+        self._bn_fwd("bn1", cnt0, training)
+        e.bn_apply(self.y0, w0["scale"], w0["shift"], None, None, None, self.a0, True)
+        e.maxpool_fwd(self.a0, self.p0)
+        x_in = self.p0
+        for b in self.blocks:
+            n = b.name
+            cnt_in = N * b.h_in * b.h_in
+            cnt_out = N * b.h_out * b.h_out
+            self._fwd[n + ".conv1"].run()
+            w1 = self._bn_fwd(n + ".bn1", cnt_in, training)
+            e.bn_apply(A[n + ".y1"], w1["scale"], w1["shift"], None, None, None, A[n + ".a1"], True)
+            self._fwd[n + ".conv2"].run()
+            w2 = self._bn_fwd(n + ".bn2", cnt_out, training)
+            e.bn_apply(A[n + ".y2"], w2["scale"], w2["shift"], None, None, None, A[n + ".a2"], True)
+            self._fwd[n + ".conv3"].run()
+            w3 = self._bn_fwd(n + ".bn3", cnt_out, training)
+            if b.downsample:
+                self._fwd[n + ".downsample.0"].run()
+                wd = self._bn_fwd(n + ".downsample.1", cnt_out, training)
+                e.bn_apply(A[n + ".y3"], w3["scale"], w3["shift"], A[n + ".yd"], wd["scale"], wd["shift"],
+                           A[n + ".out"], True)
+            else:
+                e.bn_apply(A[n + ".y3"], w3["scale"], w3["shift"], x_in, None, None, A[n + ".out"], True)
+            x_in = A[n + ".out"]
+        drop = self.dropout if training else 0.0
+        self._drop_seed = self.seed * 1000003 + self._step_count
+        e.gap_fwd(self.feat, self.pooled, drop, self._drop_seed)
+        wfc = self.w16v("fc.weight")
+        self.logits.copy_(torch.nn.functional.linear(self.pooled, wfc).float() + self.p("fc.bias"))
+        self.stats.zero_()
+        e.softmax_ce(self.logits, self.labels, self.dlogits if training else None, self.loss_rows, self.stats,
+                     1.0 / N)
+
+    # ------------------------------------------------------------------------------------------------ backward
+    def _ready(self, *names: str) -> None:
+        if self.grad_hook is None:
+            return
+        lo = min(self.spec[n].offset for n in names)
+        hi = max(self.spec[n].offset + _align(self.spec[n].numel) for n in names)
+        self.grad_hook(lo, hi)
+
+    def _bn_bwd(self, bn: str, g1, g2, mask, y, dy, dz, count: float) -> None:
+        e, w = self._e, self.bnw[bn]
+        e.bn_bwd_reduce(g1, g2, mask, y, w["sum_dz"], w["sum_dzy"])
+        e.bn_bwd_coeffs(w["sum_dz"], w["sum_dzy"], self.p(bn + ".weight"), w["mean"], w["invstd"], float(count),
+                        self.g(bn + ".weight"), self.g(bn + ".bias"), w["cA"], w["cB"], w["cC"])
+        e.bn_bwd_apply(g1, g2, mask, y, w["cA"], w["cB"], w["cC"], dy, dz)
+        self._ready(bn + ".weight", bn + ".bias")
+
+    def backward(self) -> None:
+        """dlogits -> every parameter gradient (fp32, written into the flat gradient buffer)."""
+        e, N, A = self._e, self.batch, self.act
+        self.grads.zero_()  # wgrad accumulates with atomics
+        # classifier head
+        dl16 = self.dlogits.to(torch.bfloat16)
+        torch.matmul(self.dlogits.t(), self.pooled.float(), out=self.g("fc.weight"))
+        torch.sum(self.dlogits, dim=0, out=self.g("fc.bias"))
+        self._ready("fc.weight", "fc.bias")
+        torch.matmul(dl16, self.w16v("fc.weight"), out=self.dpooled)
+        drop = self.dropout
+        gshape = self.feat.shape
+        g1 = self._scr["da"][:self.feat.numel()].view(gshape)
+        e.gap_bwd(self.dpooled, g1, drop, self._drop_seed)
+        g2 = None
+        dz_keys = ["dzA", "dzB"]
+        for bi in range(len(self.blocks) - 1, -1, -1):
+            b = self.blocks[bi]
+            n = b.name
+            x_in = A[self.blocks[bi - 1].name + ".out"] if bi > 0 else self.p0
+            cnt_in = N * b.h_in * b.h_in
+            cnt_out = N * b.h_out * b.h_out
+            y3, out = A[n + ".y3"], A[n + ".out"]
+            dy3 = self._scr["dy"][:y3.numel()].view(y3.shape)
+            dz = self._scr[dz_keys[bi % 2]][:y3.numel()].view(y3.shape)
+            self._bn_bwd(n + ".bn3", g1, g2, out, y3, dy3, dz, cnt_out)
+            self._wg[n + ".conv3"].run()
+            self._ready(n + ".conv3.weight")
+            self._dg[n + ".conv3"].run()  # -> da (a2-shaped)
+            da2 = self._scr["da"][:A[n + ".a2"].numel()].view(A[n + ".a2"].shape)
+            y2, a2 = A[n + ".y2"], A[n + ".a2"]
+            dy2 = self._scr["dy"][:y2.numel()].view(y2.shape)
+            self._bn_bwd(n + ".bn2", da2, None, a2, y2, dy2, None, cnt_out)
+            self._wg[n + ".conv2"].run()
+            self._ready(n + ".conv2.weight")
+            self._dg[n + ".conv2"].run()  # -> da (a1-shaped)
+            y1, a1 = A[n + ".y1"], A[n + ".a1"]
+            da1 = self._scr["da"][:a1.numel()].view(a1.shape)
+            dy1 = self._scr["dy"][:y1.numel()].view(y1.shape)
+            self._bn_bwd(n + ".bn1", da1, None, a1, y1, dy1, None, cnt_in)
+            self._wg[n + ".conv1"].run()
+            self._ready(n + ".conv1.weight")
+            self._dg[n + ".conv1"].run()  # -> da (x_in-shaped): main-path gradient of the block input
+            g1 = self._scr["da"][:x_in.numel()].view(x_in.shape)
+            if b.downsample:
+                # the downsample branch receives the same masked gradient dz; its BN has no ReLU
+                yd = A[n + ".yd"]
+                dyd = self._scr["dy"][:yd.numel()].view(yd.shape)
+                self._bn_bwd(n + ".downsample.1", dz, None, None, yd, dyd, None, cnt_out)
+                self._wg[n + ".downsample.0"].run()
+                self._ready(n + ".downsample.0.weight")
+                self._dg[n + ".downsample.0"].run()  # -> dds (x_in-shaped)
+                g2 = self._scr["dds"][:x_in.numel()].view(x_in.shape)
+            else:
+                g2 = dz
+        # stem
+        gsum = torch.add(g1, g2, out=g1)
+        da0 = self._scr["dy"][:self.a0.numel()].view(self.a0.shape)
+        e.maxpool_bwd(self.a0, self.p0, gsum, da0)
+        dy0 = self._scr["dzA"][:self.y0.numel()].view(self.y0.shape)
+        cnt0 = N * self.y0.shape[1] * self.y0.shape[2]
+        self._bn_bwd("bn1", da0, None, self.a0, self.y0, dy0, None, cnt0)
+        gw = torch.nn.grad.conv2d_weight(self.x16.permute(0, 3, 1, 2), (64, 3, 7, 7), dy0.permute(0, 3, 1, 2),
+                                         stride=2, padding=3)
+        self.g("conv1.weight").view(7, 7, 64, 3).copy_(gw.permute(2, 3, 0, 1))
+        self._ready("conv1.weight")
+
+    # ------------------------------------------------------------------------------------------------ utilities
+    def set_input(self, x_u8: torch.Tensor, labels: Optional[torch.Tensor] = None) -> None:
+        self.x_u8.copy_(x_u8.view(self.x_u8.shape), non_blocking=True)
+        if labels is not None:
+            self.labels.copy_(labels, non_blocking=True)
+
+    def loss_and_acc(self) -> Tuple[float, float]:
+        s = self.stats.tolist()
+        return s[0] / self.batch, s[1] / self.batch
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """torch / torchvision-compatible names and layouts (conv OIHW)."""
+        sd = {}
+        for s in self.param_specs:
+            v = self.p(s.name).detach().clone()
+            if s.kind == "conv":
+                k = int(round(math.sqrt(s.shape[0])))
+                v = C.weight_from_kernel_layout(v, k, k)
+            sd[s.name] = v.cpu()
+        for n in self.bn_names:
+            sd[n + ".running_mean"] = self.running_mean[n].detach().clone().cpu()
+            sd[n + ".running_var"] = self.running_var[n].detach().clone().cpu()
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        for s in self.param_specs:
+            v = sd[s.name].to(self.device, torch.float32)
+            if s.kind == "conv":
+                v = C.weight_to_kernel_layout(v)
+            self.p(s.name).copy_(v)
+        for n in self.bn_names:
+            if n + ".running_mean" in sd:
+                self.running_mean[n].copy_(sd[n + ".running_mean"])
+                self.running_var[n].copy_(sd[n + ".running_var"])
+        self.sync_weights()
+
+    def num_parameters(self) -> int:
+        return sum(s.numel for s in self.param_specs)
+
+
+class EngineTrainStep:
+    """forward + backward + (distributed) optimizer update of a `ResNet50Engine`, captured as ONE CUDA graph.
+
+    ``optimizer`` is a `b200ddl.optim` flat optimizer or a `b200ddl.parallel.DistributedOptimizer` around one.
+    Usage per step::
+
+        step.load(x_u8, labels)   # H2D / D2D into the static input buffers (outside the graph)
+        step.run()                # graph replay (or eager launches when use_graph=False)
+        loss, acc = step.result() # D2H of the two fp32 statistics
+    """
+
+    def __init__(self, engine: ResNet50Engine, optimizer, use_graph: bool = True, warmup_steps: int = 2):
+        self.engine = engine
+        self.optimizer = optimizer
+        self.use_graph = use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._dist = hasattr(optimizer, "on_grads_ready")
+        e = engine
+        ranges = [(s.offset, s.offset + _align(s.numel)) for s in e.param_specs]
+        if self._dist:
+            grads = optimizer.allocate_grads(e.flat_numel, e.device)
+            e.bind_grad_buffer(grads)
+            optimizer.attach(e.params, ranges, e.w16, grads)
+            e.grad_hook = optimizer.on_grads_ready
+        else:
+            e.bind_grad_buffer()
+            optimizer.attach(e.params, e.grads, e.w16)
+        e.build(training=True)
+        self._warmup_steps = warmup_steps
+        self._host_stats = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.steps = 0
+        self._captured = False
+
+    # one full step as a launch sequence on the current stream
+    def _launch(self) -> None:
+        e, opt = self.engine, self.optimizer
+        if self._dist:
+            opt.start_backward()
+        e.forward(training=True)
+        e.backward()
+        opt.step()  # distributed: waits for the comm stream first
+        for d in e._dgrads:
+            d.refresh_weights()
+        e._stem_w.copy_(e._stem_oihw_from_flat())
+
+    def capture(self) -> None:
+        self._captured = True
+        e = self.engine
+        # snapshot: warm-up steps must not change the model
+        p0 = e.params.clone()
+        r0 = e.running.clone()
+        st0 = {k: v.clone() for k, v in self._opt_state().items()}
+        s = torch.cuda.Stream(device=e.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(self._warmup_steps):
+                self._launch()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if self.use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._launch()
+            torch.cuda.synchronize()
+        e.params.copy_(p0)
+        e.running.copy_(r0)
+        for k, v in self._opt_state().items():
+            v.copy_(st0[k])
+        e.sync_weights()
+        torch.cuda.synchronize()
+
+    def _opt_state(self):
+        o = self.optimizer.opt if self._dist else self.optimizer
+        return o.state
+
+    def load(self, x_u8: torch.Tensor, labels: torch.Tensor) -> None:
+        self.engine.set_input(x_u8, labels)
+
+    def run(self) -> None:
+        if not self._captured:
+            self.capture()
+        self.optimizer.begin_step()
+        self.engine._step_count += 1
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch()
+        self.steps += 1
+
+    def result_async(self) -> torch.Tensor:
+        """Enqueue the D2H copy of [sum loss, correct]; valid after the stream is synchronised."""
+        self._host_stats.copy_(self.engine.stats, non_blocking=True)
+        return self._host_stats
+
+    def result(self) -> Tuple[float, float]:
+        self.result_async()
+        torch.cuda.current_stream().synchronize()
+        b = self.engine.batch
+        return float(self._host_stats[0]) / b, float(self._host_stats[1]) / b
+
+
+class EngineEvalStep:
+    """Inference / validation forward of a `ResNet50Engine` (BN folded to running statistics), CUDA-graphed."""
+
+    def __init__(self, engine: ResNet50Engine, use_graph: bool = True):
+        self.engine = engine
+        self.use_graph = use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        engine.build(training=engine.grads is not None)
+        self._host_stats = torch.zeros(2, dtype=torch.float32).pin_memory()
+
+    def capture(self) -> None:
+        e = self.engine
+        s = torch.cuda.Stream(device=e.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            e.forward(training=False)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            e.forward(training=False)
+        torch.cuda.synchronize()
+
+    def run(self) -> None:
+        if self.use_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+        else:
+            self.engine.forward(training=False)
+
+    def result(self) -> Tuple[float, float]:
+        self._host_stats.copy_(self.engine.stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        b = self.engine.batch
+        return float(self._host_stats[0]) / b, float(self._host_stats[1]) / b

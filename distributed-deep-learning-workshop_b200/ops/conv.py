@@ -30,9 +30,10 @@ def _divisors(n: int) -> List[int]:
 
 
 def pick_box(n: int, h: int, w: int, rows: int = 128, multiple_of: int = 1) -> Tuple[int, int, int]:
-    """Largest pixel box (bw, bh, bn) <= rows that tiles an (n, h, w) grid exactly.
+    """Pixel box (bw, bh, bn) with bw*bh*bn <= rows.  bw | w and bh | h exactly (a partial spatial box would pull in
+    halo pixels); bn may overhang n (out-of-range images are zero-filled by TMA and clipped on store).
 
-    Preference: most pixels, then widest along W (longer contiguous runs for TMA), then H."""
+    Preference: least padded work, then most pixels per box, then widest along W."""
     best = None
     for bw in _divisors(w):
         if bw > rows:
@@ -40,11 +41,14 @@ def pick_box(n: int, h: int, w: int, rows: int = 128, multiple_of: int = 1) -> T
         for bh in _divisors(h):
             if bw * bh > rows:
                 continue
-            for bn in _divisors(n):
+            for bn in range(1, rows // (bw * bh) + 1):
                 p = bw * bh * bn
-                if p > rows or p % multiple_of:
+                if p % multiple_of:
                     continue
-                key = (p, bw, bh)
+                tiles_n = -(-n // bn)
+                waste = tiles_n * bn - n                      # zero-filled images
+                mma_rows = tiles_n * (w // bw) * (h // bh)    # 128-row MMA tiles issued
+                key = (-mma_rows, -waste, p, bw, bh)
                 if best is None or key > best[0]:
                     best = (key, (bw, bh, bn))
     if best is None:
@@ -175,10 +179,14 @@ class ConvDgrad:
 
     def refresh_weights(self) -> None:
         w = self.w_master
+        full = list(range(w.shape[0]))
         for _, wbuf, idx in self.parts:
-            sel = w[idx] if len(idx) != w.shape[0] or idx != list(range(w.shape[0])) else w
-            # [t, Cout, Cin] -> [t, Cin, Cout]
-            wbuf.view(len(idx), w.shape[2], w.shape[1]).copy_(sel.transpose(1, 2))
+            if idx == full and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous():
+                # one kernel: fp32 [t, Cout, Cin] -> bf16 [t, Cin, Cout]
+                _build.load("_b200_ops").weight_prep(w, None, wbuf, w.shape[0], w.shape[1], w.shape[2])
+            else:
+                sel = w[idx]
+                wbuf.view(len(idx), w.shape[2], w.shape[1]).copy_(sel.transpose(1, 2))
 
     def run(self) -> None:
         if self.needs_zero:
@@ -200,7 +208,13 @@ class ConvWgrad:
         if flat:
             bw = bh = bn = 0
         else:
-            bw, bh, bn = pick_box(N, Ho, Wo, rows=128, multiple_of=16)
+            # keep >= 3 pipeline stages in 227 KB: stage = (dY chunks + X chunks) * P pixels * 128 B
+            cin, cout = x.shape[3], dy.shape[3]
+            cb = cin // 64
+            g = S * (2 if (cb >= 2 and S * 2 <= 6) else 1) if S > 1 else max(d for d in (1, 2, 3, 4) if cb % d == 0)
+            chunks = (1 if cout == 64 else 2) + g
+            rows = min(128, (232192 // (3 * chunks * 128)) // 16 * 16)
+            bw, bh, bn = pick_box(N, Ho, Wo, rows=rows, multiple_of=16)
         self.box = (bw, bh, bn)
         self.plan = ext.WgradPlan(dy, taps.views, dw, R, S, taps.tap_map, taps.tap_dw, taps.tap_dh, bw, bh, bn,
                                   px_chunks, max_ctas)

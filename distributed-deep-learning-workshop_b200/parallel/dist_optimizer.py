@@ -1,0 +1,184 @@
+"""DistributedOptimizer: synchronous data parallelism with the gradient all-reduce fused and overlapped.
+
+Reference: `hvd.DistributedOptimizer(optimizer)` (P1/03:302, P2/02:189) - Horovod enqueues every gradient, fuses
+ready tensors into a fusion buffer (memcpy in), calls ncclAllReduce, scales by 1/N (separate kernel) and copies
+out.  Here the gradients are *born* inside one flat symmetric buffer (the wgrad kernels write
+there), so there is no copy in/out; when a bucket of that buffer is complete the hook launches ONE kernel on a
+high-priority communication stream that reduces the bucket across GPUs over NVLink (NVLS multimem or P2P), applies
+1/N (x loss-scale^-1) and writes the result back to every rank, while backward continues on the compute stream.
+
+Modes (``algo``):  'auto' | 'nvls' | 'p2p' | 'oneshot'  - our kernels;   'nccl' - the baseline path
+(`dist.all_reduce` + separate divide), kept selectable for A/B measurements;  'gloo' is implied on CPU.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import core
+from ..optim.fused import FlatOptimizer
+
+
+class _Bucket:
+    __slots__ = ("lo", "hi", "pending", "total")
+
+    def __init__(self, lo: int, hi: int):
+        self.lo, self.hi = lo, hi
+        self.total = hi - lo
+        self.pending = self.total
+
+
+class DistributedOptimizer:
+    """Wraps a fused flat optimizer; averages gradients over all ranks before every update."""
+
+    def __init__(self, optimizer: FlatOptimizer, bucket_mb: float = 16.0, overlap: bool = True, algo: str = "auto",
+                 comm_blocks: int = 16, average: bool = True):
+        self.opt = optimizer
+        self.bucket_bytes = int(bucket_mb * 2 ** 20)
+        self.overlap = overlap
+        self.algo = algo
+        self.comm_blocks = comm_blocks
+        self.average = average
+        self.world = core.size()
+        self.rank = core.rank()
+        self.buckets: List[_Bucket] = []
+        self.grads: Optional[torch.Tensor] = None
+        self._comm = None
+        self._sym = None
+        self._comm_stream = None
+        self._launched = 0
+        self.allreduce_launches = 0
+
+    # -- forwarded optimizer surface -------------------------------------------------------------------------
+    @property
+    def learning_rate(self) -> float:
+        return self.opt.learning_rate
+
+    @learning_rate.setter
+    def learning_rate(self, v: float) -> None:
+        self.opt.learning_rate = v
+
+    lr = learning_rate
+
+    def __getattr__(self, item):
+        if item in ("opt",):
+            raise AttributeError(item)
+        return getattr(self.opt, item)
+
+    # -- setup ----------------------------------------------------------------------------------------------
+    def allocate_grads(self, numel: int, device: torch.device) -> torch.Tensor:
+        """Flat fp32 gradient buffer: symmetric (peer-mapped, multicast) memory when running on >1 GPU."""
+        use_sym = (self.world > 1 and device.type == "cuda" and self.algo not in ("nccl", "gloo"))
+        if use_sym:
+            from . import symm
+
+            self._sym = symm.SymmetricBuffer(numel, torch.float32, device)
+            self._comm = symm.make_comm(self._sym)
+            self.grads = self._sym.tensor
+            if self.algo == "auto":
+                self.algo = "nvls" if self._sym.has_multicast else "p2p"
+            if self.algo == "nvls" and not self._sym.has_multicast:
+                raise RuntimeError("algo='nvls' requested but the symmetric buffer has no multicast mapping")
+        else:
+            self.grads = torch.zeros(numel, device=device, dtype=torch.float32)
+            if self.world > 1 and self.algo == "auto":
+                self.algo = "nccl" if device.type == "cuda" else "gloo"
+        if device.type == "cuda" and self.world > 1:
+            self._comm_stream = torch.cuda.Stream(device=device, priority=-1)
+        return self.grads
+
+    def attach(self, params: torch.Tensor, spec_ranges: List[Tuple[int, int]], w16: Optional[torch.Tensor] = None,
+               grads: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Bind flat params; build buckets from the per-parameter [lo, hi) ranges (in readiness order)."""
+        if grads is None:
+            grads = self.grads if self.grads is not None else self.allocate_grads(params.numel(), params.device)
+        self.grads = grads
+        self.opt.attach(params, grads, w16)
+        self.buckets = []
+        elem_budget = max(1, self.bucket_bytes // 4)
+        lo = None
+        hi = 0
+        for a, b in spec_ranges:
+            if lo is None:
+                lo = a
+            hi = b
+            if hi - lo >= elem_budget:
+                self.buckets.append(_Bucket(lo, hi))
+                lo = None
+        if lo is not None:
+            self.buckets.append(_Bucket(lo, hi))
+        return grads
+
+    # -- hot path ------------------------------------------------------------------------------------------
+    def begin_step(self) -> None:
+        self.opt.begin_step()
+
+    def start_backward(self) -> None:
+        for b in self.buckets:
+            b.pending = b.total
+        self._launched = 0
+
+    def on_grads_ready(self, lo: int, hi: int) -> None:
+        """Engine / autograd hook: gradient elements [lo, hi) of the flat buffer are final."""
+        if self.world == 1:
+            return
+        for i, b in enumerate(self.buckets):
+            if hi <= b.lo or lo >= b.hi:
+                continue
+            b.pending -= min(hi, b.hi) - max(lo, b.lo)
+            if b.pending <= 0 and self.overlap:
+                self._reduce_bucket(b)
+
+    def _reduce_bucket(self, b: _Bucket) -> None:
+        n = b.hi - b.lo
+        scale = (1.0 / self.world) if self.average else 1.0
+        if self.algo in ("nvls", "p2p", "oneshot"):
+            cs = self._comm_stream
+            cs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cs):
+                if self.algo == "nvls":
+                    self._comm.twoshot_nvls(b.lo, n, "f32", scale, self.comm_blocks)
+                elif self.algo == "p2p":
+                    self._comm.twoshot_p2p(b.lo, n, "f32", scale, self.comm_blocks)
+                else:
+                    self._comm.oneshot(b.lo, n, "f32", self.grads[b.lo:b.hi], scale, self.comm_blocks)
+        elif self.algo == "nccl":
+            # baseline: library collective + separate elementwise kernel (what Horovod does)
+            cs = self._comm_stream
+            cs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cs):
+                view = self.grads[b.lo:b.hi]
+                dist.all_reduce(view)
+                if self.average:
+                    view.div_(self.world)
+        else:  # gloo / CPU
+            view = self.grads[b.lo:b.hi]
+            dist.all_reduce(view)
+            if self.average:
+                view.div_(self.world)
+        self.allreduce_launches += 1
+        self._launched += 1
+
+    def finish_backward(self) -> None:
+        """Reduce whatever has not been launched yet and make the compute stream wait for the comm stream."""
+        if self.world == 1:
+            return
+        if not self.overlap or self._launched < len(self.buckets):
+            for b in self.buckets:
+                if b.pending > 0 or not self.overlap:
+                    self._reduce_bucket(b)
+                    b.pending = 0
+        if self._comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+
+    def step(self) -> None:
+        self.finish_backward()
+        self.opt.step()
+
+    # -- utilities -----------------------------------------------------------------------------------------
+    def broadcast_parameters(self, params: torch.Tensor, root: int = 0) -> None:
+        core.broadcast(params, root)
+        for v in self.opt.state.values():
+            core.broadcast(v, root)
