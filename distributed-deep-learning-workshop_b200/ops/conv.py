@@ -135,6 +135,7 @@ class ConvDgrad:
         taps_total, cout, cin = w_master.shape
         assert taps_total == R * S
         self.parts = []  # (plan, weight buffer, tap index list)
+        self._idx_dev = {}
         self.needs_zero = False
         self.dx = dx
         N, Ho, Wo, _ = dy.shape
@@ -171,6 +172,7 @@ class ConvDgrad:
                         self.needs_zero = True
                         continue
                     wbuf = torch.empty(len(idx) * cin, cout, dtype=torch.bfloat16, device=dy.device)
+                    self._idx_dev[tuple(idx)] = torch.tensor(idx, device=dy.device, dtype=torch.long)
                     box = pick_box(N, out_view.shape[1], out_view.shape[2])
                     plan = ext.ConvPlan([dy], wbuf, out_view, tm, dw, dh, box[0], box[1], box[2], None, None, max_ctas)
                     _plans.add(plan)
@@ -185,7 +187,8 @@ class ConvDgrad:
                 # one kernel: fp32 [t, Cout, Cin] -> bf16 [t, Cin, Cout]
                 _build.load("_b200_ops").weight_prep(w, None, wbuf, w.shape[0], w.shape[1], w.shape[2])
             else:
-                sel = w[idx]
+                it = self._idx_dev.get(tuple(idx))
+                sel = w.index_select(0, it) if it is not None else w  # device index: CUDA-graph capturable
                 wbuf.view(len(idx), w.shape[2], w.shape[1]).copy_(sel.transpose(1, 2))
 
     def run(self) -> None:
