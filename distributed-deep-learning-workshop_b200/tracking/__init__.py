@@ -416,7 +416,7 @@ def autolog(disable: bool = False, log_models: bool = True) -> None:
     global _autolog_enabled
     _autolog_enabled = not disable
     from ..train import trainer as _tr
-    from .autolog import install
+    from ._autolog import install
 
     install(_tr, enabled=_autolog_enabled, log_models=log_models)
 

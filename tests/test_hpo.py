@@ -1,0 +1,98 @@
+"""HPO (reference Hyperopt usage: P2/01:194-243, P2/02:322-370)."""
+import math
+import threading
+import time
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from b200ddl import hpo, tracking
+from b200ddl.hpo import STATUS_FAIL, STATUS_OK, ParallelTrials, Trials, fmin, hp, rand, space_eval, tpe
+
+SPACE = {"optimizer": hp.choice("optimizer", ["Adadelta", "Adam"]),
+         "learning_rate": hp.loguniform("learning_rate", -5, 0),
+         "dropout": hp.uniform("dropout", 0.1, 0.9)}
+
+
+def test_samplers_respect_bounds():
+    rng = np.random.default_rng(0)
+    nodes = hpo._nodes(SPACE)
+    for _ in range(200):
+        v = rand.suggest(nodes, Trials(), rng)
+        assert v["optimizer"] in (0, 1)
+        assert math.exp(-5) <= v["learning_rate"] <= 1.0
+        assert 0.1 <= v["dropout"] <= 0.9
+
+
+@settings(max_examples=25, deadline=None)
+@given(low=st.floats(-10, 0), span=st.floats(0.1, 5), q=st.sampled_from([0.5, 1.0, 8.0]))
+def test_quniform_is_quantised(low, span, q):
+    n = hp.quniform("x", low, low + span, q)
+    v = hpo._sample_node(n, np.random.default_rng(1))
+    assert abs(v / q - round(v / q)) < 1e-9
+
+
+def test_fmin_returns_choice_index_and_space_eval():
+    def obj(p):
+        return {"loss": (p["dropout"] - 0.3) ** 2 + (0 if p["optimizer"] == "Adam" else 1), "status": STATUS_OK}
+
+    trials = Trials()
+    best = fmin(obj, SPACE, algo=tpe.suggest, max_evals=60, trials=trials, rstate=0)
+    assert best["optimizer"] == 1                        # index, not 'Adam' (Hyperopt behaviour, Q7)
+    assert space_eval(SPACE, best)["optimizer"] == "Adam"
+    assert abs(best["dropout"] - 0.3) < 0.15
+    assert len(trials) == 60 and trials.best_trial["result"]["loss"] < 0.03
+
+
+def test_tpe_beats_random_on_quadratic():
+    space = {"x": hp.uniform("x", -10, 10), "y": hp.uniform("y", -10, 10)}
+    f = lambda p: (p["x"] - 3) ** 2 + (p["y"] + 2) ** 2
+    res = {"tpe": [], "rand": []}
+    for seed in range(5):
+        for name, algo in (("tpe", tpe), ("rand", rand)):
+            t = Trials()
+            fmin(f, space, algo=algo.suggest, max_evals=80, trials=t, rstate=seed)
+            res[name].append(t.best_trial["result"]["loss"])
+    assert np.median(res["tpe"]) < np.median(res["rand"])
+
+
+def test_failed_trials_are_recorded_not_fatal():
+    def obj(p):
+        if p["x"] > 0.5:
+            raise RuntimeError("boom")
+        return p["x"]
+
+    t = Trials()
+    best = fmin(obj, {"x": hp.uniform("x", 0, 1)}, algo=rand.suggest, max_evals=30, trials=t, rstate=1)
+    statuses = [r["status"] for r in t.results]
+    assert STATUS_FAIL in statuses and STATUS_OK in statuses and best["x"] <= 0.5
+
+
+def test_parallel_trials_run_concurrently(tmp_path):
+    peak, cur, lock = [0], [0], threading.Lock()
+
+    def obj(p):
+        with lock:
+            cur[0] += 1
+            peak[0] = max(peak[0], cur[0])
+        time.sleep(0.05)
+        with lock:
+            cur[0] -= 1
+        return p["x"] ** 2
+
+    t = ParallelTrials(parallelism=4)
+    fmin(obj, {"x": hp.uniform("x", -1, 1)}, algo=tpe.suggest, max_evals=16, trials=t, rstate=0)
+    assert len(t) == 16 and 2 <= peak[0] <= 4
+
+
+def test_trials_become_nested_child_runs(tmp_path):
+    tracking.set_tracking_uri(str(tmp_path / "mlruns"))
+    tracking.set_experiment("hpo")
+    with tracking.start_run(run_name="hyperopt_tuning") as parent:
+        fmin(lambda p: p["x"], {"x": hp.uniform("x", 0, 1)}, algo=rand.suggest, max_evals=5,
+             trials=ParallelTrials(parallelism=2), rstate=0)
+        pid = parent.info.run_id
+    df = tracking.search_runs(filter_string=f'tags.mlflow.parentRunId = "{pid}"', order_by=["metrics.loss ASC"])
+    assert len(df) == 5 and df["metrics.loss"].is_monotonic_increasing
+    assert tracking.active_run() is None

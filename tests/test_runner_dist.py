@@ -1,0 +1,91 @@
+"""Runner + distributed runtime on CPU (gloo, world_size 2) - the reference's HorovodRunner contract
+(P1/03:391-417): closures travel by value, rank 0's return value comes back, any failing rank fails the gang."""
+import os
+
+import pytest
+
+from b200ddl.parallel import Runner
+from b200ddl.parallel.runner import RunnerError
+
+BATCH_SIZE = 7  # driver-side global captured by the closure, like the notebook globals
+
+
+def test_np_minus_one_runs_single_local_process():
+    def fn():
+        import b200ddl.parallel as hvd
+
+        hvd.init()
+        return hvd.rank(), hvd.size(), hvd.local_rank(), BATCH_SIZE
+
+    assert Runner(np=-1, driver_log_verbosity="none", force_cpu=True).run(fn) == (0, 1, 0, 7)
+
+
+def test_two_ranks_allreduce_broadcast_and_return_value():
+    scale = 3.0
+
+    def fn(offset):
+        import torch
+        import b200ddl.parallel as hvd
+
+        hvd.init()
+        t = torch.full((4,), float(hvd.rank() + offset))
+        avg = hvd.allreduce(t, average=True)
+        w = torch.full((3,), float(hvd.rank() + 5))
+        hvd.broadcast(w, 0)
+        objs = hvd.allgather_object({"rank": hvd.rank()})
+        return {"avg": avg.tolist(), "w": w.tolist(), "size": hvd.size(), "objs": objs, "scale": scale}
+
+    out = Runner(np=2, driver_log_verbosity="none", force_cpu=True).run(fn, offset=1.0)
+    assert out["size"] == 2 and out["avg"] == [1.5] * 4 and out["w"] == [5.0] * 3
+    assert [o["rank"] for o in out["objs"]] == [0, 1] and out["scale"] == 3.0
+
+
+def test_gang_failure_surfaces_worker_traceback():
+    def fn():
+        import b200ddl.parallel as hvd
+
+        hvd.init()
+        if hvd.rank() == 1:
+            raise ValueError("rank one exploded")
+        import time
+
+        time.sleep(30)
+        return "never"
+
+    r = Runner(np=2, driver_log_verbosity="none", force_cpu=True)
+    with pytest.raises(RunnerError) as ei:
+        r.run(fn)
+    assert "rank one exploded" in str(ei.value) and "rank 1" in str(ei.value)
+
+
+def test_distributed_optimizer_averages_gradients_and_keeps_replicas_identical():
+    def fn():
+        import torch
+        import b200ddl.parallel as hvd
+        from b200ddl import optim
+        from b200ddl.train import Trainer
+        from b200ddl.utils import checksum_across_ranks
+
+        hvd.init()
+        torch.manual_seed(100 + hvd.rank())  # different init per rank on purpose
+        model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 16), torch.nn.ReLU(),
+                                    torch.nn.Linear(16, 4))
+        opt = hvd.DistributedOptimizer(optim.SGD(0.1 * hvd.size(), momentum=0.9), bucket_mb=0.0001)
+        tr = Trainer(model, device="cpu").compile(optimizer=opt)
+
+        def ds():
+            g = torch.Generator().manual_seed(hvd.rank())  # disjoint shards
+            while True:
+                y = torch.randint(0, 4, (8,), generator=g)
+                x = (torch.randint(0, 30, (8, 8, 8, 3), generator=g) + (y * 50)[:, None, None, None]).to(torch.uint8)
+                yield x, y
+
+        h = tr.fit(ds(), steps_per_epoch=20, epochs=2, verbose=0,
+                   callbacks=[hvd.callbacks.BroadcastGlobalVariablesCallback(0), hvd.callbacks.MetricAverageCallback()])
+        same = checksum_across_ranks(tr.backend.flat.params)
+        return {"same": same, "loss": h.history["loss"], "buckets": len(opt.buckets), "launches": opt.allreduce_launches}
+
+    out = Runner(np=2, driver_log_verbosity="none", force_cpu=True).run(fn)
+    assert out["same"], "replicas diverged"
+    assert out["buckets"] >= 2 and out["launches"] >= 40 * out["buckets"] - 1
+    assert out["loss"][-1] < out["loss"][0]
