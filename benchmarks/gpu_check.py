@@ -178,15 +178,40 @@ def case_elementwise():
         # backward
         gout = torch.randn(M, C_, device=DEV, generator=g).to(torch.bfloat16)
         sdz = torch.zeros(C_, device=DEV); sdzy = torch.zeros(C_, device=DEV)
-        e.bn_bwd_reduce(gout, None, out, y, sdz, sdzy)
+        dz = torch.empty_like(y)
+        e.bn_bwd_reduce(1, gout, None, out, y, None, None, dz, sdz, sdzy)
         dz_ref = gout.float() * (out.float() > 0)
         ok &= report(f"bn_bwd_reduce_dz/C{C_}", rel_err(sdz, dz_ref.sum(0)), 2e-3)
         ok &= report(f"bn_bwd_reduce_dzy/C{C_}", rel_err(sdzy, (dz_ref * yf).sum(0)), 2e-3)
+        ok &= report(f"bn_bwd_dz/C{C_}", rel_err(dz, dz_ref), 1e-2)
         dgamma = torch.empty(C_, device=DEV); dbeta = torch.empty(C_, device=DEV)
         cA = torch.empty(C_, device=DEV); cB = torch.empty(C_, device=DEV); cC = torch.empty(C_, device=DEV)
         e.bn_bwd_coeffs(sdz, sdzy, gamma, mean, invstd, float(M), dgamma, dbeta, cA, cB, cC)
-        dy = torch.empty_like(y); dz = torch.empty_like(y)
-        e.bn_bwd_apply(gout, None, out, y, cA, cB, cC, dy, dz)
+        dy = torch.empty_like(y)
+        e.bn_bwd_apply(dz, y, None, None, cA, cB, cC, dy)
+        # mode 2: same BN+ReLU without residual, mask recomputed from y
+        out2 = torch.empty_like(y)
+        e.bn_apply(y, scale, shift, None, None, None, out2, True)
+        s2 = torch.zeros(C_, device=DEV); s2y = torch.zeros(C_, device=DEV)
+        e.bn_bwd_reduce(2, gout, None, None, y, scale, shift, None, s2, s2y)
+        dz2_ref = gout.float() * (out2.float() > 0)
+        ok &= report(f"bn_bwd_reduce_mode2/C{C_}", rel_err(s2, dz2_ref.sum(0)), 2e-3)
+        dg2 = torch.empty(C_, device=DEV); db2 = torch.empty(C_, device=DEV)
+        e.bn_bwd_coeffs(s2, s2y, gamma, mean, invstd, float(M), dg2, db2, cA, cB, cC)
+        dy2 = torch.empty_like(y)
+        e.bn_bwd_apply(gout, y, scale, shift, cA, cB, cC, dy2)
+        yr2 = yf.clone().requires_grad_(True)
+        torch.relu(torch.nn.functional.batch_norm(yr2, None, None, gamma, beta, True, 0.1, 1e-5)).backward(gout.float())
+        ok &= report(f"bn_bwd_dy_mode2/C{C_}", rel_err(dy2, yr2.grad), 2e-2)
+        # mode 3: no ReLU
+        s3 = torch.zeros(C_, device=DEV); s3y = torch.zeros(C_, device=DEV)
+        e.bn_bwd_reduce(3, gout, None, None, y, None, None, None, s3, s3y)
+        e.bn_bwd_coeffs(s3, s3y, gamma, mean, invstd, float(M), dg2, db2, cA, cB, cC)
+        dy3 = torch.empty_like(y)
+        e.bn_bwd_apply(gout, y, None, None, cA, cB, cC, dy3)
+        yr3 = yf.clone().requires_grad_(True)
+        torch.nn.functional.batch_norm(yr3, None, None, gamma, beta, True, 0.1, 1e-5).backward(gout.float())
+        ok &= report(f"bn_bwd_dy_mode3/C{C_}", rel_err(dy3, yr3.grad), 2e-2)
         # autograd reference
         yr = yf.clone().requires_grad_(True)
         gr = gamma.clone().requires_grad_(True); br = beta.clone().requires_grad_(True)
@@ -195,18 +220,19 @@ def case_elementwise():
         ok &= report(f"bn_bwd_dy/C{C_}", rel_err(dy, yr.grad), 2e-2)
         ok &= report(f"bn_bwd_dgamma/C{C_}", rel_err(dgamma, gr.grad), 1e-2)
         ok &= report(f"bn_bwd_dbeta/C{C_}", rel_err(dbeta, br.grad), 1e-2)
-        ok &= report(f"bn_bwd_dz/C{C_}", rel_err(dz, dz_ref), 1e-2)
     # maxpool
     x = torch.relu(torch.randn(4, 16, 16, 64, device=DEV, generator=g)).to(torch.bfloat16)
     out = torch.empty(4, 8, 8, 64, device=DEV, dtype=torch.bfloat16)
-    e.maxpool_fwd(x, out)
+    idx = torch.empty(4, 8, 8, 64, device=DEV, dtype=torch.uint8)
+    e.maxpool_fwd(x, out, idx)
     xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
     pr = torch.nn.functional.max_pool2d(xr, 3, 2, 1)
     ok &= report("maxpool_fwd", rel_err(out, pr.permute(0, 2, 3, 1)), 0.0)
     go = torch.randn(4, 8, 8, 64, device=DEV, generator=g).to(torch.bfloat16)
+    go2 = torch.randn(4, 8, 8, 64, device=DEV, generator=g).to(torch.bfloat16)
     dx = torch.empty_like(x)
-    e.maxpool_bwd(x, out, go, dx)
-    pr.backward(go.float().permute(0, 3, 1, 2))
+    e.maxpool_bwd(idx, go, go2, dx)
+    pr.backward((go.float() + go2.float()).permute(0, 3, 1, 2))
     ok &= report("maxpool_bwd", rel_err(dx, xr.grad.permute(0, 2, 3, 1)), 1e-2)
     # gap
     x = torch.randn(8, 7, 7, 2048, device=DEV, generator=g).to(torch.bfloat16)
@@ -339,13 +365,17 @@ def case_engine():
     x = torch.randint(0, 256, (N, 224, 224, 3), device=DEV, dtype=torch.uint8, generator=g)
     y = torch.randint(0, K, (N,), device=DEV, generator=g)
     eng.set_input(x, y)
+    print("STAGE engine built", flush=True)
     ref = torchvision.models.resnet50(weights=None, num_classes=K).to(DEV)
     ref.load_state_dict({k: v.to(DEV) for k, v in eng.state_dict().items()}, strict=False)
     ref.train()
     xin = (x.permute(0, 3, 1, 2).float() / 127.5 - 1.0)
     eng.forward(training=True)
+    torch.cuda.synchronize()
+    print("STAGE forward done", flush=True)
     eng.backward()
     torch.cuda.synchronize()
+    print("STAGE backward done", flush=True)
     loss_e, acc_e = eng.loss_and_acc()
     out = ref(xin)
     loss_r = torch.nn.functional.cross_entropy(out, y)
@@ -385,6 +415,7 @@ def case_engine():
     ok &= report("engine/running_mean/bn1", rel_err(eng.running_mean["bn1"], rm["bn1.running_mean"]), 3e-2)
     ok &= report("engine/running_var/layer3.0.bn2", rel_err(eng.running_var["layer3.0.bn2"], rm["layer3.0.bn2.running_var"]), 5e-2)
     # a few optimisation steps must reduce the loss on a fixed batch (graph path)
+    print("STAGE graph steps", flush=True)
     eng2 = ResNet50Engine(batch=N, num_classes=K, seed=2)
     step2 = EngineTrainStep(eng2, optim.SGD(learning_rate=0.05, momentum=0.9), use_graph=True)
     losses = []
@@ -404,6 +435,48 @@ def case_engine():
     return ok
 
 
+def case_stem():
+    """7x7/2 stem conv on uint8 input: forward (+BN stats) and weight gradient vs torch."""
+    ok = True
+    g = torch.Generator(device=DEV).manual_seed(11)
+    for N, S in ((4, 64), (16, 224), (3, 96)):
+        x = torch.randint(0, 256, (N, S, S, 3), device=DEV, dtype=torch.uint8, generator=g)
+        w = torch.randn(49, 64, 3, device=DEV, generator=g) * 0.08
+        w16 = torch.zeros(64, 192, device=DEV, dtype=torch.bfloat16)
+        C.pack_stem_weight(w, w16)
+        Ho = S // 2
+        y = torch.empty(N, Ho, Ho, 64, device=DEV, dtype=torch.bfloat16)
+        ssum = torch.zeros(64, device=DEV); ssq = torch.zeros(64, device=DEV)
+        C.StemForward(x, w16, y, ssum, ssq).run()
+        torch.cuda.synchronize()
+        xin = (x.float() / 127.5 - 1.0).to(torch.bfloat16).float().permute(0, 3, 1, 2)
+        wt = w.to(torch.bfloat16).float().view(7, 7, 64, 3).permute(2, 3, 0, 1)
+        ref = torch.nn.functional.conv2d(xin, wt, stride=2, padding=3).permute(0, 2, 3, 1)
+        ok &= report(f"stem_fwd/N{N}_S{S}", rel_err(y, ref), 1.5e-2)
+        ok &= report(f"stem_fwd_stats_sum/N{N}_S{S}", float((ssum - ref.sum((0, 1, 2))).abs().max() / (ref.sum((0, 1, 2)).abs().max() + 1e-6)), 2e-2)
+        ok &= report(f"stem_fwd_stats_sq/N{N}_S{S}", rel_err(ssq, (ref * ref).sum((0, 1, 2))), 2e-2)
+        dy = torch.randn(N, Ho, Ho, 64, device=DEV, generator=g).to(torch.bfloat16)
+        dw = torch.zeros(49 * 64 * 3, device=DEV)
+        C.StemWgrad(x, dy, dw).run()
+        torch.cuda.synchronize()
+        gref = torch.nn.grad.conv2d_weight(xin, (64, 3, 7, 7), dy.float().permute(0, 3, 1, 2), stride=2, padding=3)
+        gref = gref.permute(2, 3, 0, 1).reshape(49, 64, 3)
+        ok &= report(f"stem_wgrad/N{N}_S{S}", rel_err(dw.view(49, 64, 3), gref), 1e-2)
+    # timing at the benchmark shape
+    N, S = 256, 224
+    x = torch.randint(0, 256, (N, S, S, 3), device=DEV, dtype=torch.uint8, generator=g)
+    w16 = torch.zeros(64, 192, device=DEV, dtype=torch.bfloat16)
+    y = torch.empty(N, 112, 112, 64, device=DEV, dtype=torch.bfloat16)
+    ssum = torch.zeros(64, device=DEV); ssq = torch.zeros(64, device=DEV)
+    f = C.StemForward(x, w16, y, ssum, ssq)
+    dw = torch.zeros(49 * 64 * 3, device=DEV)
+    wg = C.StemWgrad(x, y, dw)
+    flush = torch.empty(256 * 1024 * 1024, device=DEV, dtype=torch.uint8)
+    print(f"TIME stem fwd+stats={time_fn(f.run, flush=flush)*1e3:.0f}us wgrad={time_fn(wg.run, flush=flush)*1e3:.0f}us "
+          f"(cuDNN path in the first profile: fwd 1465us + pad 228us, wgrad 759us)", flush=True)
+    return ok
+
+
 CASES = {
     "conv_fwd": case_conv_fwd,
     "conv_dgrad": case_conv_dgrad,
@@ -411,6 +484,7 @@ CASES = {
     "elementwise": case_elementwise,
     "conv_time": case_conv_time,
     "engine": case_engine,
+    "stem": case_stem,
 }
 
 if __name__ == "__main__":

@@ -30,4 +30,13 @@ struct WgradPlanRaw {
 };
 void wgrad_plan_launch(const WgradPlanRaw& plan, cudaStream_t stream);
 
+struct StemPlanRaw {
+  CUtensorMap tmW;  // forward: bf16 [64 co, 192 k] weights
+  CUtensorMap tmY;  // forward: output [M, 64];  wgrad: dY [M, 64]
+  StemParams p;
+  int grid;
+};
+void stem_fwd_launch(const StemPlanRaw& plan, cudaStream_t stream);
+void stem_wgrad_launch(const StemPlanRaw& plan, cudaStream_t stream);
+
 }  // namespace b200

@@ -214,7 +214,8 @@ struct WgradPlan {
     TORCH_CHECK(p.stages >= 2, "wgrad stage does not fit shared memory");
     const int combos = p.co_blocks * p.groups;
     const int cap = max_ctas > 0 ? (int)max_ctas : sm_count();
-    int64_t pc = px_chunks > 0 ? px_chunks : (2 * cap + combos - 1) / combos;
+    // one wave of units: every extra pixel chunk costs a full accumulator flush of fp32 atomics
+    int64_t pc = px_chunks > 0 ? px_chunks : cap / combos;
     if (pc < 1) pc = 1;
     if (pc > p.iters_total) pc = p.iters_total;
     p.iters_per_chunk = (int)((p.iters_total + pc - 1) / pc);
@@ -233,6 +234,66 @@ struct WgradPlan {
   int grid() const { return raw.grid; }
   int units() const { return raw.p.num_units; }
   int stages() const { return raw.p.stages; }
+};
+
+struct StemPlan {
+  StemPlanRaw raw;
+  std::vector<at::Tensor> keep;
+  int64_t launches = 0;
+  bool is_wgrad;
+
+  // forward: y = conv7x7s2(x_u8 * mul + add, w) (+ BN statistics);  wgrad: dw += dy (x) patches
+  StemPlan(at::Tensor x_u8, c10::optional<at::Tensor> w16, at::Tensor y_or_dy, c10::optional<at::Tensor> dw,
+           c10::optional<at::Tensor> stat_sum, c10::optional<at::Tensor> stat_sqsum, double mul, double add,
+           int64_t max_ctas) {
+    TORCH_CHECK(x_u8.is_cuda() && x_u8.scalar_type() == at::kByte && x_u8.is_contiguous() && x_u8.dim() == 4 &&
+                x_u8.size(3) == 3, "x must be uint8 [N, H, W, 3]");
+    TORCH_CHECK(y_or_dy.is_cuda() && y_or_dy.scalar_type() == at::kBFloat16 && y_or_dy.is_contiguous() &&
+                y_or_dy.dim() == 4 && y_or_dy.size(3) == 64, "y/dy must be bf16 [N, Ho, Wo, 64]");
+    std::memset(&raw.p, 0, sizeof(raw.p));
+    StemParams& p = raw.p;
+    p.x = x_u8.data_ptr<uint8_t>();
+    p.N = (int)x_u8.size(0);
+    p.H = (int)x_u8.size(1);
+    p.W = (int)x_u8.size(2);
+    p.Ho = (int)y_or_dy.size(1);
+    p.Wo = (int)y_or_dy.size(2);
+    TORCH_CHECK(p.Ho == (p.H + 6 - 7) / 2 + 1 && p.Wo == (p.W + 6 - 7) / 2 + 1 && y_or_dy.size(0) == p.N,
+                "stem output shape mismatch");
+    p.M = (int64_t)p.N * p.Ho * p.Wo;
+    p.num_tiles = (int)((p.M + 127) / 128);
+    p.mul = (float)mul;
+    p.add = (float)add;
+    is_wgrad = dw.has_value();
+    raw.tmY = map_2d(y_or_dy.data_ptr(), p.M, 64, 64, 64, 128);
+    if (is_wgrad) {
+      TORCH_CHECK(dw->is_cuda() && dw->scalar_type() == at::kFloat && dw->is_contiguous() && dw->numel() == 49 * 64 * 3);
+      p.dw = dw->data_ptr<float>();
+      raw.tmW = raw.tmY;
+      keep.push_back(*dw);
+    } else {
+      TORCH_CHECK(w16.has_value() && w16->is_cuda() && w16->scalar_type() == at::kBFloat16 && w16->is_contiguous() &&
+                  w16->dim() == 2 && w16->size(0) == 64 && w16->size(1) == 192, "stem weight must be bf16 [64, 192]");
+      raw.tmW = map_2d(w16->data_ptr(), 64, 192, 192, 64, 64);
+      keep.push_back(*w16);
+      if (stat_sum.has_value()) {
+        TORCH_CHECK(stat_sqsum.has_value() && stat_sum->scalar_type() == at::kFloat && stat_sum->numel() >= 64);
+        p.stat_sum = stat_sum->data_ptr<float>();
+        p.stat_sqsum = stat_sqsum->data_ptr<float>();
+        keep.push_back(*stat_sum);
+        keep.push_back(*stat_sqsum);
+      }
+    }
+    const int cap = max_ctas > 0 ? (int)max_ctas : sm_count();
+    raw.grid = p.num_tiles < cap ? p.num_tiles : cap;
+    keep.push_back(x_u8);
+    keep.push_back(y_or_dy);
+  }
+  void run() {
+    if (is_wgrad) stem_wgrad_launch(raw, at::cuda::getCurrentCUDAStream());
+    else stem_fwd_launch(raw, at::cuda::getCurrentCUDAStream());
+    ++launches;
+  }
 };
 
 }  // namespace b200
@@ -262,4 +323,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_property_readonly("grid", &b200::WgradPlan::grid)
       .def_property_readonly("units", &b200::WgradPlan::units)
       .def_property_readonly("stages", &b200::WgradPlan::stages);
+  py::class_<b200::StemPlan>(m, "StemPlan")
+      .def(py::init<at::Tensor, c10::optional<at::Tensor>, at::Tensor, c10::optional<at::Tensor>,
+                    c10::optional<at::Tensor>, c10::optional<at::Tensor>, double, double, int64_t>(),
+           py::arg("x_u8"), py::arg("w16"), py::arg("y_or_dy"), py::arg("dw") = c10::nullopt,
+           py::arg("stat_sum") = c10::nullopt, py::arg("stat_sqsum") = c10::nullopt, py::arg("mul") = 1.0 / 127.5,
+           py::arg("add") = -1.0, py::arg("max_ctas") = 0)
+      .def("run", &b200::StemPlan::run)
+      .def_readonly("launches", &b200::StemPlan::launches);
 }

@@ -51,4 +51,16 @@ struct WgradParams {
   float* dw;  // [taps][Cout][Cin] fp32, accumulated with vector atomics
 };
 
+// ResNet stem (7x7/2 conv over a uint8 image), forward and weight gradient (csrc/stem.cu)
+struct StemParams {
+  const uint8_t* x;  // [N, H, W, 3] uint8
+  int N, H, W, Ho, Wo;
+  int64_t M;         // N * Ho * Wo output pixels
+  int num_tiles;     // ceil(M / 128)
+  float mul, add;    // input normalisation: v = u8 * mul + add
+  float* stat_sum;   // forward: [64] BatchNorm statistics (nullable)
+  float* stat_sqsum;
+  float* dw;         // wgrad: fp32 [49][64][3], accumulated with atomics
+};
+
 }  // namespace b200

@@ -139,125 +139,125 @@ void bn_apply(const void* y, const float* scale, const float* shift, const void*
 }
 
 // ------------------------------------------------------------------------------------------------ channel stats
-// per-channel sum / sum of squares of a [M, C] bf16 matrix (used for convs that do not run our fused epilogue)
-// and the BN-backward reductions  sum(dz), sum(dz*y)  with dz = (g1 [+ g2]) * (out > 0).
-template <int MODE>  // 0: stats of y;  1: bn backward reduce
-__global__ void col_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g2,
-                                  const __nv_bfloat16* __restrict__ outp, const __nv_bfloat16* __restrict__ y,
-                                  float* __restrict__ r0, float* __restrict__ r1, int64_t M, int C) {
-  extern __shared__ float red[];  // [rows_per_block][cvec*8][2]
+// Column reductions over a [M, C] bf16 matrix.
+//   MODE 0: sum(y), sum(y^2)                                   (BatchNorm statistics of a conv we did not run)
+//   MODE 1: dz = (g1 [+ g2]) * (out > 0)      [dz optionally stored]   -> sum(dz), sum(dz*y)   (block-final BN)
+//   MODE 2: dz = g1 * (y*scale + shift > 0)   (mask recomputed from y) -> sum(dz), sum(dz*y)   (BN + ReLU, no residual)
+//   MODE 3: dz = g1                                                     -> sum(dz), sum(dz*y)   (BN without ReLU)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+col_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g2,
+                  const __nv_bfloat16* __restrict__ outp, const __nv_bfloat16* __restrict__ y,
+                  const float* __restrict__ scale, const float* __restrict__ shift,
+                  __nv_bfloat16* __restrict__ dz_out, float* __restrict__ r0, float* __restrict__ r1, int64_t M, int C) {
+  extern __shared__ float red[];  // [2][rows_per_block][C]
   const int cvec = C / 8;
-  const int lanes = cvec < (int)blockDim.x ? cvec : blockDim.x;   // threads along channels
-  const int rpb = blockDim.x / lanes;                             // rows processed concurrently
+  const int lanes = cvec < (int)blockDim.x ? cvec : blockDim.x;  // threads along channels
+  const int rpb = blockDim.x / lanes;                            // rows processed concurrently
   const int cx = threadIdx.x % lanes;
   const int ry = threadIdx.x / lanes;
-  float s0[8], s1[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) s0[k] = s1[k] = 0.f;
-  // a block owns a contiguous strip of rows
   const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
   const int64_t r_begin = blockIdx.x * rows_per_block;
   const int64_t r_end = r_begin + rows_per_block < M ? r_begin + rows_per_block : M;
-  if (ry < rpb) {
-    for (int cv = cx; cv < cvec; cv += lanes) {
-      float t0[8], t1[8];
+  float t0[8], t1[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) t0[k] = t1[k] = 0.f;
-      for (int64_t r = r_begin + ry; r < r_end; r += rpb) {
-        const int64_t off = r * C + cv * 8;
-        float f[8];
-        unpack8(ld8(a + off), f);
-        if (MODE == 0) {
+  for (int k = 0; k < 8; ++k) t0[k] = t1[k] = 0.f;
+  if (ry < rpb && cx < cvec) {
+    float sc[8], sh[8];
+    if (MODE == 2) {
+      ldf8(scale + cx * 8, sc);
+      ldf8(shift + cx * 8, sh);
+    }
+    for (int64_t r = r_begin + ry; r < r_end; r += rpb) {
+      const int64_t off = r * C + cx * 8;
+      float f[8];
+      unpack8(ld8(a + off), f);
+      if (MODE == 0) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            t0[k] += f[k];
-            t1[k] = fmaf(f[k], f[k], t1[k]);
-          }
-        } else {
+        for (int k = 0; k < 8; ++k) {
+          t0[k] += f[k];
+          t1[k] = fmaf(f[k], f[k], t1[k]);
+        }
+      } else {
+        float yy[8];
+        unpack8(ld8(y + off), yy);
+        if (MODE == 1) {
           if (g2 != nullptr) {
             float h[8];
             unpack8(ld8(g2 + off), h);
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] += h[k];
           }
-          if (outp != nullptr) {
-            float o[8];
-            unpack8(ld8(outp + off), o);
+          float o[8];
+          unpack8(ld8(outp + off), o);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = o[k] > 0.f ? f[k] : 0.f;
-          }
-          float yy[8];
-          unpack8(ld8(y + off), yy);
+          for (int k = 0; k < 8; ++k) f[k] = o[k] > 0.f ? f[k] : 0.f;
+          if (dz_out != nullptr) st8(dz_out + off, pack8(f));
+        } else if (MODE == 2) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            t0[k] += f[k];
-            t1[k] = fmaf(f[k], yy[k], t1[k]);
-          }
+          for (int k = 0; k < 8; ++k) f[k] = fmaf(yy[k], sc[k], sh[k]) > 0.f ? f[k] : 0.f;
         }
-      }
-      if (cvec <= lanes) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          s0[k] = t0[k];
-          s1[k] = t1[k];
-        }
-      } else {
-        // more channel vectors than lanes (never for C <= 2048 with 256 threads); flush directly
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          atomicAdd(r0 + cv * 8 + k, t0[k]);
-          atomicAdd(r1 + cv * 8 + k, t1[k]);
+          t0[k] += f[k];
+          t1[k] = fmaf(f[k], yy[k], t1[k]);
         }
       }
     }
   }
-  if (cvec <= lanes) {
-    // reduce across the rpb row-lanes through shared memory, then one atomic per channel per block
-    float* sm0 = red;
-    float* sm1 = red + rpb * C;
-    if (ry < rpb) {
+  // reduce across the rpb row-lanes through shared memory, then one atomic per channel per block
+  float* sm0 = red;
+  float* sm1 = red + rpb * C;
+  if (ry < rpb && cx < cvec) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        sm0[ry * C + cx * 8 + k] = s0[k];
-        sm1[ry * C + cx * 8 + k] = s1[k];
-      }
+    for (int k = 0; k < 8; ++k) {
+      sm0[ry * C + cx * 8 + k] = t0[k];
+      sm1[ry * C + cx * 8 + k] = t1[k];
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float a0 = 0.f, a1 = 0.f;
-      for (int r = 0; r < rpb; ++r) {
-        a0 += sm0[r * C + c];
-        a1 += sm1[r * C + c];
-      }
-      atomicAdd(r0 + c, a0);
-      atomicAdd(r1 + c, a1);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = 0; r < rpb; ++r) {
+      a0 += sm0[r * C + c];
+      a1 += sm1[r * C + c];
     }
+    atomicAdd(r0 + c, a0);
+    atomicAdd(r1 + c, a1);
   }
 }
 
-static void col_reduce_launch(int mode, const void* a, const void* g2, const void* outp, const void* y, float* r0,
-                              float* r1, int64_t M, int C, cudaStream_t s) {
+static void col_reduce_launch(int mode, const void* a, const void* g2, const void* outp, const void* y,
+                              const float* scale, const float* shift, void* dz_out, float* r0, float* r1, int64_t M,
+                              int C, cudaStream_t s) {
   const int threads = 256;
-  int blocks = (int)((M + 63) / 64);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  int blocks = (int)((M + 31) / 32);
+  if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   const int cvec = C / 8;
   const int lanes = cvec < threads ? cvec : threads;
   const int rpb = threads / lanes;
   const size_t smem = (size_t)2 * rpb * C * sizeof(float);
-  if (mode == 0)
-    col_reduce_kernel<0><<<blocks, threads, smem, s>>>((const __nv_bfloat16*)a, nullptr, nullptr, nullptr, r0, r1, M, C);
-  else
-    col_reduce_kernel<1><<<blocks, threads, smem, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)g2,
-                                                       (const __nv_bfloat16*)outp, (const __nv_bfloat16*)y, r0, r1, M, C);
+  auto A = (const __nv_bfloat16*)a;
+  auto G2 = (const __nv_bfloat16*)g2;
+  auto O = (const __nv_bfloat16*)outp;
+  auto Y = (const __nv_bfloat16*)y;
+  auto DZ = (__nv_bfloat16*)dz_out;
+  switch (mode) {
+    case 0: col_reduce_kernel<0><<<blocks, threads, smem, s>>>(A, G2, O, Y, scale, shift, DZ, r0, r1, M, C); break;
+    case 1: col_reduce_kernel<1><<<blocks, threads, smem, s>>>(A, G2, O, Y, scale, shift, DZ, r0, r1, M, C); break;
+    case 2: col_reduce_kernel<2><<<blocks, threads, smem, s>>>(A, G2, O, Y, scale, shift, DZ, r0, r1, M, C); break;
+    default: col_reduce_kernel<3><<<blocks, threads, smem, s>>>(A, G2, O, Y, scale, shift, DZ, r0, r1, M, C); break;
+  }
 }
 
 void channel_stats(const void* y, float* sum, float* sqsum, int64_t M, int C, cudaStream_t s) {
-  col_reduce_launch(0, y, nullptr, nullptr, nullptr, sum, sqsum, M, C, s);
+  col_reduce_launch(0, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sum, sqsum, M, C, s);
 }
-void bn_bwd_reduce(const void* g1, const void* g2, const void* outp, const void* y, float* sum_dz, float* sum_dzy,
-                   int64_t M, int C, cudaStream_t s) {
-  col_reduce_launch(1, g1, g2, outp, y, sum_dz, sum_dzy, M, C, s);
+// mode 1: mask from `outp` (g2 optional, dz_out optional);  mode 2: mask from y*scale+shift;  mode 3: no mask
+void bn_bwd_reduce(int mode, const void* g1, const void* g2, const void* outp, const void* y, const float* scale,
+                   const float* shift, void* dz_out, float* sum_dz, float* sum_dzy, int64_t M, int C, cudaStream_t s) {
+  col_reduce_launch(mode, g1, g2, outp, y, scale, shift, dz_out, sum_dz, sum_dzy, M, C, s);
 }
 
 // ------------------------------------------------------------------------------------------------ BN bwd coeffs
@@ -290,69 +290,53 @@ void bn_bwd_coeffs(float* sum_dz, float* sum_dzy, const float* gamma, const floa
                                                         dgamma, dbeta, cA, cB, cC, C);
 }
 
-// dz = (g1 [+ g2]) * (out > 0);  dy = A*dz + B*y + Cc;  optionally dz is also written (skip-connection grad).
-template <bool HAS_G2, bool HAS_MASK, bool WRITE_DZ>
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
-                                    const __nv_bfloat16* __restrict__ outp, const __nv_bfloat16* __restrict__ y,
+// dy = A*dz + B*y + Cc  with dz either read as-is (MASK=false: stored dz / BN without ReLU) or recomputed as
+// g * (y*scale + shift > 0) (MASK=true).
+template <bool MASK>
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ cA, const float* __restrict__ cB,
-                                    const float* __restrict__ cC, __nv_bfloat16* __restrict__ dy,
-                                    __nv_bfloat16* __restrict__ dz, int64_t nvec, int cvec) {
+                                    const float* __restrict__ cC, __nv_bfloat16* __restrict__ dy, int64_t nvec,
+                                    int cvec) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % cvec) * 8;
-    float g[8], yy[8], A[8], B[8], Cc[8];
-    unpack8(ld8(g1 + i * 8), g);
-    if (HAS_G2) {
-      float h[8];
-      unpack8(ld8(g2 + i * 8), h);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] += h[k];
-    }
-    if (HAS_MASK) {
-      float o[8];
-      unpack8(ld8(outp + i * 8), o);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = o[k] > 0.f ? g[k] : 0.f;
-    }
-    if (WRITE_DZ) st8(dz + i * 8, pack8(g));
+    float gg[8], yy[8], A[8], B[8], Cc[8];
+    unpack8(ld8(g + i * 8), gg);
     unpack8(ld8(y + i * 8), yy);
+    if (MASK) {
+      float sc[8], sh[8];
+      ldf8(scale + c, sc);
+      ldf8(shift + c, sh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gg[k] = fmaf(yy[k], sc[k], sh[k]) > 0.f ? gg[k] : 0.f;
+    }
     ldf8(cA + c, A);
     ldf8(cB + c, B);
     ldf8(cC + c, Cc);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g[k] = fmaf(A[k], g[k], fmaf(B[k], yy[k], Cc[k]));
-    st8(dy + i * 8, pack8(g));
+    for (int k = 0; k < 8; ++k) gg[k] = fmaf(A[k], gg[k], fmaf(B[k], yy[k], Cc[k]));
+    st8(dy + i * 8, pack8(gg));
   }
 }
-void bn_bwd_apply(const void* g1, const void* g2, const void* outp, const void* y, const float* cA, const float* cB,
-                  const float* cC, void* dy, void* dz, int64_t M, int C, cudaStream_t s) {
+void bn_bwd_apply(const void* g, const void* y, const float* scale, const float* shift, const float* cA,
+                  const float* cB, const float* cC, void* dy, int64_t M, int C, cudaStream_t s) {
   const int64_t nvec = M * C / 8;
   const int cvec = C / 8;
   const int threads = 256;
   const int blocks = grid_for(nvec, threads);
-  auto G1 = (const __nv_bfloat16*)g1;
-  auto G2 = (const __nv_bfloat16*)g2;
-  auto O = (const __nv_bfloat16*)outp;
-  auto Y = (const __nv_bfloat16*)y;
-  auto DY = (__nv_bfloat16*)dy;
-  auto DZ = (__nv_bfloat16*)dz;
-#define L(a, b, c) bn_bwd_apply_kernel<a, b, c><<<blocks, threads, 0, s>>>(G1, G2, O, Y, cA, cB, cC, DY, DZ, nvec, cvec)
-  const int key = (g2 ? 4 : 0) | (outp ? 2 : 0) | (dz ? 1 : 0);
-  switch (key) {
-    case 0: L(false, false, false); break;
-    case 1: L(false, false, true); break;
-    case 2: L(false, true, false); break;
-    case 3: L(false, true, true); break;
-    case 4: L(true, false, false); break;
-    case 5: L(true, false, true); break;
-    case 6: L(true, true, false); break;
-    default: L(true, true, true); break;
-  }
-#undef L
+  if (scale != nullptr)
+    bn_bwd_apply_kernel<true><<<blocks, threads, 0, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y, scale, shift,
+                                                         cA, cB, cC, (__nv_bfloat16*)dy, nvec, cvec);
+  else
+    bn_bwd_apply_kernel<false><<<blocks, threads, 0, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y, scale,
+                                                          shift, cA, cB, cC, (__nv_bfloat16*)dy, nvec, cvec);
 }
 
 // ------------------------------------------------------------------------------------------------ max pool 3x3 s2 p1
-__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
-                                   int W, int C, int Ho, int Wo) {
+// Forward also stores the window position (0..8, first maximum in row-major scan order = torch's tie rule) so
+// that backward is a pure gather: every input pixel checks the <= 4 windows that contain it.
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                   uint8_t* __restrict__ idx, int N, int H, int W, int C, int Ho, int Wo) {
   const int cvec = C / 8;
   const int64_t total = (int64_t)N * Ho * Wo * cvec;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -363,35 +347,51 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
     const int ho = (int)(p % Ho);
     const int n = (int)(p / Ho);
     float m[8];
+    uint32_t am[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) m[k] = -3.0e38f;
+    for (int k = 0; k < 8; ++k) {
+      m[k] = -3.0e38f;
+      am[k] = 0;
+    }
+#pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int h = 2 * ho - 1 + r;
       if (h < 0 || h >= H) continue;
+#pragma unroll
       for (int q = 0; q < 3; ++q) {
         const int w = 2 * wo - 1 + q;
         if (w < 0 || w >= W) continue;
         float f[8];
         unpack8(ld8(x + (((int64_t)n * H + h) * W + w) * C + cv * 8), f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+        for (int k = 0; k < 8; ++k) {
+          if (f[k] > m[k]) {
+            m[k] = f[k];
+            am[k] = r * 3 + q;
+          }
+        }
       }
     }
     st8(out + i * 8, pack8(m));
+    if (idx != nullptr) {
+      uint2 pk;
+      pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+      pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+      *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    }
   }
 }
-void maxpool_fwd(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s) {
+void maxpool_fwd(const void* x, void* out, void* idx, int N, int H, int W, int C, cudaStream_t s) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
-  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, C,
-                                                          Ho, Wo);
+  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, (uint8_t*)idx,
+                                                          N, H, W, C, Ho, Wo);
 }
 
-// Backward by gather: input pixel (h, w) receives dout of every window in which it is the FIRST maximum
-// (row-major scan order, torch's tie rule) - no atomics, no saved indices.
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ out,
-                                   const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int N,
-                                   int H, int W, int C, int Ho, int Wo) {
+// dx[h, w] = sum over windows (ho, wo) containing (h, w) whose argmax is this position of (g1 [+ g2])[ho, wo].
+__global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ g1,
+                                   const __nv_bfloat16* __restrict__ g2, __nv_bfloat16* __restrict__ dx, int N, int H,
+                                   int W, int C, int Ho, int Wo) {
   const int cvec = C / 8;
   const int64_t total = (int64_t)N * H * W * cvec;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -401,52 +401,43 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __
     p /= W;
     const int h = (int)(p % H);
     const int n = (int)(p / H);
-    float xv[8], acc[8];
-    unpack8(ld8(x + i * 8), xv);
+    float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    // windows (ho, wo) containing (h, w): 2*ho-1 <= h <= 2*ho+1  <=>  ho in [h/2, (h+1)/2]
+    // windows containing (h, w): 2*ho-1 <= h <= 2*ho+1  <=>  ho in [h/2, (h+1)/2]
     for (int ho = h / 2; ho <= (h + 1) / 2; ++ho) {
-      if (ho < 0 || ho >= Ho) continue;
-      if (h < 2 * ho - 1 || h > 2 * ho + 1) continue;
+      if (ho >= Ho) continue;
+      const int r = h - (2 * ho - 1);
       for (int wo = w / 2; wo <= (w + 1) / 2; ++wo) {
-        if (wo < 0 || wo >= Wo) continue;
-        if (w < 2 * wo - 1 || w > 2 * wo + 1) continue;
-        const int64_t oidx = ((((int64_t)n * Ho + ho) * Wo + wo) * C) + cv * 8;
-        float ov[8], gv[8];
-        unpack8(ld8(out + oidx), ov);
-        unpack8(ld8(dout + oidx), gv);
-        // is (h, w) the first max of this window?  count earlier positions that also equal the max
-        bool first[8];
+        if (wo >= Wo) continue;
+        const uint32_t pos = r * 3 + (w - (2 * wo - 1));
+        const int64_t o = ((((int64_t)n * Ho + ho) * Wo + wo) * C) + cv * 8;
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
+        float gv[8];
+        unpack8(ld8(g1 + o), gv);
+        if (g2 != nullptr) {
+          float hv[8];
+          unpack8(ld8(g2 + o), hv);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) first[k] = (xv[k] == ov[k]);
-        for (int r = 0; r < 3; ++r) {
-          const int hh = 2 * ho - 1 + r;
-          if (hh < 0 || hh >= H) continue;
-          for (int q = 0; q < 3; ++q) {
-            const int ww = 2 * wo - 1 + q;
-            if (ww < 0 || ww >= W) continue;
-            if (hh > h || (hh == h && ww >= w)) continue;  // only strictly earlier positions
-            float ev[8];
-            unpack8(ld8(x + (((int64_t)n * H + hh) * W + ww) * C + cv * 8), ev);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) first[k] = first[k] && !(ev[k] == ov[k]);
-          }
+          for (int k = 0; k < 8; ++k) gv[k] += hv[k];
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += first[k] ? gv[k] : 0.f;
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t a = ((k < 4 ? pk.x : pk.y) >> (8 * (k & 3))) & 0xFFu;
+          acc[k] += (a == pos) ? gv[k] : 0.f;
+        }
       }
     }
     st8(dx + i * 8, pack8(acc));
   }
 }
-void maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, int N, int H, int W, int C,
+void maxpool_bwd(const void* idx, const void* g1, const void* g2, void* dx, int N, int H, int W, int C,
                  cudaStream_t s) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int64_t total = (int64_t)N * H * W * (C / 8);
-  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)out,
-                                                          (const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, H, W, C,
-                                                          Ho, Wo);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>((const uint8_t*)idx, (const __nv_bfloat16*)g1,
+                                                          (const __nv_bfloat16*)g2, (__nv_bfloat16*)dx, N, H, W, C, Ho,
+                                                          Wo);
 }
 
 // ------------------------------------------------------------------------------------------------ global avg pool

@@ -11,14 +11,14 @@ void bn_finalize(float* sum, float* sqsum, double count, const float* gamma, con
 void bn_apply(const void* y, const float* scale, const float* shift, const void* res, const float* res_scale,
               const float* res_shift, void* out, int64_t M, int C, bool relu, cudaStream_t s);
 void channel_stats(const void* y, float* sum, float* sqsum, int64_t M, int C, cudaStream_t s);
-void bn_bwd_reduce(const void* g1, const void* g2, const void* outp, const void* y, float* sum_dz, float* sum_dzy,
-                   int64_t M, int C, cudaStream_t s);
+void bn_bwd_reduce(int mode, const void* g1, const void* g2, const void* outp, const void* y, const float* scale,
+                   const float* shift, void* dz_out, float* sum_dz, float* sum_dzy, int64_t M, int C, cudaStream_t s);
 void bn_bwd_coeffs(float* sum_dz, float* sum_dzy, const float* gamma, const float* mean, const float* invstd,
                    double count, float* dgamma, float* dbeta, float* cA, float* cB, float* cC, int C, cudaStream_t s);
-void bn_bwd_apply(const void* g1, const void* g2, const void* outp, const void* y, const float* cA, const float* cB,
-                  const float* cC, void* dy, void* dz, int64_t M, int C, cudaStream_t s);
-void maxpool_fwd(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s);
-void maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, int N, int H, int W, int C,
+void bn_bwd_apply(const void* g, const void* y, const float* scale, const float* shift, const float* cA,
+                  const float* cB, const float* cC, void* dy, int64_t M, int C, cudaStream_t s);
+void maxpool_fwd(const void* x, void* out, void* idx, int N, int H, int W, int C, cudaStream_t s);
+void maxpool_bwd(const void* idx, const void* g1, const void* g2, void* dx, int N, int H, int W, int C,
                  cudaStream_t s);
 void gap_fwd(const void* x, void* out, int N, int HW, int C, float drop_p, uint64_t seed, cudaStream_t s);
 void gap_bwd(const void* dout, void* dx, int N, int HW, int C, float drop_p, uint64_t seed, cudaStream_t s);

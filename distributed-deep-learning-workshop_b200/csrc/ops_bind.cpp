@@ -55,12 +55,18 @@ void channel_stats(Tensor y, Tensor sum, Tensor sqsum) {
   after();
 }
 
-void bn_bwd_reduce(Tensor g1, OptT g2, OptT outp, Tensor y, Tensor sum_dz, Tensor sum_dzy) {
+// mode: 1 = ReLU mask from `outp` (g2 / dz_out optional), 2 = mask from y*scale+shift, 3 = no mask
+void bn_bwd_reduce(int64_t mode, Tensor g1, OptT g2, OptT outp, Tensor y, OptT scale, OptT shift, OptT dz_out,
+                   Tensor sum_dz, Tensor sum_dzy) {
   chk(g1, at::kBFloat16, "g1");
   chk(y, at::kBFloat16, "y");
   const int C = (int)y.size(-1);
   TORCH_CHECK(C % 8 == 0 && C <= 2048 && g1.numel() == y.numel());
-  b200::bn_bwd_reduce(g1.data_ptr(), vp(g2), vp(outp), y.data_ptr(), sum_dz.data_ptr<float>(),
+  TORCH_CHECK(mode >= 1 && mode <= 3);
+  TORCH_CHECK(mode != 1 || outp.has_value(), "mode 1 needs the activation output");
+  TORCH_CHECK(mode != 2 || (scale.has_value() && shift.has_value()), "mode 2 needs scale/shift");
+  b200::bn_bwd_reduce((int)mode, g1.data_ptr(), vp(g2), vp(outp), y.data_ptr(), fp(scale), fp(shift),
+                      dz_out.has_value() ? dz_out->data_ptr() : nullptr, sum_dz.data_ptr<float>(),
                       sum_dzy.data_ptr<float>(), y.numel() / C, C, cur());
   after();
 }
@@ -75,28 +81,31 @@ void bn_bwd_coeffs(Tensor sum_dz, Tensor sum_dzy, Tensor gamma, Tensor mean, Ten
   after();
 }
 
-void bn_bwd_apply(Tensor g1, OptT g2, OptT outp, Tensor y, Tensor cA, Tensor cB, Tensor cC, Tensor dy, OptT dz) {
-  chk(g1, at::kBFloat16, "g1");
+// dy = A*dz + B*y + C;  dz = g (scale absent) or g * (y*scale+shift > 0)
+void bn_bwd_apply(Tensor g, Tensor y, OptT scale, OptT shift, Tensor cA, Tensor cB, Tensor cC, Tensor dy) {
+  chk(g, at::kBFloat16, "g");
   chk(y, at::kBFloat16, "y");
   chk(dy, at::kBFloat16, "dy");
   const int C = (int)y.size(-1);
-  b200::bn_bwd_apply(g1.data_ptr(), vp(g2), vp(outp), y.data_ptr(), cA.data_ptr<float>(), cB.data_ptr<float>(),
-                     cC.data_ptr<float>(), dy.data_ptr(), dz.has_value() ? dz->data_ptr() : nullptr, y.numel() / C, C,
-                     cur());
+  b200::bn_bwd_apply(g.data_ptr(), y.data_ptr(), fp(scale), fp(shift), cA.data_ptr<float>(), cB.data_ptr<float>(),
+                     cC.data_ptr<float>(), dy.data_ptr(), y.numel() / C, C, cur());
   after();
 }
 
-void maxpool_fwd(Tensor x, Tensor out) {
+void maxpool_fwd(Tensor x, Tensor out, OptT idx) {
   chk(x, at::kBFloat16, "x");
   chk(out, at::kBFloat16, "out");
-  b200::maxpool_fwd(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2), (int)x.size(3), cur());
+  if (idx.has_value()) { chk(*idx, at::kByte, "idx"); TORCH_CHECK(idx->numel() == out.numel()); }
+  b200::maxpool_fwd(x.data_ptr(), out.data_ptr(), idx.has_value() ? idx->data_ptr() : nullptr, (int)x.size(0),
+                    (int)x.size(1), (int)x.size(2), (int)x.size(3), cur());
   after();
 }
-void maxpool_bwd(Tensor x, Tensor out, Tensor dout, Tensor dx) {
-  chk(x, at::kBFloat16, "x");
-  chk(dout, at::kBFloat16, "dout");
-  b200::maxpool_bwd(x.data_ptr(), out.data_ptr(), dout.data_ptr(), dx.data_ptr(), (int)x.size(0), (int)x.size(1),
-                    (int)x.size(2), (int)x.size(3), cur());
+void maxpool_bwd(Tensor idx, Tensor g1, OptT g2, Tensor dx) {
+  chk(idx, at::kByte, "idx");
+  chk(g1, at::kBFloat16, "g1");
+  chk(dx, at::kBFloat16, "dx");
+  b200::maxpool_bwd(idx.data_ptr(), g1.data_ptr(), vp(g2), dx.data_ptr(), (int)dx.size(0), (int)dx.size(1),
+                    (int)dx.size(2), (int)dx.size(3), cur());
   after();
 }
 void gap_fwd(Tensor x, Tensor out, double drop_p, int64_t seed) {

@@ -84,9 +84,10 @@ class ResNet50Engine:
 
     def __init__(self, batch: int, num_classes: int = 1000, device: Optional[torch.device] = None,
                  image_size: int = 224, dropout: float = 0.0, bn_momentum: float = 0.1, bn_eps: float = 1e-5,
-                 seed: int = 0, max_ctas: int = 0, zero_init_residual: bool = True):
+                 seed: int = 0, max_ctas: int = 0, zero_init_residual: bool = True, native_stem: bool = True):
         ops.require_native()
         self.zero_init_residual = zero_init_residual
+        self.native_stem = native_stem
         if image_size % 32:
             raise ValueError("image_size must be a multiple of 32")
         self.batch = int(batch)
@@ -197,6 +198,12 @@ class ResNet50Engine:
         if self._built:
             for d in self._dgrads:
                 d.refresh_weights()
+            self._refresh_stem_weight()
+
+    def _refresh_stem_weight(self) -> None:
+        if self.native_stem:
+            C.pack_stem_weight(self.p("conv1.weight"), self._stem_w16)
+        else:
             self._stem_w.copy_(self._stem_oihw_from_flat())
 
     def _stem_oihw_from_flat(self) -> torch.Tensor:
@@ -239,8 +246,14 @@ class ResNet50Engine:
         self.y0 = torch.zeros(N, H0, H0, 64, **bf)
         self.a0 = torch.zeros(N, H0, H0, 64, **bf)
         self.p0 = torch.zeros(N, H0 // 2, H0 // 2, 64, **bf)
-        self._stem_w = torch.zeros(64, 3, 7, 7, **bf).contiguous(memory_format=torch.channels_last)
-        self._stem_w.copy_(self._stem_oihw_from_flat())
+        self.pool_idx = torch.zeros(N, H0 // 2, H0 // 2, 64, device=dev, dtype=torch.uint8)
+        w0 = self.bnw["bn1"]
+        if self.native_stem:
+            self._stem_w16 = torch.zeros(64, 192, **bf)
+            self._stem_fwd = C.StemForward(self.x_u8, self._stem_w16, self.y0, w0["sum"], w0["sqsum"], max_ctas=self.max_ctas)
+        else:
+            self._stem_w = torch.zeros(64, 3, 7, 7, **bf).contiguous(memory_format=torch.channels_last)
+        self._refresh_stem_weight()
 
         max_act = N * (S // 4) * (S // 4) * 256
         max_act = max(max_act, N * H0 * H0 * 64)
@@ -295,6 +308,9 @@ class ResNet50Engine:
         self.pooled = torch.zeros(N, 2048, **bf)
         if training:
             self.dpooled = torch.zeros(N, 2048, **bf)
+            if self.native_stem:
+                dy0 = self._scr["dzA"][:self.y0.numel()].view(self.y0.shape)
+                self._stem_wg = C.StemWgrad(self.x_u8, dy0, self.g("conv1.weight").view(-1), max_ctas=self.max_ctas)
         self._training_built = training
         self._built = True
         self.sync_weights()
@@ -311,16 +327,19 @@ class ResNet50Engine:
     def forward(self, training: bool = True) -> None:
         """x_u8 / labels (static inputs) -> logits, loss stats.  All launches go to the current stream."""
         e, N, A = self._e, self.batch, self.act
-        e.preprocess_u8(self.x_u8, self.x16, 1.0 / 127.5, -1.0)
-        # stem: 7x7/2 conv, 3 input channels (library conv; K=147 is below the TMA 16-byte channel granule)
-        y0 = torch.nn.functional.conv2d(self.x16.permute(0, 3, 1, 2), self._stem_w, stride=2, padding=3)
-        self.y0.copy_(y0.permute(0, 2, 3, 1))
         w0 = self.bnw["bn1"]
-        e.channel_stats(self.y0, w0["sum"], w0["sqsum"])
+        if self.native_stem:
+            # 7x7/2 stem on the tensor cores straight from the uint8 batch (normalisation + BN statistics fused)
+            self._stem_fwd.run()
+        else:
+            e.preprocess_u8(self.x_u8, self.x16, 1.0 / 127.5, -1.0)
+            y0 = torch.nn.functional.conv2d(self.x16.permute(0, 3, 1, 2), self._stem_w, stride=2, padding=3)
+            self.y0.copy_(y0.permute(0, 2, 3, 1))
+            e.channel_stats(self.y0, w0["sum"], w0["sqsum"])
         cnt0 = N * self.y0.shape[1] * self.y0.shape[2]
         self._bn_fwd("bn1", cnt0, training)
         e.bn_apply(self.y0, w0["scale"], w0["shift"], None, None, None, self.a0, True)
-        e.maxpool_fwd(self.a0, self.p0)
+        e.maxpool_fwd(self.a0, self.p0, self.pool_idx)
         x_in = self.p0
         for b in self.blocks:
             n = b.name
@@ -359,12 +378,27 @@ class ResNet50Engine:
         hi = max(self.spec[n].offset + _align(self.spec[n].numel) for n in names)
         self.grad_hook(lo, hi)
 
-    def _bn_bwd(self, bn: str, g1, g2, mask, y, dy, dz, count: float) -> None:
+    def _bn_bwd(self, bn: str, mode: int, g1, g2, out, y, dy, dz, count: float) -> None:
+        """BatchNorm(+ReLU) backward = reduce pass + apply pass.
+
+        mode 1: block-final BN: dz = (g1 + g2) * (out > 0) is stored (it is also the skip-connection gradient);
+        mode 2: BN + ReLU without residual: the mask is recomputed from y (no read of the activation);
+        mode 3: BN without ReLU (downsample branch): dz = g1."""
         e, w = self._e, self.bnw[bn]
-        e.bn_bwd_reduce(g1, g2, mask, y, w["sum_dz"], w["sum_dzy"])
+        if mode == 1:
+            e.bn_bwd_reduce(1, g1, g2, out, y, None, None, dz, w["sum_dz"], w["sum_dzy"])
+        elif mode == 2:
+            e.bn_bwd_reduce(2, g1, None, None, y, w["scale"], w["shift"], None, w["sum_dz"], w["sum_dzy"])
+        else:
+            e.bn_bwd_reduce(3, g1, None, None, y, None, None, None, w["sum_dz"], w["sum_dzy"])
         e.bn_bwd_coeffs(w["sum_dz"], w["sum_dzy"], self.p(bn + ".weight"), w["mean"], w["invstd"], float(count),
                         self.g(bn + ".weight"), self.g(bn + ".bias"), w["cA"], w["cB"], w["cC"])
-        e.bn_bwd_apply(g1, g2, mask, y, w["cA"], w["cB"], w["cC"], dy, dz)
+        if mode == 1:
+            e.bn_bwd_apply(dz, y, None, None, w["cA"], w["cB"], w["cC"], dy)
+        elif mode == 2:
+            e.bn_bwd_apply(g1, y, w["scale"], w["shift"], w["cA"], w["cB"], w["cC"], dy)
+        else:
+            e.bn_bwd_apply(g1, y, None, None, w["cA"], w["cB"], w["cC"], dy)
         self._ready(bn + ".weight", bn + ".bias")
 
     def backward(self) -> None:
@@ -392,21 +426,21 @@ class ResNet50Engine:
             y3, out = A[n + ".y3"], A[n + ".out"]
             dy3 = self._scr["dy"][:y3.numel()].view(y3.shape)
             dz = self._scr[dz_keys[bi % 2]][:y3.numel()].view(y3.shape)
-            self._bn_bwd(n + ".bn3", g1, g2, out, y3, dy3, dz, cnt_out)
+            self._bn_bwd(n + ".bn3", 1, g1, g2, out, y3, dy3, dz, cnt_out)
             self._wg[n + ".conv3"].run()
             self._ready(n + ".conv3.weight")
             self._dg[n + ".conv3"].run()  # -> da (a2-shaped)
             da2 = self._scr["da"][:A[n + ".a2"].numel()].view(A[n + ".a2"].shape)
             y2, a2 = A[n + ".y2"], A[n + ".a2"]
             dy2 = self._scr["dy"][:y2.numel()].view(y2.shape)
-            self._bn_bwd(n + ".bn2", da2, None, a2, y2, dy2, None, cnt_out)
+            self._bn_bwd(n + ".bn2", 2, da2, None, None, y2, dy2, None, cnt_out)
             self._wg[n + ".conv2"].run()
             self._ready(n + ".conv2.weight")
             self._dg[n + ".conv2"].run()  # -> da (a1-shaped)
             y1, a1 = A[n + ".y1"], A[n + ".a1"]
             da1 = self._scr["da"][:a1.numel()].view(a1.shape)
             dy1 = self._scr["dy"][:y1.numel()].view(y1.shape)
-            self._bn_bwd(n + ".bn1", da1, None, a1, y1, dy1, None, cnt_in)
+            self._bn_bwd(n + ".bn1", 2, da1, None, None, y1, dy1, None, cnt_in)
             self._wg[n + ".conv1"].run()
             self._ready(n + ".conv1.weight")
             self._dg[n + ".conv1"].run()  # -> da (x_in-shaped): main-path gradient of the block input
@@ -415,7 +449,7 @@ class ResNet50Engine:
                 # the downsample branch receives the same masked gradient dz; its BN has no ReLU
                 yd = A[n + ".yd"]
                 dyd = self._scr["dy"][:yd.numel()].view(yd.shape)
-                self._bn_bwd(n + ".downsample.1", dz, None, None, yd, dyd, None, cnt_out)
+                self._bn_bwd(n + ".downsample.1", 3, dz, None, None, yd, dyd, None, cnt_out)
                 self._wg[n + ".downsample.0"].run()
                 self._ready(n + ".downsample.0.weight")
                 self._dg[n + ".downsample.0"].run()  # -> dds (x_in-shaped)
@@ -423,15 +457,17 @@ class ResNet50Engine:
             else:
                 g2 = dz
         # stem
-        gsum = torch.add(g1, g2, out=g1)
         da0 = self._scr["dy"][:self.a0.numel()].view(self.a0.shape)
-        e.maxpool_bwd(self.a0, self.p0, gsum, da0)
+        e.maxpool_bwd(self.pool_idx, g1, g2, da0)
         dy0 = self._scr["dzA"][:self.y0.numel()].view(self.y0.shape)
         cnt0 = N * self.y0.shape[1] * self.y0.shape[2]
-        self._bn_bwd("bn1", da0, None, self.a0, self.y0, dy0, None, cnt0)
-        gw = torch.nn.grad.conv2d_weight(self.x16.permute(0, 3, 1, 2), (64, 3, 7, 7), dy0.permute(0, 3, 1, 2),
-                                         stride=2, padding=3)
-        self.g("conv1.weight").view(7, 7, 64, 3).copy_(gw.permute(2, 3, 0, 1))
+        self._bn_bwd("bn1", 2, da0, None, None, self.y0, dy0, None, cnt0)
+        if self.native_stem:
+            self._stem_wg.run()
+        else:
+            gw = torch.nn.grad.conv2d_weight(self.x16.permute(0, 3, 1, 2), (64, 3, 7, 7), dy0.permute(0, 3, 1, 2),
+                                             stride=2, padding=3)
+            self.g("conv1.weight").view(7, 7, 64, 3).copy_(gw.permute(2, 3, 0, 1))
         self._ready("conv1.weight")
 
     # ------------------------------------------------------------------------------------------------ utilities
@@ -517,7 +553,7 @@ class EngineTrainStep:
         opt.step()  # distributed: waits for the comm stream first
         for d in e._dgrads:
             d.refresh_weights()
-        e._stem_w.copy_(e._stem_oihw_from_flat())
+        e._refresh_stem_weight()
 
     def capture(self) -> None:
         self._captured = True

@@ -227,6 +227,40 @@ class ConvWgrad:
         self.plan.run()
 
 
+class StemForward:
+    """y = conv7x7/2(x_u8 / 127.5 - 1, w) for the 3-channel uint8 input batch (+ fused BatchNorm statistics).
+
+    ``w16`` is the bf16 filter as ``[64, 192]`` with k = (r*7 + s)*3 + c (147 real columns, zero padded)."""
+
+    def __init__(self, x_u8: torch.Tensor, w16: torch.Tensor, y: torch.Tensor, stat_sum=None, stat_sqsum=None,
+                 mul: float = 1.0 / 127.5, add: float = -1.0, max_ctas: int = 0):
+        ext = _build.load("_b200_conv")
+        self.plan = ext.StemPlan(x_u8, w16, y, None, stat_sum, stat_sqsum, mul, add, max_ctas)
+        _plans.add(self.plan)
+
+    def run(self) -> None:
+        self.plan.run()
+
+
+class StemWgrad:
+    """dw[49, 64, 3] (fp32, accumulated) = sum_px dy[px, co] * patch(x_u8)[px, k]."""
+
+    def __init__(self, x_u8: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, mul: float = 1.0 / 127.5,
+                 add: float = -1.0, max_ctas: int = 0):
+        ext = _build.load("_b200_conv")
+        self.plan = ext.StemPlan(x_u8, None, dy, dw, None, None, mul, add, max_ctas)
+        _plans.add(self.plan)
+
+    def run(self) -> None:
+        self.plan.run()
+
+
+def pack_stem_weight(w_tck: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """[49, 64, 3] (tap, co, c) -> bf16 [64, 192] with k = tap*3 + c (columns 147.. stay zero)."""
+    out[:, :147].copy_(w_tck.permute(1, 0, 2).reshape(64, 147))
+    return out
+
+
 # ------------------------------------------------------------------------------------------- references (tests)
 def weight_to_kernel_layout(w_oihw: torch.Tensor) -> torch.Tensor:
     """torch [Cout, Cin, R, S] -> kernel layout [R*S, Cout, Cin]."""

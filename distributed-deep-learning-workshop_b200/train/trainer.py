@@ -270,7 +270,10 @@ class Trainer:
                 if steps is None:
                     break
                 it = iter(x)
-                xb, yb = next(it)
+                try:
+                    xb, yb = next(it)
+                except StopIteration:
+                    break  # empty dataset
             self.backend.eval_batch(xb, yb)
             k += 1
         for l, a in self.backend.pop_results(keep=0):

@@ -1,0 +1,96 @@
+"""Part 2 / 03_pyfunc_distributed_inference  (reference: 03_pyfunc_distributed_inference.py).
+
+One-function training pipeline -> pyfunc artefact (model + image params) -> single-node predict on 10 rows ->
+sharded batch inference (`spark_udf`) on 1000 rows, one scoring process per GPU."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from common import *  # noqa: F401,F403
+from dataclasses import dataclass
+import numpy as np
+import pandas as pd
+from b200ddl import optim, pyfunc, tracking
+from b200ddl.loader import make_converter
+from b200ddl.models import CLASSES, build_model, decode_image
+from b200ddl.train import EarlyStopping, Trainer
+
+BATCH_SIZE = 16 if SMALL else 128     # reference :64
+EPOCHS = 1 if SMALL else 2            # reference :403
+ARCH = default_arch()
+
+
+@dataclass
+class DataCfg:                        # reference :85-94
+    train_tbl_name: str
+    validation_tbl_name: str
+    petastorm_cache_dir: str = session.cache_dir
+
+
+class FlowerPyFunc(pyfunc.PythonModel):                                    # reference :157-234
+    def load_context(self, context):
+        with open(context.artifacts["img_params_dict_path"]) as f:
+            d = json.load(f)
+        self.img_height, self.img_width = d["img_height"], d["img_width"]
+        self.model = tracking.keras.load_model(context.artifacts["keras_model_path"])
+
+    def preprocess(self, img_bytes):
+        # ONE preprocessing for training and serving (the reference resizes with PIL and skips normalisation here,
+        # SURVEY.md Q6); normalisation runs on the device inside the model's first kernel.
+        return decode_image(img_bytes, (self.img_height, self.img_width))
+
+    def predict(self, context, model_input: pd.Series) -> np.ndarray:
+        arr = np.stack([self.preprocess(b) for b in model_input])
+        logits = self.model.predict(arr, batch_size=BATCH_SIZE)
+        return np.take(CLASSES, np.argmax(logits, axis=1))
+
+
+def train_model_petastorm_data_ingest(data_cfg, compile_kwargs, fit_kwargs):    # reference :253-377
+    tracking.autolog()
+    with tracking.start_run(run_name="pyfunc_model_petastorm") as mlflow_run:
+        tracking.log_dict({"img_height": IMG_HEIGHT, "img_width": IMG_WIDTH}, "img_params_dict.json")
+        batch_size = fit_kwargs.pop("batch_size")
+        tracking.log_param("BATCH_SIZE", batch_size)
+        train_df = catalog.table(data_cfg.train_tbl_name).select(["content", "label_idx"]).repartition(2)
+        val_df = catalog.table(data_cfg.validation_tbl_name).select(["content", "label_idx"]).repartition(2)
+        conv_train = make_converter(train_df, data_cfg.petastorm_cache_dir)
+        conv_val = make_converter(val_df, data_cfg.petastorm_cache_dir)
+        model = build_model(IMG_HEIGHT, IMG_WIDTH, 3, len(CLASSES), arch=ARCH, batch_size=batch_size)
+        trainer = Trainer(model).compile(**compile_kwargs)
+        with conv_train.make_dataset(batch_size=batch_size, image_size=(IMG_HEIGHT, IMG_WIDTH)) as train_ds, \
+             conv_val.make_dataset(batch_size=batch_size, image_size=(IMG_HEIGHT, IMG_WIDTH)) as val_ds:
+            history = trainer.fit(train_ds, steps_per_epoch=max(1, len(conv_train) // batch_size),
+                                  validation_data=val_ds, validation_steps=max(1, len(conv_val) // batch_size),
+                                  **fit_kwargs)
+            pyfunc.log_model("pyfunc_model", python_model=FlowerPyFunc(),
+                             artifacts={"img_params_dict_path": f"runs:/{mlflow_run.info.run_id}/img_params_dict.json",
+                                        "keras_model_path": f"runs:/{mlflow_run.info.run_id}/model"})   # :354-363
+            metrics = trainer.evaluate(val_ds, steps=max(1, len(conv_val) // batch_size))
+            tracking.log_metrics({"val_" + n: v for n, v in zip(trainer.metrics_names, metrics)})       # :369-371
+        conv_train.delete()
+        conv_val.delete()
+    tracking.autolog(disable=True)
+    return mlflow_run, trainer, history
+
+
+tracking.set_experiment(f"/Users/{user}/distributed_dl_workshop")
+data_cfg = DataCfg(f"{database_name}.silver_train", f"{database_name}.silver_val")
+compile_kwargs = {"optimizer": optim.Adam(learning_rate=0.001), "loss": "sparse_categorical_crossentropy",
+                  "metrics": ["accuracy"]}                                                              # :392-395
+callbacks = [EarlyStopping(monitor="val_loss", min_delta=1e-2, patience=3)]                             # :397-401 (used)
+fit_kwargs = {"batch_size": BATCH_SIZE, "epochs": EPOCHS, "verbose": 1, "callbacks": callbacks}        # :402-404
+mlflow_run, trainer, history = train_model_petastorm_data_ingest(data_cfg, compile_kwargs, fit_kwargs)
+
+# -- single-node inference on 10 rows (reference :440-450)
+inference_df = catalog.table(f"{database_name}.silver")
+model_uri = f"runs:/{mlflow_run.info.run_id}/pyfunc_model"
+loaded_model = pyfunc.load_model(model_uri)
+sample_pdf = inference_df.limit(10).toPandas()
+print(loaded_model.predict(sample_pdf["content"]))
+
+# -- distributed inference on 1000 rows (reference :466-476)
+classify_udf = pyfunc.spark_udf(None, model_uri, result_type="string")
+pred_df = inference_df.limit(1000).withColumn("prediction", classify_udf("content")) \
+    .select("path", "content", "label", "prediction")
+pred_df.display(10)
+pdf = pred_df.toPandas()
+print(f"scored {len(pdf)} rows with {classify_udf.stats['workers']} worker(s): "
+      f"{classify_udf.stats['rows_per_sec']:.0f} rows/s, accuracy {(pdf.label == pdf.prediction).mean():.3f}")

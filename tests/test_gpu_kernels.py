@@ -1,0 +1,85 @@
+"""GPU tests (run on the B200 box: `pytest tests -m gpu`): every hand-written kernel against a PyTorch fp32
+reference of the same op, plus the ResNet-50 engine against torchvision with identical weights."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+
+
+@pytest.fixture(scope="module")
+def checks():
+    import gpu_check
+
+    return gpu_check
+
+
+def test_native_extensions_are_loaded():
+    from b200ddl import ops
+
+    ops.require_native()
+    for n in ops.EXT_NAMES:
+        m = ops.ext(n)
+        assert m.__file__.endswith(".so") and "csrc/build" in m.__file__
+
+
+def test_elementwise_and_optimizer_kernels(checks):
+    assert checks.case_elementwise()
+
+
+def test_conv_forward_tcgen05(checks):
+    assert checks.case_conv_fwd()
+
+
+def test_conv_dgrad_tcgen05(checks):
+    assert checks.case_conv_dgrad()
+
+
+def test_conv_wgrad_tcgen05(checks):
+    assert checks.case_conv_wgrad()
+
+
+def test_stem_conv_tcgen05(checks):
+    assert checks.case_stem()
+
+
+def test_resnet50_engine_matches_torchvision(checks):
+    assert checks.case_engine()
+
+
+def test_ring_loader_h2d_roundtrip():
+    from b200ddl.loader import SyntheticDataset
+
+    with SyntheticDataset(batch_size=16, num_classes=10, image_size=(64, 64), threads=2, pool_images=64) as ds:
+        seen = []
+        for _ in range(6):
+            x, y = next(ds)
+            assert x.is_cuda and x.shape == (16, 64, 64, 3) and x.dtype == torch.uint8
+            assert y.is_cuda and int(y.min()) >= 0 and int(y.max()) < 10
+            seen.append(int(x.sum()))
+        assert ds.ring.h2d_bytes == 6 * 16 * (64 * 64 * 3 + 8)
+    assert len(set(seen)) > 1
+
+
+def test_smoke_entry():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+
+    g.smoke()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_allreduce_two_gpus():
+    import subprocess
+
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611",
+                        os.path.join(ROOT, "benchmarks", "allreduce_check.py"), "--quick"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
+    assert "ALLREDUCE CHECK PASS" in p.stdout

@@ -1,0 +1,118 @@
+"""pyfunc packaging + batch inference (reference P2/03) and the converter/ring loader (reference Petastorm usage)."""
+import io
+import json
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from b200ddl import Session, optim, pyfunc, tracking
+from b200ddl.data import synthetic_images, pandas_udf, col
+from b200ddl.loader import make_converter
+from b200ddl.models import CLASSES, build_model, decode_image
+from b200ddl.train import Trainer
+
+IMG = 32
+
+
+class FlowerPyFunc(pyfunc.PythonModel):                       # reference P2/03:157-234
+    def load_context(self, context):
+        with open(context.artifacts["img_params_dict_path"]) as f:
+            d = json.load(f)
+        self.img_height, self.img_width = d["img_height"], d["img_width"]
+        self.model = tracking.keras.load_model(context.artifacts["keras_model_path"])
+
+    def preprocess(self, img_bytes):
+        return decode_image(img_bytes, (self.img_height, self.img_width))
+
+    def predict(self, context, model_input: pd.Series) -> np.ndarray:
+        arr = np.stack([self.preprocess(b) for b in model_input])
+        logits = self.model.predict(arr, batch_size=16)
+        return np.take(CLASSES, np.argmax(logits, axis=1))
+
+
+@pytest.fixture()
+def session(tmp_path):
+    s = Session(user="me@example.com", root=str(tmp_path))
+    tracking.set_experiment("pyfunc")
+    return s
+
+
+def _tables(session, n=48):
+    raw = synthetic_images(n, size=(IMG, IMG), jpeg=True, seed=2)
+
+    @pandas_udf("string")
+    def label(path):
+        return path.map(lambda p: p.split("/")[-2])
+
+    @pandas_udf("int")
+    def label_idx(lab):
+        return lab.map(lambda l: CLASSES.index(l))
+
+    return raw.withColumn("label", label(col("path"))).withColumn("label_idx", label_idx(col("label")))
+
+
+def test_converter_len_sharding_and_infinite_epochs(session):
+    t = _tables(session, 40).select(["content", "label_idx"])
+    conv = make_converter(t, session.cache_dir)
+    assert len(conv) == 40                                                         # reference P1/03:143
+    seen = []
+    for shard in range(2):
+        with conv.make_dataset(batch_size=4, cur_shard=shard, shard_count=2, workers_count=1, image_size=(IMG, IMG),
+                               device="cpu") as ds:                                # reference P1/03:332-337
+            labs = []
+            for _ in range(7):                                                     # 20 rows / 4 = 5 batches per epoch -> wraps
+                x, y = next(ds)
+                assert x.shape == (4, IMG, IMG, 3) and x.dtype == torch.uint8 and y.dtype == torch.int64
+                labs.append(y.clone())
+            seen.append(torch.cat(labs)[:20])
+    full = t.to_pandas()["label_idx"].to_numpy()
+    assert sorted(torch.cat(seen).tolist()) == sorted(full.tolist())                # disjoint shards cover the table
+    with pytest.raises(ValueError):
+        conv.make_dataset(4, cur_shard=0)
+    conv.delete()
+    import os
+    assert not os.path.exists(conv.cache_dir)                                      # reference P1/03:425-426
+
+
+def test_decoded_pixels_match_pil(session):
+    t = _tables(session, 4).select(["content", "label_idx"])
+    conv = make_converter(t, session.cache_dir)
+    with conv.make_dataset(batch_size=4, workers_count=1, image_size=(IMG, IMG), device="cpu", num_epochs=1) as ds:
+        x, y = next(ds)
+    from PIL import Image
+
+    ref = np.stack([np.asarray(Image.open(io.BytesIO(c)).convert("RGB")) for c in t.to_pandas()["content"]])
+    assert np.array_equal(x.numpy(), ref)
+    conv.delete()
+
+
+def test_train_log_pyfunc_and_batch_inference(session):
+    data = _tables(session, 48)
+    conv = make_converter(data.select(["content", "label_idx"]), session.cache_dir)
+    tracking.autolog()
+    try:
+        with tracking.start_run(run_name="pyfunc_model_petastorm") as run:         # reference P2/03:280
+            tracking.log_dict({"img_height": IMG, "img_width": IMG}, "img_params_dict.json")
+            model = build_model(IMG, IMG, 3, 5, arch="mobilenetv2", freeze_base=False)
+            tr = Trainer(model, device="cpu").compile(optimizer=optim.Adam(2e-3))
+            with conv.make_dataset(batch_size=8, workers_count=2, image_size=(IMG, IMG), device="cpu") as ds:
+                tr.fit(ds, steps_per_epoch=len(conv) // 8, epochs=2, verbose=0)
+            rid = run.info.run_id
+            pyfunc.log_model("pyfunc_model", python_model=FlowerPyFunc(),
+                             artifacts={"img_params_dict_path": f"runs:/{rid}/img_params_dict.json",
+                                        "keras_model_path": f"runs:/{rid}/model"})   # reference P2/03:354-363
+    finally:
+        tracking.autolog(disable=True)
+    conv.delete()
+    loaded = pyfunc.load_model(f"runs:/{rid}/pyfunc_model")                         # reference P2/03:446
+    pdf = data.limit(10).toPandas()
+    pred = loaded.predict(pdf["content"])                                           # reference P2/03:448
+    assert pred.shape == (10,) and set(pred) <= set(CLASSES)
+    udf = pyfunc.spark_udf(None, f"runs:/{rid}/pyfunc_model", result_type="string")  # reference P2/03:466
+    udf.num_workers = 1
+    out = data.limit(20).withColumn("prediction", udf("content")).select("path", "content", "label", "prediction")
+    df = out.to_pandas()
+    assert len(df) == 20 and list(df["prediction"][:10]) == list(pred)
+    assert udf.stats["rows"] == 20
