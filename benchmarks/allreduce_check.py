@@ -81,7 +81,7 @@ def main():
             algos.append("p2p")
             if buf.has_multicast:
                 algos.append("nvls")
-            blocks = 4 if nbytes <= (256 << 10) else (16 if nbytes <= (16 << 20) else 32)
+            blocks = 4 if nbytes <= (256 << 10) else (16 if nbytes <= (4 << 20) else (32 if nbytes <= (32 << 20) else 64))
             tol = 1e-5 if dtype == torch.float32 else 2.5e-2
             res = {"dtype": name, "bytes": nbytes, "world": world}
             for algo in algos:

@@ -17,7 +17,10 @@ fi
 echo "allreduce rc=$?"; grep -E "world=|FAIL|ALLREDUCE|f32 |bf16 " gpurun_out/allreduce_w$N.log | tail -30
 timeout 400 $TR --master-port 29602 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_w$N.log 2>&1
 echo "bench rc=$?"; tail -n 1 gpurun_out/bench_w$N.log | cut -c1-900
-timeout 300 $TR --master-port 29603 bench.py --gpus $N --steps 20 --warmup 5 --algo nccl --no-e2e > gpurun_out/bench_w${N}_ncclpath.log 2>&1
-echo "bench(nccl path) rc=$?"; tail -n 1 gpurun_out/bench_w${N}_ncclpath.log | cut -c1-400
+# A/B of the communication path only (both eager, no CUDA graph): our fused kernel vs dist.all_reduce + div
+timeout 200 $TR --master-port 29603 bench.py --gpus $N --steps 15 --warmup 4 --algo nccl --no-e2e --no-graph > gpurun_out/bench_w${N}_ncclpath.log 2>&1
+echo "bench(nccl path, eager) rc=$?"; tail -n 1 gpurun_out/bench_w${N}_ncclpath.log | cut -c1-300
+timeout 200 $TR --master-port 29605 bench.py --gpus $N --steps 15 --warmup 4 --no-e2e --no-graph > gpurun_out/bench_w${N}_eager.log 2>&1
+echo "bench(fused path, eager) rc=$?"; tail -n 1 gpurun_out/bench_w${N}_eager.log | cut -c1-300
 timeout 300 $TR --master-port 29604 baseline/torch_resnet50.py --steps 20 --warmup 5 > gpurun_out/base_w$N.log 2>&1
 echo "torch baseline rc=$?"; tail -n 1 gpurun_out/base_w$N.log | cut -c1-300

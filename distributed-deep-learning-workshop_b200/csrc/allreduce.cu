@@ -123,7 +123,9 @@ __global__ void __launch_bounds__(512) allreduce_oneshot_kernel(CommCtx c, int64
 }
 
 // ------------------------------------------------------------------------------------------------ two-shot P2P
-template <int T>
+// UNROLL independent 16-byte vectors per thread per iteration: all peer loads of an iteration are issued before the
+// first add, so UNROLL * world loads are in flight per thread (NVLink latency is ~3 us; bandwidth needs depth).
+template <int T, int UNROLL>
 __global__ void __launch_bounds__(512) allreduce_twoshot_p2p_kernel(CommCtx c, int64_t off, int64_t n, float scale) {
   constexpr int E = Vec<T>::kElems;
   const int64_t nvec = n / E;
@@ -131,21 +133,41 @@ __global__ void __launch_bounds__(512) allreduce_twoshot_p2p_kernel(CommCtx c, i
   const int64_t v0 = per * c.rank;
   const int64_t v1 = (v0 + per < nvec) ? v0 + per : nvec;
   block_barrier(c, 0);
-  for (int64_t i = v0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < v1; i += (int64_t)gridDim.x * blockDim.x) {
-    float acc[8];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = v0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < v1; i += stride * UNROLL) {
+    uint4 raw[UNROLL];
+    float acc[UNROLL][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[u][k] = 0.f;
     for (int r = 0; r < c.world; ++r) {
-      float f[8];
-      Vec<T>::load(reinterpret_cast<const char*>(c.peer_bufs[r]) + (off + i * E) * esize<T>(), f);
+      const char* base = reinterpret_cast<const char*>(c.peer_bufs[r]) + off * esize<T>();
 #pragma unroll
-      for (int k = 0; k < E; ++k) acc[k] += f[k];
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t j = i + u * stride;
+        raw[u] = (j < v1) ? *reinterpret_cast<const uint4*>(base + j * 16) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        float f[8];
+        Vec<T>::load(&raw[u], f);
+#pragma unroll
+        for (int k = 0; k < E; ++k) acc[u][k] += f[k];
+      }
     }
 #pragma unroll
-    for (int k = 0; k < E; ++k) acc[k] *= scale;
-    // all-gather by P2P stores: push the reduced vector into every rank's buffer
-    for (int r = 0; r < c.world; ++r)
-      Vec<T>::store(reinterpret_cast<char*>(c.peer_bufs[r]) + (off + i * E) * esize<T>(), acc);
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t j = i + u * stride;
+      if (j >= v1) continue;
+#pragma unroll
+      for (int k = 0; k < E; ++k) acc[u][k] *= scale;
+      uint4 outv;
+      Vec<T>::store(&outv, acc[u]);
+      // all-gather by P2P stores: push the reduced vector into every rank's buffer
+      for (int r = 0; r < c.world; ++r)
+        *reinterpret_cast<uint4*>(reinterpret_cast<char*>(c.peer_bufs[r]) + off * esize<T>() + j * 16) = outv;
+    }
   }
   block_barrier(c, 1);
 }
@@ -174,7 +196,7 @@ __device__ __forceinline__ void mm_st_b32x4(void* mc, const uint32_t (&w)[4]) {
                : "memory");
 }
 
-template <int T>
+template <int T, int UNROLL>
 __global__ void __launch_bounds__(512) allreduce_twoshot_nvls_kernel(CommCtx c, int64_t off, int64_t n, float scale) {
   constexpr int E = Vec<T>::kElems;
   const int64_t nvec = n / E;
@@ -183,24 +205,43 @@ __global__ void __launch_bounds__(512) allreduce_twoshot_nvls_kernel(CommCtx c, 
   const int64_t v1 = (v0 + per < nvec) ? v0 + per : nvec;
   block_barrier(c, 0);
   char* mc = reinterpret_cast<char*>(c.mc_buf) + off * esize<T>();
-  for (int64_t i = v0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < v1; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = v0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < v1; i += stride * UNROLL) {
     if (T == kF32) {
-      float f[4];
-      mm_ld_reduce_f32(mc + i * 16, f);
+      float f[UNROLL][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) f[k] *= scale;
-      mm_st_f32(mc + i * 16, f);
-    } else {
-      uint32_t w[4];
-      mm_ld_reduce_bf16(mc + i * 16, w);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&w[k]);
-        float2 t = __bfloat1622float2(h);
-        h = __floats2bfloat162_rn(t.x * scale, t.y * scale);
-        w[k] = *reinterpret_cast<uint32_t*>(&h);
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t j = i + u * stride;
+        if (j < v1) mm_ld_reduce_f32(mc + j * 16, f[u]);
       }
-      mm_st_b32x4(mc + i * 16, w);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t j = i + u * stride;
+        if (j >= v1) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[u][k] *= scale;
+        mm_st_f32(mc + j * 16, f[u]);
+      }
+    } else {
+      uint32_t w[UNROLL][4];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t j = i + u * stride;
+        if (j < v1) mm_ld_reduce_bf16(mc + j * 16, w[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t j = i + u * stride;
+        if (j >= v1) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&w[u][k]);
+          float2 t = __bfloat1622float2(h);
+          h = __floats2bfloat162_rn(t.x * scale, t.y * scale);
+          w[u][k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        mm_st_b32x4(mc + j * 16, w[u]);
+      }
     }
   }
   block_barrier(c, 1);
@@ -290,16 +331,21 @@ void allreduce_oneshot(const CommCtx& c, int64_t off, int64_t n, CommDtype in_t,
 void allreduce_twoshot_p2p(const CommCtx& c, int64_t off, int64_t n, CommDtype t, float scale, int blocks,
                            cudaStream_t s) {
   blocks = clamp_blocks(blocks);
-  if (t == kF32) allreduce_twoshot_p2p_kernel<kF32><<<blocks, 512, 0, s>>>(c, off, n, scale);
-  else allreduce_twoshot_p2p_kernel<kBF16><<<blocks, 512, 0, s>>>(c, off, n, scale);
+  if (c.world <= 2) {
+    if (t == kF32) allreduce_twoshot_p2p_kernel<kF32, 4><<<blocks, 512, 0, s>>>(c, off, n, scale);
+    else allreduce_twoshot_p2p_kernel<kBF16, 4><<<blocks, 512, 0, s>>>(c, off, n, scale);
+  } else {
+    if (t == kF32) allreduce_twoshot_p2p_kernel<kF32, 2><<<blocks, 512, 0, s>>>(c, off, n, scale);
+    else allreduce_twoshot_p2p_kernel<kBF16, 2><<<blocks, 512, 0, s>>>(c, off, n, scale);
+  }
   check_launch("allreduce_twoshot_p2p");
 }
 void allreduce_twoshot_nvls(const CommCtx& c, int64_t off, int64_t n, CommDtype t, float scale, int blocks,
                             cudaStream_t s) {
   if (c.mc_buf == nullptr) throw std::runtime_error("allreduce_twoshot_nvls: no multicast mapping");
   blocks = clamp_blocks(blocks);
-  if (t == kF32) allreduce_twoshot_nvls_kernel<kF32><<<blocks, 512, 0, s>>>(c, off, n, scale);
-  else allreduce_twoshot_nvls_kernel<kBF16><<<blocks, 512, 0, s>>>(c, off, n, scale);
+  if (t == kF32) allreduce_twoshot_nvls_kernel<kF32, 8><<<blocks, 512, 0, s>>>(c, off, n, scale);
+  else allreduce_twoshot_nvls_kernel<kBF16, 8><<<blocks, 512, 0, s>>>(c, off, n, scale);
   check_launch("allreduce_twoshot_nvls");
 }
 void broadcast_sym(const CommCtx& c, int64_t off, int64_t n, CommDtype t, int root, int blocks, cudaStream_t s) {

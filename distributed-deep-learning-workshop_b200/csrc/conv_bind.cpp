@@ -260,12 +260,13 @@ struct StemPlan {
     p.Wo = (int)y_or_dy.size(2);
     TORCH_CHECK(p.Ho == (p.H + 6 - 7) / 2 + 1 && p.Wo == (p.W + 6 - 7) / 2 + 1 && y_or_dy.size(0) == p.N,
                 "stem output shape mismatch");
+    TORCH_CHECK(p.Wo <= 128 && p.W % 16 == 0 && p.W <= 256, "stem kernel needs W % 16 == 0 and W <= 256");
     p.M = (int64_t)p.N * p.Ho * p.Wo;
-    p.num_tiles = (int)((p.M + 127) / 128);
+    p.num_tiles = p.N * p.Ho;  // one output row per tile
     p.mul = (float)mul;
     p.add = (float)add;
     is_wgrad = dw.has_value();
-    raw.tmY = map_2d(y_or_dy.data_ptr(), p.M, 64, 64, 64, 128);
+    raw.tmY = map_2d(y_or_dy.data_ptr(), p.M, 64, 64, 64, p.Wo);
     if (is_wgrad) {
       TORCH_CHECK(dw->is_cuda() && dw->scalar_type() == at::kFloat && dw->is_contiguous() && dw->numel() == 49 * 64 * 3);
       p.dw = dw->data_ptr<float>();

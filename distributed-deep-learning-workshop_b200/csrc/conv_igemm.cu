@@ -64,7 +64,7 @@ static void launch_t(const ConvPlanRaw& pl, cudaStream_t s) {
     if (e != cudaSuccess) throw std::runtime_error(std::string("conv_igemm: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
-  kern<<<pl.grid, 256, ConvSmem<BN>::kTotal, s>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmA[3], pl.tmB, pl.tmD, pl.p);
+  kern<<<pl.grid, ST ? 384 : 256, ConvSmem<BN>::kTotal, s>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmA[3], pl.tmB, pl.tmD, pl.p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("conv_igemm launch: ") + cudaGetErrorString(e));
 }

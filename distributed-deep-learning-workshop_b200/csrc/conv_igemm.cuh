@@ -36,7 +36,7 @@ struct ConvSmem {
 };
 
 template <int BLOCK_N, bool kStats>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kStats ? 384 : 256, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
@@ -162,7 +162,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         acc_phase ^= 1;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue (128 threads)
     const int ew = warp - 4;           // TMEM lane quarter == warp_id % 4
     const int row = ew * 32 + lane;    // tile row owned by this thread
@@ -190,7 +190,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       for (int c64 = 0; c64 < BLOCK_N / 64; ++c64, ++chunk_ctr) {
         uint8_t* sbuf = sStage + (chunk_ctr & 1) * (kBlockM * 128);
         if (etid == 0) tma_store_wait_read<1>();  // the store that used this buffer two chunks ago is done
-        named_bar_sync(1, 128);
+        if (kStats)
+          named_bar_sync(4 + (chunk_ctr & 1), 256);  // ... and the statistics warps are done reading it
+        else
+          named_bar_sync(1, 128);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t r[32];
@@ -216,6 +219,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
+        if (kStats) named_bar_arrive(6 + (chunk_ctr & 1), 256);  // staged tile is complete: wake the statistics warps
         if (etid == 0) {
           const int ccol = nb * BLOCK_N + c64 * 64;
           if (p.mode == 0)
@@ -224,42 +228,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             tma_store_4d(&tmD, sbuf, ccol, w0, h0, n0);
           tma_store_commit();
         }
-        if (kStats) {
-          // Column statistics from the bf16 tile that was just staged (exactly the values BatchNorm will read):
-          // thread = (column pair cp, 32-row group rg); one conflict-free LDS.32 per row, no shuffles.
-          const int cp = etid & 31;
-          const int rg = etid >> 5;
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-          const int r_end = min(rg * 32 + 32, p.valid_rows);
-#pragma unroll 8
-          for (int r = rg * 32; r < r_end; ++r) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-            s0 += f.x;
-            s1 += f.y;
-            q0 = fmaf(f.x, f.x, q0);
-            q1 = fmaf(f.y, f.y, q1);
-          }
-          const int col = c64 * 64 + cp * 2;
-          atomicAdd(&sStat[col], s0);
-          atomicAdd(&sStat[col + 1], s1);
-          atomicAdd(&sStat[BLOCK_N + col], q0);
-          atomicAdd(&sStat[BLOCK_N + col + 1], q1);
-        }
-      }
-      if (kStats) {
-        const int next = tile + gridDim.x;
-        const bool flush = (next >= p.num_tiles) || ((next % p.n_blocks) != nb);
-        if (flush) {
-          named_bar_sync(3, 128);  // all smem atomics of this tile landed
-          for (int i = etid; i < 2 * BLOCK_N; i += 128) {
-            const float v = sStat[i];
-            sStat[i] = 0.f;
-            float* dst = (i < BLOCK_N) ? (p.stat_sum + nb * BLOCK_N + i) : (p.stat_sqsum + nb * BLOCK_N + (i - BLOCK_N));
-            atomicAdd(dst, v);
-          }
-          // the next tile's first named_bar_sync(1) orders the zeroing before new atomics
-        }
       }
       if (++acc == 2) {
         acc = 0;
@@ -267,6 +235,55 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
     if (etid == 0) tma_store_wait_all<0>();
+  } else if (kStats && warp >= 8) {
+    // ------------------------------------------------------------------ BatchNorm statistics warps (128 threads)
+    // Column sums / sums of squares of the bf16 tile the epilogue just staged (exactly the values BatchNorm will
+    // read), running concurrently with the epilogue's next chunk: thread = (column pair cp, 32-row group rg),
+    // one conflict-free LDS.32 per row.  Named barriers 4/5 = "staging buffer b is free", 6/7 = "buffer b is full".
+    const int stid = threadIdx.x - 256;
+    const int cp = stid & 31;
+    const int rg = stid >> 5;
+    named_bar_arrive(4, 256);
+    named_bar_arrive(5, 256);
+    int chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nb = tile % p.n_blocks;
+#pragma unroll 1
+      for (int c64 = 0; c64 < BLOCK_N / 64; ++c64, ++chunk_ctr) {
+        const int b = chunk_ctr & 1;
+        const uint8_t* sbuf = sStage + b * (kBlockM * 128);
+        named_bar_sync(6 + b, 256);
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        const int r_end = min(rg * 32 + 32, p.valid_rows);
+#pragma unroll 8
+        for (int r = rg * 32; r < r_end; ++r) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+          s0 += f.x;
+          s1 += f.y;
+          q0 = fmaf(f.x, f.x, q0);
+          q1 = fmaf(f.y, f.y, q1);
+        }
+        named_bar_arrive(4 + b, 256);  // done reading the staging buffer
+        const int col = c64 * 64 + cp * 2;
+        atomicAdd(&sStat[col], s0);
+        atomicAdd(&sStat[col + 1], s1);
+        atomicAdd(&sStat[BLOCK_N + col], q0);
+        atomicAdd(&sStat[BLOCK_N + col + 1], q1);
+      }
+      const int next = tile + gridDim.x;
+      const bool flush = (next >= p.num_tiles) || ((next % p.n_blocks) != nb);
+      if (flush) {
+        named_bar_sync(3, 128);  // all smem atomics of this n-block landed
+        for (int i = stid; i < 2 * BLOCK_N; i += 128) {
+          const float v = sStat[i];
+          sStat[i] = 0.f;
+          float* dst = (i < BLOCK_N) ? (p.stat_sum + nb * BLOCK_N + i) : (p.stat_sqsum + nb * BLOCK_N + (i - BLOCK_N));
+          atomicAdd(dst, v);
+        }
+        named_bar_sync(3, 128);  // zeroing is complete before the next tile's atomics
+      }
+    }
   }
 
   tc_fence_before();

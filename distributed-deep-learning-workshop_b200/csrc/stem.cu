@@ -21,56 +21,112 @@ namespace b200 {
 constexpr int kStemK = 192;        // 147 padded to 3 x 64
 constexpr int kStemStages = 3;
 constexpr int kStemTileBytes = 3 * 128 * 128;  // 48 KB im2col tile
+constexpr int kPatchRowMax = 16 + 256 * 3 + 16;
+constexpr int kPatchBytes = 7 * kPatchRowMax;  // one output row needs 7 input rows (uint8, zero padded)
 
-__device__ __forceinline__ void stem_build_rows(const StemParams& p, uint8_t* tile, int tile_idx, int bt) {
-  // builder thread bt in [0, 256): pixel row m = bt & 127, k-chunks [half*12, half*12 + 12)
-  const int m = bt & 127;
-  const int half = bt >> 7;
-  const int64_t px = (int64_t)tile_idx * 128 + m;
-  const bool live = px < p.M;
-  int n = 0, ho = 0, wo = 0;
-  if (live) {
-    const int hw = p.Ho * p.Wo;
-    n = (int)(px / hw);
-    const int rem = (int)(px - (int64_t)n * hw);
-    ho = rem / p.Wo;
-    wo = rem - ho * p.Wo;
+// A tile is ONE output row (n, ho): Wo <= 128 output pixels.
+// Step 1 (all 256 builder threads): stage the 7 input rows the tile needs in shared memory with 16-byte loads;
+//         rows outside the image are zero, 16 zero bytes on either side provide the horizontal padding.
+// Step 2: thread (pixel m, half) converts its half of the 147-byte patch: 6 aligned LDS.32 + funnel shifts per
+//         input row, PRMT into an exact integer float, FADD/FFMA normalisation, bf16 pack, 16-byte smem stores
+//         into the SWIZZLE_128B tile.
+__device__ __forceinline__ void stem_load_patch(const StemParams& p, uint8_t* patch, int tile_idx, int bt) {
+  const int n = tile_idx / p.Ho;
+  const int ho = tile_idx - n * p.Ho;
+  const int row_vec = p.W * 3 / 16;  // W % 16 == 0
+  const int stride = 16 + p.W * 3 + 16;
+  for (int i = bt; i < 7 * row_vec; i += 256) {
+    const int r = i / row_vec;
+    const int c16 = i - r * row_vec;
+    const int h = 2 * ho - 3 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (h >= 0 && h < p.H) v = *reinterpret_cast<const uint4*>(p.x + ((int64_t)(n * p.H + h) * p.W) * 3 + c16 * 16);
+    *reinterpret_cast<uint4*>(patch + r * stride + 16 + c16 * 16) = v;
   }
-  const int h0 = 2 * ho - 3, w0 = 2 * wo - 3;
-  const uint8_t* img = p.x + (int64_t)n * p.H * p.W * 3;
+}
+
+template <int R0, int NROWS>
+__device__ __forceinline__ void stem_fetch_rows(const uint8_t* patch, int stride, int wo, uint32_t (&S)[NROWS][6]) {
 #pragma unroll
-  for (int cc = 0; cc < 12; ++cc) {
-    uint32_t w32[4] = {0u, 0u, 0u, 0u};
-    if (half == 0) {
+  for (int r = 0; r < NROWS; ++r) {
+    const uint32_t a = (R0 + r) * stride + 7 + 6 * wo;  // byte address of (h, w = 2*wo-3, c = 0) in the patch
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(patch + (a & ~3u));
+    const uint32_t sh = (a & 3u) * 8u;
+    uint32_t w[7];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = cc * 8 + e;  // 0..95 < 147
-        const int r = k / 21, j = k % 21, s = j / 3;
-        const int h = h0 + r, w = w0 + s;
-        float f = 0.f;
-        if (live && h >= 0 && h < p.H && w >= 0 && w < p.W) f = fmaf((float)img[((int64_t)h * p.W + w0) * 3 + j], p.mul, p.add);
-        const uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(f));
-        w32[e >> 1] |= b << (16 * (e & 1));
+    for (int i = 0; i < 6; ++i) w[i] = wp[i];
+    w[6] = 0u;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) S[r][i] = __funnelshift_r(w[i], w[i + 1], sh);
+  }
+}
+
+__device__ __forceinline__ float stem_elem(uint32_t word, int byte_in_word, float mul, float add) {
+  // byte -> exact float via the 2^23 trick (PRMT + FADD), then the input normalisation (FFMA)
+  const uint32_t u = __byte_perm(word, 0x4B000000u, 0x7540u | (uint32_t)byte_in_word);
+  return fmaf(__uint_as_float(u) - 8388608.0f, mul, add);
+}
+
+__device__ __forceinline__ void stem_build_rows(const StemParams& p, const uint8_t* patch, uint8_t* tile, int bt) {
+  const int m = bt & 127;   // output pixel wo
+  const int half = bt >> 7;
+  if (m >= p.Wo) return;
+  const int stride = 16 + p.W * 3 + 16;
+  if (half == 0) {
+    uint32_t S[5][6];  // rows 0..4 (row 4: bytes 0..11 only)
+    stem_fetch_rows<0, 5>(patch, stride, m, S);
+#pragma unroll
+    for (int cc = 0; cc < 12; ++cc) {
+      uint32_t w32[4];
+#pragma unroll
+      for (int e2 = 0; e2 < 4; ++e2) {
+        const int k0 = cc * 8 + e2 * 2, k1 = k0 + 1;
+        const float f0 = stem_elem(S[k0 / 21][(k0 % 21) >> 2], (k0 % 21) & 3, p.mul, p.add);
+        const float f1 = stem_elem(S[k1 / 21][(k1 % 21) >> 2], (k1 % 21) & 3, p.mul, p.add);
+        w32[e2] = pack_bf16x2(f0, f1);
       }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = 96 + cc * 8 + e;
-        if (k < 147) {
-          const int r = k / 21, j = k % 21, s = j / 3;
-          const int h = h0 + r, w = w0 + s;
-          float f = 0.f;
-          if (live && h >= 0 && h < p.H && w >= 0 && w < p.W) f = fmaf((float)img[((int64_t)h * p.W + w0) * 3 + j], p.mul, p.add);
-          const uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(f));
-          w32[e >> 1] |= b << (16 * (e & 1));
-        }
-      }
+      const int kb = cc >> 3, c8 = cc & 7;
+      *reinterpret_cast<uint4*>(tile + kb * (128 * 128) + m * 128 + ((c8 ^ (m & 7)) << 4)) =
+          make_uint4(w32[0], w32[1], w32[2], w32[3]);
     }
-    const int chunk = half * 12 + cc;    // 16-byte chunk index along K, 0..23
-    const int kb = chunk >> 3;           // k-block (64 k each)
-    const int c8 = chunk & 7;
-    *reinterpret_cast<uint4*>(tile + kb * (128 * 128) + m * 128 + ((c8 ^ (m & 7)) << 4)) =
-        make_uint4(w32[0], w32[1], w32[2], w32[3]);
+  } else {
+    uint32_t S[3][6];  // rows 4..6
+    stem_fetch_rows<4, 3>(patch, stride, m, S);
+#pragma unroll
+    for (int cc = 0; cc < 7; ++cc) {  // k = 96 .. 151 (147.. are zero); chunks 12..18
+      uint32_t w32[4];
+#pragma unroll
+      for (int e2 = 0; e2 < 4; ++e2) {
+        const int k0 = 96 + cc * 8 + e2 * 2, k1 = k0 + 1;
+        const float f0 = k0 < 147 ? stem_elem(S[k0 / 21 - 4][(k0 % 21) >> 2], (k0 % 21) & 3, p.mul, p.add) : 0.f;
+        const float f1 = k1 < 147 ? stem_elem(S[k1 / 21 - 4][(k1 % 21) >> 2], (k1 % 21) & 3, p.mul, p.add) : 0.f;
+        w32[e2] = pack_bf16x2(f0, f1);
+      }
+      const int chunk = 12 + cc;
+      const int kb = chunk >> 3, c8 = chunk & 7;
+      *reinterpret_cast<uint4*>(tile + kb * (128 * 128) + m * 128 + ((c8 ^ (m & 7)) << 4)) =
+          make_uint4(w32[0], w32[1], w32[2], w32[3]);
+    }
+  }
+}
+
+// builder-side main loop shared by forward and wgrad; `tile_at(i)` enumerates the CTA's tiles
+template <int STAGE_BYTES, class TileFn>
+__device__ __forceinline__ void stem_builder_loop(const StemParams& p, uint8_t* stage_base, uint8_t* patches,
+                                                  uint64_t* full_bar, uint64_t* empty_bar, int n_my_tiles, TileFn tile_at,
+                                                  int bt, int lane) {
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int i = 0; i < n_my_tiles; ++i) {
+    uint8_t* patch = patches + (i & 1) * kPatchBytes;
+    stem_load_patch(p, patch, tile_at(i), bt);
+    named_bar_sync(4, 256);  // patch complete; also: every builder is done with the previous tile's patch buffer
+    mbar_wait(&empty_bar[stage], phase ^ 1);
+    stem_build_rows(p, patch, stage_base + stage * STAGE_BYTES, bt);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full_bar[stage]);
+    if (++stage == kStemStages) { stage = 0; phase ^= 1; }
   }
 }
 
@@ -78,7 +134,7 @@ __device__ __forceinline__ void stem_build_rows(const StemParams& p, uint8_t* ti
 struct StemFwdSmem {
   static constexpr int kB = 3 * 64 * 128;            // weights: 3 k-blocks of [64 co x 64 k]
   static constexpr int kStaging = 2 * 128 * 128;
-  static constexpr int kTotal = kStemStages * kStemTileBytes + kB + kStaging + 256 + 2 * 64 * 4;
+  static constexpr int kTotal = kStemStages * kStemTileBytes + kB + kStaging + 256 + 2 * 64 * 4 + 2 * kPatchBytes;
 };
 
 __global__ void __launch_bounds__(512, 1)
@@ -97,6 +153,7 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   uint64_t* w_bar = bars + 10;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   float* sStat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][64]
+  uint8_t* sPatch = reinterpret_cast<uint8_t*>(sStat) + 2 * 64 * 4;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,6 +172,10 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 128; i += blockDim.x) sStat[i] = 0.f;
+  // zero the im2col stages (rows >= Wo and the k >= 152 chunks are never written) and the patch padding
+  for (int i = threadIdx.x; i < kStemStages * kStemTileBytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 2 * kPatchBytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(sPatch)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
   if (warp == 2) {
     tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
@@ -188,15 +249,13 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       fence_proxy_async_smem();
       named_bar_sync(2, 128);
       if (etid == 0) {
-        tma_store_2d(&tmY, sbuf, 0, tile * 128);
+        tma_store_2d(&tmY, sbuf, 0, tile * p.Wo);
         tma_store_commit();
       }
       if (p.stat_sum != nullptr) {
         const int cp = etid & 31, rg = etid >> 5;
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        const int64_t left = p.M - (int64_t)tile * 128;
-        const int valid = left < 128 ? (int)left : 128;
-        const int r_end = min(rg * 32 + 32, valid);
+        const int r_end = min(rg * 32 + 32, p.Wo);
 #pragma unroll 8
         for (int r = rg * 32; r < r_end; ++r) {
           const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
@@ -220,16 +279,9 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   } else if (warp >= 8) {
     // ---------------------------------------------------------------- im2col builders (256 threads)
     const int bt = threadIdx.x - 256;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      stem_build_rows(p, sA + stage * kStemTileBytes, tile, bt);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[stage]);
-      if (++stage == kStemStages) { stage = 0; phase ^= 1; }
-    }
+    const int n_my = blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    stem_builder_loop<kStemTileBytes>(p, sA, sPatch, full_bar, empty_bar, n_my,
+                                      [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; }, bt, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -242,7 +294,7 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 // ------------------------------------------------------------------------------------------------ weight gradient
 struct StemWgSmem {
   static constexpr int kStage = kStemTileBytes + 128 * 128;   // im2col tile + dY tile
-  static constexpr int kTotal = kStemStages * kStage + 256;
+  static constexpr int kTotal = kStemStages * kStage + 256 + 2 * kPatchBytes;
 };
 
 __global__ void __launch_bounds__(512, 1)
@@ -254,6 +306,7 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   uint64_t* empty_bar = bars + 3; // [3]
   uint64_t* tfull_bar = bars + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint8_t* sPatch = reinterpret_cast<uint8_t*>(bars) + 256;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -265,6 +318,10 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
   }
+  // zero all stages: pixel rows >= Wo of both operands must be exact zeros (they are never written)
+  for (int i = threadIdx.x; i < kStemStages * StemWgSmem::kStage / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 2 * kPatchBytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(sPatch)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
   if (warp == 2) {
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
@@ -283,8 +340,8 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     uint32_t phase = 0;
     for (int tile = t0; tile < t1; ++tile) {
       mbar_wait(&empty_bar[stage], phase ^ 1);
-      mbar_arrive_expect_tx(&full_bar[stage], 128 * 128);
-      tma_load_2d(smem + stage * StemWgSmem::kStage + kStemTileBytes, &tmDY, &full_bar[stage], 0, tile * 128);
+      mbar_arrive_expect_tx(&full_bar[stage], p.Wo * 128);
+      tma_load_2d(smem + stage * StemWgSmem::kStage + kStemTileBytes, &tmDY, &full_bar[stage], 0, tile * p.Wo);
       if (++stage == kStemStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
@@ -296,8 +353,8 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       tc_fence_after();
       const uint32_t b0 = smem_u32(smem + stage * StemWgSmem::kStage);
       const uint32_t a0 = b0 + kStemTileBytes;
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
+      const int ksteps = (p.Wo + 15) / 16;
+      for (int ks = 0; ks < ksteps; ++ks) {
         const uint64_t da = umma_desc_sw128(a0 + ks * 2048, 0, 1024);              // 64 co; rows 64..127 mirror
         const uint64_t db = umma_desc_sw128(b0 + ks * 2048, 128 * 128, 1024);      // 3 chunks of 64 k
         umma_bf16(tmem_base, da, db, idesc, (tile != t0 || ks != 0) ? 1u : 0u);
@@ -327,16 +384,8 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
   } else if (warp >= 8) {
     const int bt = threadIdx.x - 256;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = t0; tile < t1; ++tile) {
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      stem_build_rows(p, smem + stage * StemWgSmem::kStage, tile, bt);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[stage]);
-      if (++stage == kStemStages) { stage = 0; phase ^= 1; }
-    }
+    stem_builder_loop<StemWgSmem::kStage>(p, smem, sPatch, full_bar, empty_bar, t1 > t0 ? t1 - t0 : 0,
+                                          [&](int i) { return t0 + i; }, bt, lane);
   }
   tc_fence_before();
   __syncthreads();

@@ -522,11 +522,19 @@ class EngineTrainStep:
     """
 
     def __init__(self, engine: ResNet50Engine, optimizer, use_graph: bool = True, warmup_steps: int = 2):
+        from ..parallel import core as _core
+        from ..utils.timeline import timeline_from_env
+
         self.engine = engine
         self.optimizer = optimizer
+        self.timeline = timeline_from_env(_core.rank())  # B200DDL_TIMELINE=trace.json (HOROVOD_TIMELINE equivalent)
+        if self.timeline is not None:
+            use_graph = False  # CUDA-event timing cannot be captured into a graph
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._dist = hasattr(optimizer, "on_grads_ready")
+        if self._dist:
+            optimizer.timeline = self.timeline
         e = engine
         ranges = [(s.offset, s.offset + _align(s.numel)) for s in e.param_specs]
         if self._dist:
@@ -545,15 +553,30 @@ class EngineTrainStep:
 
     # one full step as a launch sequence on the current stream
     def _launch(self) -> None:
-        e, opt = self.engine, self.optimizer
+        e, opt, tl = self.engine, self.optimizer, self.timeline
         if self._dist:
             opt.start_backward()
-        e.forward(training=True)
-        e.backward()
-        opt.step()  # distributed: waits for the comm stream first
-        for d in e._dgrads:
-            d.refresh_weights()
-        e._refresh_stem_weight()
+        if tl is None:
+            e.forward(training=True)
+            e.backward()
+            opt.step()  # distributed: waits for the comm stream first
+            for d in e._dgrads:
+                d.refresh_weights()
+            e._refresh_stem_weight()
+            return
+        with tl.device_span("forward", "step"):
+            e.forward(training=True)
+        with tl.device_span("backward", "step"):
+            e.backward()
+        with tl.device_span("allreduce_wait+optimizer", "step"):
+            opt.step()
+        with tl.device_span("weight_relayout", "step"):
+            for d in e._dgrads:
+                d.refresh_weights()
+            e._refresh_stem_weight()
+
+    def dump_timeline(self) -> Optional[str]:
+        return self.timeline.dump() if self.timeline is not None else None
 
     def capture(self) -> None:
         self._captured = True

@@ -12,6 +12,7 @@ Modes (``algo``):  'auto' | 'nvls' | 'p2p' | 'oneshot'  - our kernels;   'nccl' 
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List, Optional, Tuple
 
 import torch
@@ -50,6 +51,7 @@ class DistributedOptimizer:
         self._comm_stream = None
         self._launched = 0
         self.allreduce_launches = 0
+        self.timeline = None  # utils.Timeline: per-bucket all-reduce spans on the comm stream
 
     # -- forwarded optimizer surface -------------------------------------------------------------------------
     @property
@@ -137,7 +139,9 @@ class DistributedOptimizer:
         if self.algo in ("nvls", "p2p", "oneshot"):
             cs = self._comm_stream
             cs.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(cs):
+            span = (self.timeline.device_span(f"allreduce[{b.lo}:{b.hi}] {self.algo}", "comm", stream=cs)
+                    if self.timeline is not None else contextlib.nullcontext())
+            with torch.cuda.stream(cs), span:
                 if self.algo == "nvls":
                     self._comm.twoshot_nvls(b.lo, n, "f32", scale, self.comm_blocks)
                 elif self.algo == "p2p":

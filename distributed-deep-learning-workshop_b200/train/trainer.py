@@ -249,6 +249,11 @@ class Trainer:
             if self.stop_training:
                 break
         cbs.call("on_train_end", {})
+        step = getattr(self.backend, "step", None)
+        if step is not None and getattr(step, "timeline", None) is not None:
+            path = step.dump_timeline()
+            if is_chief:
+                print(f"timeline written to {path}")
         return self.history
 
     @staticmethod
