@@ -17,16 +17,40 @@
 
 namespace b200 {
 
+// Watchdog: a peer that died or never launched its kernel would leave us spinning forever; after
+// kCommTimeoutNs of wall time the kernel traps, the CUDA error kills this rank and the Runner stops the gang.
+constexpr unsigned long long kCommTimeoutNs = 120ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ void flag_signal(uint32_t* addr) {
   uint32_t old;
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
   do {
     asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory");
+    if (old != 0u && (++spins & 0xFFFFu) == 0u) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kCommTimeoutNs) __trap();
+    }
   } while (old != 0u);
 }
 __device__ __forceinline__ void flag_wait(uint32_t* addr) {
   uint32_t old;
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
   do {
     asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory");
+    if (old != 1u && (++spins & 0xFFFFu) == 0u) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kCommTimeoutNs) __trap();
+    }
   } while (old != 1u);
 }
 

@@ -213,6 +213,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
             v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
             v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+            if (kStats && row >= p.valid_rows) v = make_uint4(0u, 0u, 0u, 0u);  // rows past the pixel box: no statistics
             const int chunk = (h * 4 + j) ^ (row & 7);
             *reinterpret_cast<uint4*>(sbuf + row * 128 + chunk * 16) = v;
           }
@@ -238,50 +239,59 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   } else if (kStats && warp >= 8) {
     // ------------------------------------------------------------------ BatchNorm statistics warps (128 threads)
     // Column sums / sums of squares of the bf16 tile the epilogue just staged (exactly the values BatchNorm will
-    // read), running concurrently with the epilogue's next chunk: thread = (column pair cp, 32-row group rg),
-    // one conflict-free LDS.32 per row.  Named barriers 4/5 = "staging buffer b is free", 6/7 = "buffer b is full".
+    // read), concurrent with the epilogue's next chunk.  Thread = (column pair cp, 32-row group rg): one
+    // conflict-free LDS.32 per row with precomputed swizzled offsets, accumulators live in registers across tiles
+    // and are flushed with global atomics only when the CTA moves to another n-block.
+    // Named barriers 4/5 = "staging buffer b is free", 6/7 = "staging buffer b is full".
     const int stid = threadIdx.x - 256;
     const int cp = stid & 31;
     const int rg = stid >> 5;
+    uint32_t xoff[8];  // byte offset of this thread's column pair in a row with (row & 7) == j
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xoff[j] = ((((cp >> 2) ^ j) << 4) + ((cp & 3) << 2)) + rg * 32 * 128;
+    constexpr int kChunks = BLOCK_N / 64;
+    float acc[kChunks][4];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
     named_bar_arrive(4, 256);
     named_bar_arrive(5, 256);
     int chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nb = tile % p.n_blocks;
-#pragma unroll 1
-      for (int c64 = 0; c64 < BLOCK_N / 64; ++c64, ++chunk_ctr) {
+#pragma unroll
+      for (int c64 = 0; c64 < kChunks; ++c64, ++chunk_ctr) {
         const int b = chunk_ctr & 1;
         const uint8_t* sbuf = sStage + b * (kBlockM * 128);
         named_bar_sync(6 + b, 256);
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        const int r_end = min(rg * 32 + 32, p.valid_rows);
-#pragma unroll 8
-        for (int r = rg * 32; r < r_end; ++r) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-          s0 += f.x;
-          s1 += f.y;
-          q0 = fmaf(f.x, f.x, q0);
-          q1 = fmaf(f.y, f.y, q1);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + xoff[i & 7] + i * 128);
+          const float lo = __uint_as_float(w << 16);
+          const float hi = __uint_as_float(w & 0xFFFF0000u);
+          s0 += lo;
+          s1 += hi;
+          q0 = fmaf(lo, lo, q0);
+          q1 = fmaf(hi, hi, q1);
         }
         named_bar_arrive(4 + b, 256);  // done reading the staging buffer
-        const int col = c64 * 64 + cp * 2;
-        atomicAdd(&sStat[col], s0);
-        atomicAdd(&sStat[col + 1], s1);
-        atomicAdd(&sStat[BLOCK_N + col], q0);
-        atomicAdd(&sStat[BLOCK_N + col + 1], q1);
+        acc[c64][0] += s0;
+        acc[c64][1] += s1;
+        acc[c64][2] += q0;
+        acc[c64][3] += q1;
       }
       const int next = tile + gridDim.x;
       const bool flush = (next >= p.num_tiles) || ((next % p.n_blocks) != nb);
       if (flush) {
-        named_bar_sync(3, 128);  // all smem atomics of this n-block landed
-        for (int i = stid; i < 2 * BLOCK_N; i += 128) {
-          const float v = sStat[i];
-          sStat[i] = 0.f;
-          float* dst = (i < BLOCK_N) ? (p.stat_sum + nb * BLOCK_N + i) : (p.stat_sqsum + nb * BLOCK_N + (i - BLOCK_N));
-          atomicAdd(dst, v);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int col = nb * BLOCK_N + c * 64 + cp * 2;
+          atomicAdd(p.stat_sum + col, acc[c][0]);
+          atomicAdd(p.stat_sum + col + 1, acc[c][1]);
+          atomicAdd(p.stat_sqsum + col, acc[c][2]);
+          atomicAdd(p.stat_sqsum + col + 1, acc[c][3]);
+          acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
         }
-        named_bar_sync(3, 128);  // zeroing is complete before the next tile's atomics
       }
     }
   }

@@ -60,8 +60,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   const int n_acc = p.G / p.acc_chunks;
   const int acc_cols = 64 * p.acc_chunks;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one warp; lane j issues chunk j)
+    // All per-chunk parameters (tensor map, channel coordinate, tap offset) are hoisted out of the k loop and the
+    // <= 8 loads of a stage are issued by 8 lanes in parallel: a single thread doing the index arithmetic for every
+    // load was the bottleneck of this kernel (ncu: tensor pipe 26 % active, everything else idle).
+    const int n_loads = p.a_chunks + p.G;
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t tx = static_cast<uint32_t>(stage_bytes);
@@ -74,40 +78,49 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const int cbg = g - r * p.cgroups;
       const int it0 = pxc * p.iters_per_chunk;
       const int it1 = min(it0 + p.iters_per_chunk, p.iters_total);
+      // this lane's load
+      const CUtensorMap* my_map = &tmDY;
+      int my_c = 0, my_dw = 0, my_dh = 0;
+      if (lane < p.a_chunks) {
+        my_c = (cob * 2 + lane) * 64;
+      } else if (lane < n_loads) {
+        const int j = lane - p.a_chunks;
+        const int cbi = j / p.S;
+        const int sx = j - cbi * p.S;
+        const int tap = r * p.S + sx;
+        my_c = (cbg * p.cb_per_group + cbi) * 64;
+        my_dw = p.tap_dw[tap];
+        my_dh = p.tap_dh[tap];
+        my_map = &tmX0;
+        if (p.tap_map[tap] == 1) my_map = &tmX1;
+        if (p.tap_map[tap] == 2) my_map = &tmX2;
+        if (p.tap_map[tap] == 3) my_map = &tmX3;
+      }
+      // pixel-box coordinates advance incrementally (no div/mod in the loop)
+      int tw = 0, th = 0, tn = 0;
+      if (p.mode == 1) {
+        tw = it0 % p.tiles_w;
+        const int rest = it0 / p.tiles_w;
+        th = rest % p.tiles_h;
+        tn = rest / p.tiles_h;
+      }
       for (int it = it0; it < it1; ++it) {
-        int w0 = 0, h0 = 0, n0 = 0;
-        if (p.mode == 1) {
-          const int tw = it % p.tiles_w;
-          const int rest = it / p.tiles_w;
-          const int th = rest % p.tiles_h;
-          w0 = tw * p.bw;
-          h0 = th * p.bh;
-          n0 = (rest / p.tiles_h) * p.bn;
-        }
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], tx);
-        uint8_t* base = smem + stage * stage_bytes;
-        for (int i = 0; i < p.a_chunks; ++i) {
-          const int c = (cob * 2 + i) * 64;
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
+        __syncwarp();
+        if (lane < n_loads) {
+          uint8_t* dst = smem + stage * stage_bytes + lane * slot_bytes;
           if (p.mode == 0)
-            tma_load_2d(base + i * slot_bytes, &tmDY, &full_bar[stage], c, it * p.P);
+            tma_load_2d(dst, my_map, &full_bar[stage], my_c, it * p.P);
           else
-            tma_load_4d(base + i * slot_bytes, &tmDY, &full_bar[stage], c, w0, h0, n0);
+            tma_load_4d(dst, my_map, &full_bar[stage], my_c, tw * p.bw + my_dw, th * p.bh + my_dh, tn * p.bn);
         }
-        uint8_t* bbase = base + p.a_chunks * slot_bytes;
-        for (int j = 0; j < p.G; ++j) {
-          const int cbi = j / p.S;
-          const int s = j - cbi * p.S;
-          const int tap = r * p.S + s;
-          const int c = (cbg * p.cb_per_group + cbi) * 64;
-          const CUtensorMap* xm = &tmX0;
-          if (p.tap_map[tap] == 1) xm = &tmX1;
-          if (p.tap_map[tap] == 2) xm = &tmX2;
-          if (p.tap_map[tap] == 3) xm = &tmX3;
-          if (p.mode == 0)
-            tma_load_2d(bbase + j * slot_bytes, xm, &full_bar[stage], c, it * p.P);
-          else
-            tma_load_4d(bbase + j * slot_bytes, xm, &full_bar[stage], c, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+        if (++tw == p.tiles_w) {
+          tw = 0;
+          if (++th == p.tiles_h) {
+            th = 0;
+            ++tn;
+          }
         }
         if (++stage == p.stages) {
           stage = 0;
@@ -119,6 +132,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc_bf16(128, acc_cols, 1, 1);  // both operands MN-major
     const uint32_t a_lbo = (p.a_chunks == 2) ? slot_bytes : 0;    // Cout == 64: rows 64..127 mirror rows 0..63
+    // descriptors differ only in the 14-bit start-address field: build one per stage up front, then add offsets
+    const uint64_t da0 = umma_desc_sw128(smem_u32(smem), a_lbo, 1024);
+    const uint64_t db0 = umma_desc_sw128(smem_u32(smem) + p.a_chunks * slot_bytes, slot_bytes, 1024);
+    const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
+    const uint32_t acc_step = static_cast<uint32_t>(p.acc_chunks * slot_bytes) >> 4;
+    const int ksteps = p.P / 16;
     int stage = 0;
     uint32_t phase = 0;
     uint32_t uphase = 0;
@@ -131,16 +150,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       for (int it = it0; it < it1; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t abase = smem_u32(smem + stage * stage_bytes);
-        const uint32_t bbase = abase + p.a_chunks * slot_bytes;
-        const int ksteps = p.P / 16;
+        const uint64_t da_s = da0 + stage * stage_step;
+        const uint64_t db_s = db0 + stage * stage_step;
         for (int ks = 0; ks < ksteps; ++ks) {
-          // 16 pixels = two 8-row swizzle atoms = 2048 B along the (slow) K dimension
-          const uint64_t da = umma_desc_sw128(abase + ks * 2048, a_lbo, 1024);
-          for (int a = 0; a < n_acc; ++a) {
-            const uint64_t db = umma_desc_sw128(bbase + a * p.acc_chunks * slot_bytes + ks * 2048, slot_bytes, 1024);
-            umma_bf16(tmem_base + a * acc_cols, da, db, idesc, (it != it0 || ks != 0) ? 1u : 0u);
-          }
+          // 16 pixels = two 8-row swizzle atoms = 2048 B along the (slow) K dimension -> +128 in the address field
+          const uint32_t acc_flag = (it != it0 || ks != 0) ? 1u : 0u;
+          for (int a = 0; a < n_acc; ++a)
+            umma_bf16(tmem_base + a * acc_cols, da_s + ks * 128, db_s + a * acc_step + ks * 128, idesc, acc_flag);
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == p.stages) {

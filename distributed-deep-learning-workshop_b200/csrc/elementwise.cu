@@ -667,4 +667,33 @@ void weight_prep(const float* w, void* wf, void* wd, int taps, int cout, int cin
       w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, taps, cout, cin);
 }
 
+
+// All conv layers in one launch: table rows = (src offset in the flat fp32 master, dst offset in the flat bf16
+// dgrad buffer, taps, cout, cin, first flat element index of the layer); binary search over <= 64 layers in smem.
+__global__ void weight_prep_batched_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ wd,
+                                           const int64_t* __restrict__ table, int layers, int64_t total) {
+  __shared__ int64_t t[64 * 6];
+  for (int i = threadIdx.x; i < layers * 6; i += blockDim.x) t[i] = table[i];
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = layers - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (t[mid * 6 + 5] <= i) lo = mid; else hi = mid - 1;
+    }
+    const int64_t* L = t + lo * 6;
+    const int64_t j = i - L[5];
+    const int cin = (int)L[4], cout = (int)L[3];
+    const int ci = (int)(j % cin);
+    const int co = (int)((j / cin) % cout);
+    const int tp = (int)(j / ((int64_t)cin * cout));
+    wd[L[1] + ((int64_t)tp * cin + ci) * cout + co] = __float2bfloat16(params[L[0] + j]);
+  }
+}
+void weight_prep_batched(const float* params, void* wd, const int64_t* table, int layers, int64_t total,
+                         cudaStream_t s) {
+  weight_prep_batched_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, s>>>(params, (__nv_bfloat16*)wd, table, layers,
+                                                                          total);
+}
+
 }  // namespace b200

@@ -27,6 +27,8 @@ void softmax_ce(const float* logits, const int64_t* labels, float* dlogits, floa
 void preprocess_u8(const uint8_t* x, void* out, int64_t npix, int cpad, float mul, float add, cudaStream_t s);
 void resize_bilinear_u8(const uint8_t* x, uint8_t* out, int N, int H, int W, int OH, int OW, cudaStream_t s);
 void weight_prep(const float* w, void* wf, void* wd, int taps, int cout, int cin, cudaStream_t s);
+void weight_prep_batched(const float* params, void* wd, const int64_t* table, int layers, int64_t total,
+                         cudaStream_t s);
 
 // Fused flat-buffer optimizers.  `hyper` is a DEVICE array (so LR schedules do not invalidate CUDA graphs):
 //   [0] lr  [1] momentum/beta1  [2] beta2/rho  [3] eps  [4] weight_decay  [5] grad_scale  [6] bias_corr1  [7] bias_corr2

@@ -153,6 +153,16 @@ void weight_prep(Tensor w, OptT wf, OptT wd, int64_t taps, int64_t cout, int64_t
                     wd.has_value() ? wd->data_ptr() : nullptr, (int)taps, (int)cout, (int)cin, cur());
   after();
 }
+// table: int64 [layers, 6] on the device = (src_off, dst_off, taps, cout, cin, first_flat_index)
+void weight_prep_batched(Tensor params, Tensor wd, Tensor table, int64_t total) {
+  chk(params, at::kFloat, "params");
+  chk(wd, at::kBFloat16, "wd");
+  chk(table, at::kLong, "table");
+  TORCH_CHECK(table.dim() == 2 && table.size(1) == 6 && table.size(0) <= 64);
+  b200::weight_prep_batched(params.data_ptr<float>(), wd.data_ptr(), table.data_ptr<int64_t>(), (int)table.size(0),
+                            total, cur());
+  after();
+}
 void sgd_step(Tensor p, Tensor g, Tensor mom, OptT p16, Tensor hyper, bool nesterov) {
   chk(p, at::kFloat, "p"); chk(g, at::kFloat, "g"); chk(mom, at::kFloat, "mom"); chk(hyper, at::kFloat, "hyper");
   TORCH_CHECK(p.numel() % 4 == 0 && g.numel() == p.numel() && mom.numel() == p.numel() && hyper.numel() >= b200::kHyperLen);
@@ -201,6 +211,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("preprocess_u8", &preprocess_u8);
   m.def("resize_bilinear_u8", &resize_bilinear_u8);
   m.def("weight_prep", &weight_prep);
+  m.def("weight_prep_batched", &weight_prep_batched);
   m.def("sgd_step", &sgd_step);
   m.def("adam_step", &adam_step);
   m.def("adadelta_step", &adadelta_step);

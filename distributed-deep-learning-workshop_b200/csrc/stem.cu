@@ -61,17 +61,25 @@ __device__ __forceinline__ void stem_fetch_rows(const uint8_t* patch, int stride
   }
 }
 
-__device__ __forceinline__ float stem_elem(uint32_t word, int byte_in_word, float mul, float add) {
-  // byte -> exact float via the 2^23 trick (PRMT + FADD), then the input normalisation (FFMA)
+__device__ __forceinline__ float stem_elem(uint32_t word, int byte_in_word, float mul, float add, bool valid) {
+  // byte -> exact float via the 2^23 trick (PRMT + FADD), then the input normalisation (FFMA).
+  // Zero padding applies to the NORMALISED image, so out-of-image taps must produce 0 (not 0*mul+add).
   const uint32_t u = __byte_perm(word, 0x4B000000u, 0x7540u | (uint32_t)byte_in_word);
-  return fmaf(__uint_as_float(u) - 8388608.0f, mul, add);
+  return valid ? fmaf(__uint_as_float(u) - 8388608.0f, mul, add) : 0.f;
 }
 
-__device__ __forceinline__ void stem_build_rows(const StemParams& p, const uint8_t* patch, uint8_t* tile, int bt) {
+__device__ __forceinline__ void stem_build_rows(const StemParams& p, const uint8_t* patch, uint8_t* tile, int bt,
+                                                int ho) {
   const int m = bt & 127;   // output pixel wo
   const int half = bt >> 7;
   if (m >= p.Wo) return;
   const int stride = 16 + p.W * 3 + 16;
+  bool rv[7], cv[7];  // validity of input row 2*ho-3+r and input column 2*wo-3+s
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    rv[i] = (2 * ho - 3 + i) >= 0 && (2 * ho - 3 + i) < p.H;
+    cv[i] = (2 * m - 3 + i) >= 0 && (2 * m - 3 + i) < p.W;
+  }
   if (half == 0) {
     uint32_t S[5][6];  // rows 0..4 (row 4: bytes 0..11 only)
     stem_fetch_rows<0, 5>(patch, stride, m, S);
@@ -81,8 +89,10 @@ __device__ __forceinline__ void stem_build_rows(const StemParams& p, const uint8
 #pragma unroll
       for (int e2 = 0; e2 < 4; ++e2) {
         const int k0 = cc * 8 + e2 * 2, k1 = k0 + 1;
-        const float f0 = stem_elem(S[k0 / 21][(k0 % 21) >> 2], (k0 % 21) & 3, p.mul, p.add);
-        const float f1 = stem_elem(S[k1 / 21][(k1 % 21) >> 2], (k1 % 21) & 3, p.mul, p.add);
+        const float f0 = stem_elem(S[k0 / 21][(k0 % 21) >> 2], (k0 % 21) & 3, p.mul, p.add,
+                                   rv[k0 / 21] && cv[(k0 % 21) / 3]);
+        const float f1 = stem_elem(S[k1 / 21][(k1 % 21) >> 2], (k1 % 21) & 3, p.mul, p.add,
+                                   rv[k1 / 21] && cv[(k1 % 21) / 3]);
         w32[e2] = pack_bf16x2(f0, f1);
       }
       const int kb = cc >> 3, c8 = cc & 7;
@@ -98,8 +108,10 @@ __device__ __forceinline__ void stem_build_rows(const StemParams& p, const uint8
 #pragma unroll
       for (int e2 = 0; e2 < 4; ++e2) {
         const int k0 = 96 + cc * 8 + e2 * 2, k1 = k0 + 1;
-        const float f0 = k0 < 147 ? stem_elem(S[k0 / 21 - 4][(k0 % 21) >> 2], (k0 % 21) & 3, p.mul, p.add) : 0.f;
-        const float f1 = k1 < 147 ? stem_elem(S[k1 / 21 - 4][(k1 % 21) >> 2], (k1 % 21) & 3, p.mul, p.add) : 0.f;
+        const float f0 = k0 < 147 ? stem_elem(S[k0 / 21 - 4][(k0 % 21) >> 2], (k0 % 21) & 3, p.mul, p.add,
+                                              rv[(k0 / 21) % 7] && cv[(k0 % 21) / 3]) : 0.f;
+        const float f1 = k1 < 147 ? stem_elem(S[k1 / 21 - 4][(k1 % 21) >> 2], (k1 % 21) & 3, p.mul, p.add,
+                                              rv[(k1 / 21) % 7] && cv[(k1 % 21) / 3]) : 0.f;
         w32[e2] = pack_bf16x2(f0, f1);
       }
       const int chunk = 12 + cc;
@@ -119,10 +131,11 @@ __device__ __forceinline__ void stem_builder_loop(const StemParams& p, uint8_t* 
   uint32_t phase = 0;
   for (int i = 0; i < n_my_tiles; ++i) {
     uint8_t* patch = patches + (i & 1) * kPatchBytes;
-    stem_load_patch(p, patch, tile_at(i), bt);
+    const int tile = tile_at(i);
+    stem_load_patch(p, patch, tile, bt);
     named_bar_sync(4, 256);  // patch complete; also: every builder is done with the previous tile's patch buffer
     mbar_wait(&empty_bar[stage], phase ^ 1);
-    stem_build_rows(p, patch, stage_base + stage * STAGE_BYTES, bt);
+    stem_build_rows(p, patch, stage_base + stage * STAGE_BYTES, bt, tile % p.Ho);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(&full_bar[stage]);

@@ -188,6 +188,26 @@ class Converter:
         shutil.rmtree(self.cache_dir, ignore_errors=True)
 
 
+class InMemoryDataset:
+    """`toPandas()` + `from_tensor_slices((content, label_idx)).map(preprocess).batch(B)` (reference P1/02:97-139,
+    P2/01:137-151): the whole table is decoded once into driver memory; finite, re-iterable, `len()` = batches."""
+
+    def __init__(self, table_or_pdf, batch_size: int, image_size=(IMG_HEIGHT, IMG_WIDTH), drop_last: bool = True):
+        pdf = table_or_pdf.to_pandas() if hasattr(table_or_pdf, "to_pandas") else table_or_pdf
+        self.images = torch.from_numpy(np.stack([decode_image(c, image_size) for c in pdf["content"]]))
+        self.labels = torch.from_numpy(pdf["label_idx"].to_numpy(dtype=np.int64))
+        self.batch_size = max(1, min(batch_size, len(self.labels)))
+        n = len(self.labels)
+        self.n = n // self.batch_size * self.batch_size if drop_last else n
+
+    def __len__(self) -> int:
+        return max(1, -(-self.n // self.batch_size))
+
+    def __iter__(self):
+        for i in range(0, self.n, self.batch_size):
+            yield self.images[i:i + self.batch_size], self.labels[i:i + self.batch_size]
+
+
 def make_converter(table, cache_dir: Optional[str] = None) -> Converter:
     """`make_spark_converter(df)` (reference P1/03:140-141)."""
     if cache_dir is None:
@@ -197,4 +217,4 @@ def make_converter(table, cache_dir: Optional[str] = None) -> Converter:
 
 make_spark_converter = make_converter
 
-__all__ = ["make_converter", "make_spark_converter", "Converter", "SyntheticDataset", "RingDataset"]
+__all__ = ["make_converter", "make_spark_converter", "Converter", "SyntheticDataset", "RingDataset", "InMemoryDataset"]

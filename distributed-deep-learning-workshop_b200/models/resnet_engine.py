@@ -196,9 +196,16 @@ class ResNet50Engine:
         """Refresh every bf16 working copy from the fp32 master (after an optimizer step or a weight load)."""
         self._e.cast_bf16(self.params, self.w16)
         if self._built:
-            for d in self._dgrads:
-                d.refresh_weights()
-            self._refresh_stem_weight()
+            self.refresh_derived_weights()
+
+    def refresh_derived_weights(self) -> None:
+        """bf16 copies in layouts other than the master's: dgrad filters (one batched kernel + the few stride-2
+        tap subsets) and the packed stem filter."""
+        if getattr(self, "_wd_total", 0) > 0:
+            self._e.weight_prep_batched(self.params, self._wd16, self._wd_table, self._wd_total)
+        for d in self._dgrads:
+            d.refresh_weights()  # no-op for the batched ones
+        self._refresh_stem_weight()
 
     def _refresh_stem_weight(self) -> None:
         if self.native_stem:
@@ -260,6 +267,25 @@ class ResNet50Engine:
         if training:
             self._scr = {k: torch.zeros(max_act, **bf) for k in ("dy", "da", "dds", "dzA", "dzB")}
 
+        # bf16 dgrad copies ([tap][Cin][Cout]) of every stride-1 filter live in one flat buffer refreshed by ONE kernel
+        self._wd_table_rows = []
+        wd_total = 0
+        if training:
+            for b in self.blocks:
+                for cname, k, stride in (("conv1", 1, 1), ("conv2", 3, b.stride), ("conv3", 1, 1),
+                                         ("downsample.0", 1, b.stride)):
+                    if cname == "downsample.0" and not b.downsample:
+                        continue
+                    if stride != 1:
+                        continue
+                    sp = self.spec[b.name + "." + cname + ".weight"]
+                    self._wd_table_rows.append([sp.offset, wd_total, sp.shape[0], sp.shape[1], sp.shape[2], wd_total])
+                    wd_total += sp.numel
+            self._wd16 = torch.zeros(max(wd_total, 8), **bf)
+            self._wd_total = wd_total
+            self._wd_table = torch.tensor(self._wd_table_rows, device=dev, dtype=torch.int64).view(-1, 6)
+            self._wd_off = {r[0]: (r[1], r[2] * r[3] * r[4]) for r in self._wd_table_rows}
+
         self.act: Dict[str, torch.Tensor] = {}
         self._fwd: Dict[str, C.ConvForward] = {}
         self._dg: Dict[str, C.ConvDgrad] = {}
@@ -300,7 +326,11 @@ class ResNet50Engine:
                     self._wg[full] = C.ConvWgrad(dy, xin, gw.view(gw.shape[0] * gw.shape[1], gw.shape[2]), k, k,
                                                  stride, pad, 0, mc)
                     dx = scr("dds" if cname == "downsample.0" else "da", xin.shape)
-                    dgr = C.ConvDgrad(dy, self.p(full + ".weight"), dx, k, k, stride, pad, mc)
+                    wview = None
+                    if stride == 1:
+                        o, nel = self._wd_off[self.spec[full + ".weight"].offset]
+                        wview = self._wd16[o:o + nel]
+                    dgr = C.ConvDgrad(dy, self.p(full + ".weight"), dx, k, k, stride, pad, mc, wbuf=wview)
                     self._dg[full] = dgr
                     self._dgrads.append(dgr)
             x_in = A[b.name + ".out"]
@@ -560,9 +590,7 @@ class EngineTrainStep:
             e.forward(training=True)
             e.backward()
             opt.step()  # distributed: waits for the comm stream first
-            for d in e._dgrads:
-                d.refresh_weights()
-            e._refresh_stem_weight()
+            e.refresh_derived_weights()
             return
         with tl.device_span("forward", "step"):
             e.forward(training=True)
@@ -571,9 +599,7 @@ class EngineTrainStep:
         with tl.device_span("allreduce_wait+optimizer", "step"):
             opt.step()
         with tl.device_span("weight_relayout", "step"):
-            for d in e._dgrads:
-                d.refresh_weights()
-            e._refresh_stem_weight()
+            e.refresh_derived_weights()
 
     def dump_timeline(self) -> Optional[str]:
         return self.timeline.dump() if self.timeline is not None else None

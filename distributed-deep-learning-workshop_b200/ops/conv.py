@@ -128,10 +128,11 @@ class ConvDgrad:
     needs are (re)built by :meth:`refresh_weights` (cheap: filters are tiny next to activations)."""
 
     def __init__(self, dy: torch.Tensor, w_master: torch.Tensor, dx: torch.Tensor, R: int, S: int, stride: int = 1,
-                 pad: int = 0, max_ctas: int = 0):
+                 pad: int = 0, max_ctas: int = 0, wbuf: Optional[torch.Tensor] = None):
         ext = _build.load("_b200_conv")
         self.R, self.S, self.stride, self.pad = R, S, stride, pad
         self.w_master = w_master
+        self.external_wbuf = wbuf is not None  # owner refreshes it (e.g. one batched kernel for all layers)
         taps_total, cout, cin = w_master.shape
         assert taps_total == R * S
         self.parts = []  # (plan, weight buffer, tap index list)
@@ -148,7 +149,10 @@ class ConvDgrad:
                     tm.append(0)
                     dh.append(pad - r)
                     dw.append(pad - s)
-            wbuf = torch.empty(len(idx) * cin, cout, dtype=torch.bfloat16, device=dy.device)
+            if wbuf is None:
+                wbuf = torch.empty(len(idx) * cin, cout, dtype=torch.bfloat16, device=dy.device)
+            else:
+                wbuf = wbuf.view(len(idx) * cin, cout)
             flat = (R == 1 and S == 1 and pad == 0 and dy.is_contiguous() and dx.is_contiguous())
             box = (0, 0, 0) if flat else pick_box(N, dx.shape[1], dx.shape[2])
             plan = ext.ConvPlan([dy], wbuf, dx, tm, dw, dh, box[0], box[1], box[2], None, None, max_ctas)
@@ -180,6 +184,8 @@ class ConvDgrad:
         self.refresh_weights()
 
     def refresh_weights(self) -> None:
+        if self.external_wbuf:
+            return
         w = self.w_master
         full = list(range(w.shape[0]))
         for _, wbuf, idx in self.parts:
