@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--graph-baseline", action="store_true")
     ap.add_argument("--optimizer", default="sgd", choices=["sgd", "adam"])
+    ap.add_argument("--fused-update", action="store_true", help="all-reduce + SGD + weight multicast in one kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -148,7 +149,8 @@ def main():
                             max_ctas=0)
     lr = 0.1 * world  # LR x world size (reference P1/03:301)
     base_opt = optim.SGD(lr, momentum=0.9, weight_decay=1e-4) if args.optimizer == "sgd" else optim.Adam(1e-3 * world)
-    opt = dist.DistributedOptimizer(base_opt, bucket_mb=args.bucket_mb, algo=args.algo) if world > 1 else base_opt
+    opt = (dist.DistributedOptimizer(base_opt, bucket_mb=args.bucket_mb, algo=args.algo, fused_update=args.fused_update)
+           if world > 1 else base_opt)
     trainer = Trainer(engine, use_graph=not args.no_graph)
     trainer.compile(optimizer=opt, loss="sparse_categorical_crossentropy", metrics=["accuracy"])
     if world > 1:
@@ -223,6 +225,7 @@ def main():
             "config": {"model": "resnet50", "global_batch": global_batch, "per_gpu_batch": args.batch,
                        "image": "224x224x3", "classes": args.classes, "parallelism": f"dp{world}",
                        "optimizer": args.optimizer, "allreduce": getattr(opt, "algo", "none") if world > 1 else "none",
+                       "fused_allreduce_sgd": bool(getattr(opt, "fused_update", False)),
                        "cuda_graph": not args.no_graph,
                        "l2": "activations per step are several GB (>> 126 MB L2); no explicit flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),

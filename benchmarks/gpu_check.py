@@ -172,9 +172,17 @@ def case_elementwise():
         ok &= report(f"bn_finalize_invstd/C{C_}", rel_err(invstd, (vref + 1e-5).rsqrt()), 2e-3)
         ok &= report(f"bn_finalize_zeroed/C{C_}", float(s.abs().max() + q.abs().max()), 0.0)
         out = torch.empty_like(y)
-        e.bn_apply(y, scale, shift, res, None, None, out, True)
+        mask = torch.zeros(M * C_ // 8, device=DEV, dtype=torch.uint8)
+        e.bn_apply(y, scale, shift, res, None, None, out, True, mask)
         ref = torch.relu((yf - mref) * (vref + 1e-5).rsqrt() * gamma + beta + res.float())
         ok &= report(f"bn_apply_relu_res/C{C_}", rel_err(out, ref), 1.5e-2)
+        bits = (out.float() > 0).view(M, C_ // 8, 8).to(torch.int32)
+        packed = (bits * (2 ** torch.arange(8, device=DEV, dtype=torch.int32))).sum(-1).to(torch.uint8).view(-1)
+        ok &= report(f"bn_apply_mask_bits/C{C_}", float((packed != mask).float().mean()), 0.0)
+        s4 = torch.zeros(C_, device=DEV); s4y = torch.zeros(C_, device=DEV); dz4 = torch.empty_like(y)
+        g4 = torch.randn(M, C_, device=DEV, generator=g).to(torch.bfloat16)
+        e.bn_bwd_reduce(4, g4, None, mask, y, None, None, dz4, s4, s4y)
+        ok &= report(f"bn_bwd_reduce_mode4/C{C_}", rel_err(dz4, g4.float() * (out.float() > 0)), 1e-2)
         # backward
         gout = torch.randn(M, C_, device=DEV, generator=g).to(torch.bfloat16)
         sdz = torch.zeros(C_, device=DEV); sdzy = torch.zeros(C_, device=DEV)

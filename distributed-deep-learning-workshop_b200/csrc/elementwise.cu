@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                 const float* __restrict__ res_scale, const float* __restrict__ res_shift,
-                __nv_bfloat16* __restrict__ out, int64_t M, int C) {
+                __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ mask, int64_t M, int C) {
   const int cvec = C / 8;
   const int lanes = cvec < (int)blockDim.x ? cvec : blockDim.x;
   const int rpb = blockDim.x / lanes;
@@ -124,6 +124,12 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
         for (int k = 0; k < 8; ++k) f[k] += q[k];
       }
       if (RELU) {
+        if (mask != nullptr) {  // 1 bit per element: the backward pass reads this instead of the activation
+          uint32_t mbits = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) mbits |= (f[k] > 0.f ? 1u : 0u) << k;
+          mask[r * cvec + cv] = (uint8_t)mbits;
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
       }
@@ -144,14 +150,15 @@ static inline int rows_grid(int64_t M, int C, int threads) {
 }
 
 void bn_apply(const void* y, const float* scale, const float* shift, const void* res, const float* res_scale,
-              const float* res_shift, void* out, int64_t M, int C, bool relu, cudaStream_t s) {
+              const float* res_shift, void* out, void* mask, int64_t M, int C, bool relu, cudaStream_t s) {
   const int threads = 256;
   const int blocks = rows_grid(M, C, threads);
   auto Y = (const __nv_bfloat16*)y;
   auto R = (const __nv_bfloat16*)res;
   auto O = (__nv_bfloat16*)out;
+  auto MK = (uint8_t*)mask;
   const int rmode = res == nullptr ? 0 : (res_scale == nullptr ? 1 : 2);
-#define LAUNCH(RL, RM) bn_apply_kernel<RL, RM><<<blocks, threads, 0, s>>>(Y, scale, shift, R, res_scale, res_shift, O, M, C)
+#define LAUNCH(RL, RM) bn_apply_kernel<RL, RM><<<blocks, threads, 0, s>>>(Y, scale, shift, R, res_scale, res_shift, O, MK, M, C)
   if (relu) {
     if (rmode == 0) LAUNCH(true, 0); else if (rmode == 1) LAUNCH(true, 1); else LAUNCH(true, 2);
   } else {
@@ -166,6 +173,7 @@ void bn_apply(const void* y, const float* scale, const float* shift, const void*
 //   MODE 1: dz = (g1 [+ g2]) * (out > 0)      [dz optionally stored]   -> sum(dz), sum(dz*y)   (block-final BN)
 //   MODE 2: dz = g1 * (y*scale + shift > 0)   (mask recomputed from y) -> sum(dz), sum(dz*y)   (BN + ReLU, no residual)
 //   MODE 3: dz = g1                                                     -> sum(dz), sum(dz*y)   (BN without ReLU)
+//   MODE 4: like MODE 1 but the ReLU mask is the 1-bit/element bitmap written by bn_apply (outp = uint8 [M, C/8])
 template <int MODE>
 __global__ void __launch_bounds__(256)
 col_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g2,
@@ -203,17 +211,23 @@ col_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
       } else {
         float yy[8];
         unpack8(ld8(y + off), yy);
-        if (MODE == 1) {
+        if (MODE == 1 || MODE == 4) {
           if (g2 != nullptr) {
             float h[8];
             unpack8(ld8(g2 + off), h);
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] += h[k];
           }
-          float o[8];
-          unpack8(ld8(outp + off), o);
+          if (MODE == 1) {
+            float o[8];
+            unpack8(ld8(outp + off), o);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] = o[k] > 0.f ? f[k] : 0.f;
+            for (int k = 0; k < 8; ++k) f[k] = o[k] > 0.f ? f[k] : 0.f;
+          } else {
+            const uint32_t mbits = reinterpret_cast<const uint8_t*>(outp)[r * cvec + cx];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = ((mbits >> k) & 1u) ? f[k] : 0.f;
+          }
           if (dz_out != nullptr) st8(dz_out + off, pack8(f));
         } else if (MODE == 2) {
 #pragma unroll
@@ -269,6 +283,7 @@ static void col_reduce_launch(int mode, const void* a, const void* g2, const voi
     case 0: col_reduce_kernel<0><<<blocks, threads, smem, s>>>(A, G2, O, Y, scale, shift, DZ, r0, r1, M, C); break;
     case 1: col_reduce_kernel<1><<<blocks, threads, smem, s>>>(A, G2, O, Y, scale, shift, DZ, r0, r1, M, C); break;
     case 2: col_reduce_kernel<2><<<blocks, threads, smem, s>>>(A, G2, O, Y, scale, shift, DZ, r0, r1, M, C); break;
+    case 4: col_reduce_kernel<4><<<blocks, threads, smem, s>>>(A, G2, O, Y, scale, shift, DZ, r0, r1, M, C); break;
     default: col_reduce_kernel<3><<<blocks, threads, smem, s>>>(A, G2, O, Y, scale, shift, DZ, r0, r1, M, C); break;
   }
 }

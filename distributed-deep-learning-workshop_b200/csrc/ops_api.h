@@ -9,7 +9,7 @@ void bn_finalize(float* sum, float* sqsum, double count, const float* gamma, con
                  float* running_var, float momentum, float eps, float* mean, float* invstd, float* scale,
                  float* shift, int C, bool training, cudaStream_t s);
 void bn_apply(const void* y, const float* scale, const float* shift, const void* res, const float* res_scale,
-              const float* res_shift, void* out, int64_t M, int C, bool relu, cudaStream_t s);
+              const float* res_shift, void* out, void* mask, int64_t M, int C, bool relu, cudaStream_t s);
 void channel_stats(const void* y, float* sum, float* sqsum, int64_t M, int C, cudaStream_t s);
 void bn_bwd_reduce(int mode, const void* g1, const void* g2, const void* outp, const void* y, const float* scale,
                    const float* shift, void* dz_out, float* sum_dz, float* sum_dzy, int64_t M, int C, cudaStream_t s);

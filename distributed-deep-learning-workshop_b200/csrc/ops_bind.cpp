@@ -35,15 +35,17 @@ void bn_finalize(Tensor sum, Tensor sqsum, double count, Tensor gamma, Tensor be
   after();
 }
 
-void bn_apply(Tensor y, Tensor scale, Tensor shift, OptT res, OptT res_scale, OptT res_shift, Tensor out, bool relu) {
+void bn_apply(Tensor y, Tensor scale, Tensor shift, OptT res, OptT res_scale, OptT res_shift, Tensor out, bool relu,
+              OptT mask) {
   chk(y, at::kBFloat16, "y");
   chk(out, at::kBFloat16, "out");
   const int C = (int)y.size(-1);
   const int64_t M = y.numel() / C;
   TORCH_CHECK(C % 8 == 0 && scale.numel() == C && shift.numel() == C && out.numel() == y.numel());
   if (res.has_value()) { chk(*res, at::kBFloat16, "res"); TORCH_CHECK(res->numel() == y.numel()); }
+  if (mask.has_value()) { chk(*mask, at::kByte, "mask"); TORCH_CHECK(mask->numel() * 8 == y.numel()); }
   b200::bn_apply(y.data_ptr(), scale.data_ptr<float>(), shift.data_ptr<float>(), vp(res), fp(res_scale),
-                 fp(res_shift), out.data_ptr(), M, C, relu, cur());
+                 fp(res_shift), out.data_ptr(), mask.has_value() ? mask->data_ptr() : nullptr, M, C, relu, cur());
   after();
 }
 
@@ -62,8 +64,8 @@ void bn_bwd_reduce(int64_t mode, Tensor g1, OptT g2, OptT outp, Tensor y, OptT s
   chk(y, at::kBFloat16, "y");
   const int C = (int)y.size(-1);
   TORCH_CHECK(C % 8 == 0 && C <= 2048 && g1.numel() == y.numel());
-  TORCH_CHECK(mode >= 1 && mode <= 3);
-  TORCH_CHECK(mode != 1 || outp.has_value(), "mode 1 needs the activation output");
+  TORCH_CHECK(mode >= 1 && mode <= 4);
+  TORCH_CHECK((mode != 1 && mode != 4) || outp.has_value(), "modes 1/4 need the activation output / bitmask");
   TORCH_CHECK(mode != 2 || (scale.has_value() && shift.has_value()), "mode 2 needs scale/shift");
   b200::bn_bwd_reduce((int)mode, g1.data_ptr(), vp(g2), vp(outp), y.data_ptr(), fp(scale), fp(shift),
                       dz_out.has_value() ? dz_out->data_ptr() : nullptr, sum_dz.data_ptr<float>(),
@@ -198,7 +200,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "b200ddl bandwidth-bound sm_100a kernels and fused optimizers";
   m.def("bn_finalize", &bn_finalize);
   m.def("bn_apply", &bn_apply, py::arg("y"), py::arg("scale"), py::arg("shift"), py::arg("res") = c10::nullopt,
-        py::arg("res_scale") = c10::nullopt, py::arg("res_shift") = c10::nullopt, py::arg("out"), py::arg("relu") = true);
+        py::arg("res_scale") = c10::nullopt, py::arg("res_shift") = c10::nullopt, py::arg("out"), py::arg("relu") = true,
+        py::arg("mask") = c10::nullopt);
   m.def("channel_stats", &channel_stats);
   m.def("bn_bwd_reduce", &bn_bwd_reduce);
   m.def("bn_bwd_coeffs", &bn_bwd_coeffs);

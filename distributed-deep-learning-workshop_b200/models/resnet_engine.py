@@ -307,6 +307,8 @@ class ResNet50Engine:
             A[b.name + ".a2"] = torch.zeros(N, Ho, Ho, mid, **bf)
             A[b.name + ".y3"] = torch.zeros(N, Ho, Ho, cout, **bf)
             A[b.name + ".out"] = torch.zeros(N, Ho, Ho, cout, **bf)
+            if training:  # 1 bit per element ReLU mask of the block output (read by the backward pass)
+                A[b.name + ".mask"] = torch.zeros(N * Ho * Ho * cout // 8, device=dev, dtype=torch.uint8)
             if b.downsample:
                 A[b.name + ".yd"] = torch.zeros(N, Ho, Ho, cout, **bf)
             convs = [("conv1", x_in, "y1", "bn1", 1, 1, 0), ("conv2", A[b.name + ".a1"], "y2", "bn2", 3, b.stride, 1),
@@ -387,9 +389,10 @@ class ResNet50Engine:
                 self._fwd[n + ".downsample.0"].run()
                 wd = self._bn_fwd(n + ".downsample.1", cnt_out, training)
                 e.bn_apply(A[n + ".y3"], w3["scale"], w3["shift"], A[n + ".yd"], wd["scale"], wd["shift"],
-                           A[n + ".out"], True)
+                           A[n + ".out"], True, A.get(n + ".mask") if training else None)
             else:
-                e.bn_apply(A[n + ".y3"], w3["scale"], w3["shift"], x_in, None, None, A[n + ".out"], True)
+                e.bn_apply(A[n + ".y3"], w3["scale"], w3["shift"], x_in, None, None, A[n + ".out"], True,
+                           A.get(n + ".mask") if training else None)
             x_in = A[n + ".out"]
         drop = self.dropout if training else 0.0
         self._drop_seed = self.seed * 1000003 + self._step_count
@@ -416,7 +419,8 @@ class ResNet50Engine:
         mode 3: BN without ReLU (downsample branch): dz = g1."""
         e, w = self._e, self.bnw[bn]
         if mode == 1:
-            e.bn_bwd_reduce(1, g1, g2, out, y, None, None, dz, w["sum_dz"], w["sum_dzy"])
+            # `out` is the 1-bit ReLU mask written by the forward pass (reduce mode 4)
+            e.bn_bwd_reduce(4, g1, g2, out, y, None, None, dz, w["sum_dz"], w["sum_dzy"])
         elif mode == 2:
             e.bn_bwd_reduce(2, g1, None, None, y, w["scale"], w["shift"], None, w["sum_dz"], w["sum_dzy"])
         else:
@@ -456,7 +460,7 @@ class ResNet50Engine:
             y3, out = A[n + ".y3"], A[n + ".out"]
             dy3 = self._scr["dy"][:y3.numel()].view(y3.shape)
             dz = self._scr[dz_keys[bi % 2]][:y3.numel()].view(y3.shape)
-            self._bn_bwd(n + ".bn3", 1, g1, g2, out, y3, dy3, dz, cnt_out)
+            self._bn_bwd(n + ".bn3", 1, g1, g2, A[n + ".mask"], y3, dy3, dz, cnt_out)
             self._wg[n + ".conv3"].run()
             self._ready(n + ".conv3.weight")
             self._dg[n + ".conv3"].run()  # -> da (a2-shaped)
@@ -570,6 +574,9 @@ class EngineTrainStep:
         if self._dist:
             grads = optimizer.allocate_grads(e.flat_numel, e.device)
             e.bind_grad_buffer(grads)
+            if getattr(optimizer, "fused_update", False):
+                # fused all-reduce + SGD: master weights and the bf16 copy move to symmetric/multicast memory
+                e.params, e.w16 = optimizer.allocate_weights(e.params, e.w16)
             optimizer.attach(e.params, ranges, e.w16, grads)
             e.grad_hook = optimizer.on_grads_ready
         else:

@@ -35,13 +35,19 @@ class DistributedOptimizer:
     """Wraps a fused flat optimizer; averages gradients over all ranks before every update."""
 
     def __init__(self, optimizer: FlatOptimizer, bucket_mb: float = 16.0, overlap: bool = True, algo: str = "auto",
-                 comm_blocks: int = 16, average: bool = True):
+                 comm_blocks: int = 16, average: bool = True, fused_update: bool = False):
         self.opt = optimizer
         self.bucket_bytes = int(bucket_mb * 2 ** 20)
         self.overlap = overlap
         self.algo = algo
         self.comm_blocks = comm_blocks
         self.average = average
+        # fused_update: reduce-scatter + SGD-momentum update of my 1/N slice + multicast of the new fp32/bf16 weights
+        # in ONE kernel per bucket (csrc/allreduce.cu: allreduce_sgd_nvls); optimizer state is sharded over ranks.
+        self.fused_update = fused_update
+        self._wsym = None
+        self._w16sym = None
+        self._wcomm = None
         self.world = core.size()
         self.rank = core.rank()
         self.buckets: List[_Bucket] = []
@@ -91,6 +97,26 @@ class DistributedOptimizer:
             self._comm_stream = torch.cuda.Stream(device=device, priority=-1)
         return self.grads
 
+    def allocate_weights(self, params: torch.Tensor, w16: Optional[torch.Tensor]):
+        """fused_update only: move the fp32 master (and bf16 copy) into symmetric + multicast memory.  Returns the
+        (params, w16) tensors the model must use from now on, or the inputs unchanged when fusion is unavailable."""
+        ok = (self.fused_update and self.world > 1 and params.is_cuda and self._sym is not None
+              and self._sym.has_multicast and getattr(self.opt, "name", "") == "SGD" and not self.opt.nesterov)
+        if not ok:
+            self.fused_update = False
+            return params, w16
+        from . import symm
+
+        self._wsym = symm.SymmetricBuffer(params.numel(), torch.float32, params.device)
+        self._wsym.tensor.copy_(params)
+        self._wcomm = symm.make_comm(self._wsym)
+        new_w16 = w16
+        if w16 is not None:
+            self._w16sym = symm.SymmetricBuffer(w16.numel(), torch.bfloat16, w16.device)
+            self._w16sym.tensor.copy_(w16)
+            new_w16 = self._w16sym.tensor
+        return self._wsym.tensor, new_w16
+
     def attach(self, params: torch.Tensor, spec_ranges: List[Tuple[int, int]], w16: Optional[torch.Tensor] = None,
                grads: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Bind flat params; build buckets from the per-parameter [lo, hi) ranges (in readiness order)."""
@@ -136,7 +162,16 @@ class DistributedOptimizer:
     def _reduce_bucket(self, b: _Bucket) -> None:
         n = b.hi - b.lo
         scale = (1.0 / self.world) if self.average else 1.0
-        if self.algo in ("nvls", "p2p", "oneshot"):
+        if self.fused_update:
+            cs = self._comm_stream
+            cs.wait_stream(torch.cuda.current_stream())
+            span = (self.timeline.device_span(f"allreduce+sgd[{b.lo}:{b.hi}]", "comm", stream=cs)
+                    if self.timeline is not None else contextlib.nullcontext())
+            with torch.cuda.stream(cs), span:
+                self._comm.allreduce_sgd(self._wcomm, b.lo, n, self.opt.state["momentum"],
+                                         self._w16sym.mc_ptr if self._w16sym is not None else 0, scale,
+                                         self.opt._hyper, self.comm_blocks)
+        elif self.algo in ("nvls", "p2p", "oneshot"):
             cs = self._comm_stream
             cs.wait_stream(torch.cuda.current_stream())
             span = (self.timeline.device_span(f"allreduce[{b.lo}:{b.hi}] {self.algo}", "comm", stream=cs)
@@ -179,7 +214,8 @@ class DistributedOptimizer:
 
     def step(self) -> None:
         self.finish_backward()
-        self.opt.step()
+        if not self.fused_update:
+            self.opt.step()  # fused_update: the per-bucket kernels already updated and broadcast the weights
 
     # -- utilities -----------------------------------------------------------------------------------------
     def broadcast_parameters(self, params: torch.Tensor, root: int = 0) -> None:
