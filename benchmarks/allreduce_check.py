@@ -48,6 +48,7 @@ def time_op(fn, iters, warmup=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--medium", action="store_true", help="1 KB, 64 KB, 1 MB, 16 MB, 128 MB, 1 GB")
     ap.add_argument("--max-mb", type=float, default=1024.0)
     ap.add_argument("--out", default="gpurun_out")
     args = ap.parse_args()
@@ -62,6 +63,8 @@ def main():
         print(f"world={world} multicast={'yes' if buf.has_multicast else 'no'} buffer={max_bytes / 2**20:.0f} MiB", flush=True)
     if args.quick:
         sizes = [4096, 1 << 20, 32 << 20]
+    elif args.medium:
+        sizes = [s for s in (1 << 10, 1 << 16, 1 << 20, 1 << 24, 1 << 27, 1 << 30) if s <= max_bytes]
     else:
         sizes = [1 << k for k in range(10, 31, 2) if (1 << k) <= max_bytes]  # 1 KB .. 1 GB, x4
     ok_all = True
