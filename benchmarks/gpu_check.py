@@ -485,6 +485,26 @@ def case_stem():
     return ok
 
 
+def case_umma_probe():
+    """Row-shifted SWIZZLE_128B descriptors: which (shift, base_offset) combinations read the right rows?"""
+    ext = ops.ext("_b200_conv")
+    g = torch.Generator(device=DEV).manual_seed(21)
+    T = torch.randn(160, 64, device=DEV, generator=g).to(torch.bfloat16)
+    B = torch.randn(64, 64, device=DEV, generator=g).to(torch.bfloat16)
+    ok0 = True
+    for shift in (0, 1, 2, 3, 7, 8, 9, 30):
+        ref = T[shift:shift + 128].float() @ B.float().t()
+        res = []
+        for bo in (False, True):
+            out = ext.umma_probe(T, B, shift, bo)
+            torch.cuda.synchronize()
+            res.append(rel_err(out, ref))
+        print(f"PROBE shift={shift:2d} err(base_offset=0)={res[0]:.3e} err(base_offset=(addr>>7)&7)={res[1]:.3e}", flush=True)
+        if shift == 0:
+            ok0 &= res[0] < 1e-2
+    return ok0
+
+
 CASES = {
     "conv_fwd": case_conv_fwd,
     "conv_dgrad": case_conv_dgrad,
@@ -493,6 +513,7 @@ CASES = {
     "conv_time": case_conv_time,
     "engine": case_engine,
     "stem": case_stem,
+    "umma_probe": case_umma_probe,
 }
 
 if __name__ == "__main__":

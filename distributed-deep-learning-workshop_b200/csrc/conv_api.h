@@ -38,5 +38,7 @@ struct StemPlanRaw {
 };
 void stem_fwd_launch(const StemPlanRaw& plan, cudaStream_t stream);
 void stem_wgrad_launch(const StemPlanRaw& plan, cudaStream_t stream);
+void umma_probe_launch(const CUtensorMap& tmT, const CUtensorMap& tmB, float* out, int shift, int use_base_offset,
+                       cudaStream_t s);
 
 }  // namespace b200

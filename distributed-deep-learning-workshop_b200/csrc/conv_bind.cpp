@@ -297,6 +297,18 @@ struct StemPlan {
   }
 };
 
+// hardware probe (see csrc/umma_probe.cu): T [160, 64] bf16, B [64, 64] bf16 -> out fp32 [128, 64]
+static at::Tensor umma_probe(at::Tensor T, at::Tensor B, int64_t shift, bool use_base_offset) {
+  TORCH_CHECK(T.is_cuda() && T.scalar_type() == at::kBFloat16 && T.is_contiguous() && T.size(0) == 160 && T.size(1) == 64);
+  TORCH_CHECK(B.is_cuda() && B.scalar_type() == at::kBFloat16 && B.is_contiguous() && B.size(0) == 64 && B.size(1) == 64);
+  TORCH_CHECK(shift >= 0 && shift <= 32);
+  auto out = at::zeros({128, 64}, T.options().dtype(at::kFloat));
+  CUtensorMap tmT = map_2d(T.data_ptr(), 160, 64, 64, 64, 160);
+  CUtensorMap tmB = map_2d(B.data_ptr(), 64, 64, 64, 64, 64);
+  umma_probe_launch(tmT, tmB, out.data_ptr<float>(), (int)shift, use_base_offset ? 1 : 0, at::cuda::getCurrentCUDAStream());
+  return out;
+}
+
 }  // namespace b200
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -324,6 +336,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_property_readonly("grid", &b200::WgradPlan::grid)
       .def_property_readonly("units", &b200::WgradPlan::units)
       .def_property_readonly("stages", &b200::WgradPlan::stages);
+  m.def("umma_probe", &b200::umma_probe);
   py::class_<b200::StemPlan>(m, "StemPlan")
       .def(py::init<at::Tensor, c10::optional<at::Tensor>, at::Tensor, c10::optional<at::Tensor>,
                     c10::optional<at::Tensor>, c10::optional<at::Tensor>, double, double, int64_t>(),
