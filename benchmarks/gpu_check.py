@@ -120,6 +120,22 @@ def case_conv_dgrad():
             ref = torch.nn.grad.conv2d_input((N, cin, H, W), wt, dy.float().permute(0, 3, 1, 2), stride=stride,
                                              padding=pad).permute(0, 2, 3, 1)
             ok &= report(f"conv_dgrad/{name}", rel_err(dx, ref), 1.5e-2, f"parts={len(op.parts)}")
+            if stride == 1:
+                # fused BatchNorm-backward reduction in the dgrad epilogue
+                yb = torch.randn(N, H, W, cin, device=DEV, generator=g).to(torch.bfloat16)
+                sc = torch.rand(cin, device=DEV, generator=g) + 0.5
+                sh = torch.randn(cin, device=DEV, generator=g) * 0.5
+                s_dz = torch.zeros(cin, device=DEV); s_dzy = torch.zeros(cin, device=DEV)
+                dx2 = torch.empty_like(dx)
+                op2 = C.ConvDgrad(dy, w, dx2, R, R, stride, pad, bwd_stats=(yb, sc, sh, s_dz, s_dzy))
+                op2.run()
+                torch.cuda.synchronize()
+                mask = (yb.float() * sc + sh) > 0
+                dzr = dx2.float() * mask
+                ok &= report(f"conv_dgrad_fused_dx/{name}", rel_err(dx2, ref), 1.5e-2)
+                ok &= report(f"conv_dgrad_fused_sum_dz/{name}", float((s_dz - dzr.sum((0, 1, 2))).abs().max() / (dzr.sum((0, 1, 2)).abs().max() + 1e-6)), 2e-3)
+                r2 = (dzr * yb.float()).sum((0, 1, 2))
+                ok &= report(f"conv_dgrad_fused_sum_dzy/{name}", float((s_dzy - r2).abs().max() / (r2.abs().max() + 1e-6)), 2e-3)
         except Exception:
             ok = False
             print(f"CHECK conv_dgrad/{name} EXCEPTION FAIL\n{traceback.format_exc()}", flush=True)

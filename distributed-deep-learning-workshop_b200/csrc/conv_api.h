@@ -12,10 +12,11 @@ struct ConvPlanRaw {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
   CUtensorMap tmD;
+  CUtensorMap tmY;  // stats mode 2: pre-BN tensor on the output's geometry
   ConvParams p;
   int block_n;
   int grid;
-  bool stats;
+  int stats;  // 0 none, 1 forward BN statistics, 2 fused BN-backward reduction
 };
 
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1; SWIZZLE_128B, zero OOB fill.

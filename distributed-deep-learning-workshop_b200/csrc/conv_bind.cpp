@@ -47,7 +47,8 @@ struct ConvPlan {
   // tap_map/dw/dh: per tap view index + pixel offset;  bw/bh/bn: pixel box (0 => flat 1x1 mode)
   ConvPlan(std::vector<at::Tensor> views, at::Tensor weight, at::Tensor out, std::vector<int64_t> tap_map,
            std::vector<int64_t> tap_dw, std::vector<int64_t> tap_dh, int64_t bw, int64_t bh, int64_t bn,
-           c10::optional<at::Tensor> stat_sum, c10::optional<at::Tensor> stat_sqsum, int64_t max_ctas) {
+           c10::optional<at::Tensor> stat_sum, c10::optional<at::Tensor> stat_sqsum, int64_t max_ctas,
+           c10::optional<at::Tensor> bwd_y, c10::optional<at::Tensor> bn_scale, c10::optional<at::Tensor> bn_shift) {
     TORCH_CHECK(!views.empty() && views.size() <= 4, "1..4 input views");
     for (auto& v : views) check_nhwc_view(v, "input view");
     check_nhwc_view(out, "out");
@@ -109,7 +110,23 @@ struct ConvPlan {
     }
     raw.tmB = map_2d(weight.data_ptr(), taps * cout, cin, cin, 64, raw.block_n);
     p.num_tiles = p.m_tiles * p.n_blocks;
-    raw.stats = stat_sum.has_value();
+    raw.stats = stat_sum.has_value() ? (bwd_y.has_value() ? 2 : 1) : 0;
+    raw.tmY = raw.tmD;
+    if (raw.stats == 2) {
+      // fused BatchNorm-backward reduction: y has exactly the output's shape / layout
+      TORCH_CHECK(bn_scale.has_value() && bn_shift.has_value(), "bwd stats need the forward BN scale/shift");
+      check_nhwc_view(*bwd_y, "bwd_y");
+      TORCH_CHECK(bwd_y->sizes() == out.sizes() && bwd_y->strides() == out.strides(), "bwd_y must match the output");
+      TORCH_CHECK(bn_scale->scalar_type() == at::kFloat && bn_shift->scalar_type() == at::kFloat &&
+                  bn_scale->numel() >= cout && bn_shift->numel() >= cout);
+      p.bn_scale = bn_scale->data_ptr<float>();
+      p.bn_shift = bn_shift->data_ptr<float>();
+      if (bw == 0) raw.tmY = map_2d(bwd_y->data_ptr(), N * Ho * Wo, cout, cout, 64, kBlockM);
+      else raw.tmY = map_nhwc(*bwd_y, 64, (int)bw, (int)bh, (int)bn);
+      keep.push_back(*bwd_y);
+      keep.push_back(*bn_scale);
+      keep.push_back(*bn_shift);
+    }
     if (raw.stats) {
       TORCH_CHECK(stat_sqsum.has_value());
       TORCH_CHECK(stat_sum->is_cuda() && stat_sum->scalar_type() == at::kFloat && stat_sum->numel() >= cout);
@@ -141,7 +158,7 @@ struct WgradPlan {
   // dy: NHWC view (N, Ho, Wo, Cout) bf16;  views: input views on the same pixel grid;  dw: fp32 [taps*Cout, Cin]
   WgradPlan(at::Tensor dy, std::vector<at::Tensor> views, at::Tensor dw, int64_t R, int64_t S,
             std::vector<int64_t> tap_map, std::vector<int64_t> tap_dw, std::vector<int64_t> tap_dh, int64_t bw,
-            int64_t bh, int64_t bn, int64_t px_chunks, int64_t max_ctas) {
+            int64_t bh, int64_t bn, int64_t px_chunks, int64_t max_ctas, int64_t smem_budget) {
     check_nhwc_view(dy, "dy");
     TORCH_CHECK(!views.empty() && views.size() <= 4);
     for (auto& v : views) check_nhwc_view(v, "input view");
@@ -209,7 +226,9 @@ struct WgradPlan {
       }
     }
     const int stage_bytes = (p.a_chunks + p.G) * p.P * 128;
-    p.stages = (232448 - 256) / stage_bytes;
+    // smem_budget < 227 KB leaves room for bandwidth-bound kernels to co-reside when wgrad runs on a side stream
+    const int budget = (smem_budget > 0 && smem_budget < 232448) ? (int)smem_budget : 232448;
+    p.stages = (budget - 256) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     TORCH_CHECK(p.stages >= 2, "wgrad stage does not fit shared memory");
     const int combos = p.co_blocks * p.groups;
@@ -317,20 +336,22 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   py::class_<b200::ConvPlan>(m, "ConvPlan")
       .def(py::init<std::vector<at::Tensor>, at::Tensor, at::Tensor, std::vector<int64_t>, std::vector<int64_t>,
                     std::vector<int64_t>, int64_t, int64_t, int64_t, c10::optional<at::Tensor>,
-                    c10::optional<at::Tensor>, int64_t>(),
+                    c10::optional<at::Tensor>, int64_t, c10::optional<at::Tensor>, c10::optional<at::Tensor>,
+                    c10::optional<at::Tensor>>(),
            py::arg("views"), py::arg("weight"), py::arg("out"), py::arg("tap_map"), py::arg("tap_dw"),
            py::arg("tap_dh"), py::arg("bw"), py::arg("bh"), py::arg("bn"), py::arg("stat_sum") = c10::nullopt,
-           py::arg("stat_sqsum") = c10::nullopt, py::arg("max_ctas") = 0)
+           py::arg("stat_sqsum") = c10::nullopt, py::arg("max_ctas") = 0, py::arg("bwd_y") = c10::nullopt,
+           py::arg("bn_scale") = c10::nullopt, py::arg("bn_shift") = c10::nullopt)
       .def("run", &b200::ConvPlan::run)
       .def_readonly("launches", &b200::ConvPlan::launches)
       .def_property_readonly("grid", &b200::ConvPlan::grid)
       .def_property_readonly("block_n", &b200::ConvPlan::block_n);
   py::class_<b200::WgradPlan>(m, "WgradPlan")
       .def(py::init<at::Tensor, std::vector<at::Tensor>, at::Tensor, int64_t, int64_t, std::vector<int64_t>,
-                    std::vector<int64_t>, std::vector<int64_t>, int64_t, int64_t, int64_t, int64_t, int64_t>(),
+                    std::vector<int64_t>, std::vector<int64_t>, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t>(),
            py::arg("dy"), py::arg("views"), py::arg("dw"), py::arg("R"), py::arg("S"), py::arg("tap_map"),
            py::arg("tap_dw"), py::arg("tap_dh"), py::arg("bw"), py::arg("bh"), py::arg("bn"),
-           py::arg("px_chunks") = 0, py::arg("max_ctas") = 0)
+           py::arg("px_chunks") = 0, py::arg("max_ctas") = 0, py::arg("smem_budget") = 0)
       .def("run", &b200::WgradPlan::run)
       .def_readonly("launches", &b200::WgradPlan::launches)
       .def_property_readonly("grid", &b200::WgradPlan::grid)

@@ -55,30 +55,32 @@ CUtensorMap encode_bf16(void* ptr, int rank, const uint64_t* dims, const uint64_
 }
 
 
-template <int BN, bool ST>
+template <int BN, int ST>
 static void launch_t(const ConvPlanRaw& pl, cudaStream_t s) {
   auto kern = conv_igemm_kernel<BN, ST>;
+  using L = ConvSmem<BN, ST>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<BN>::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) throw std::runtime_error(std::string("conv_igemm: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
-  kern<<<pl.grid, ST ? 384 : 256, ConvSmem<BN>::kTotal, s>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmA[3], pl.tmB, pl.tmD, pl.p);
+  kern<<<pl.grid, ST ? 384 : 256, L::kTotal, s>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmA[3], pl.tmB, pl.tmD, pl.tmY, pl.p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("conv_igemm launch: ") + cudaGetErrorString(e));
 }
 
+template <int ST>
+static void launch_n(const ConvPlanRaw& pl, cudaStream_t s) {
+  if (pl.block_n == 256) launch_t<256, ST>(pl, s);
+  else if (pl.block_n == 128) launch_t<128, ST>(pl, s);
+  else launch_t<64, ST>(pl, s);
+}
+
 void conv_plan_launch(const ConvPlanRaw& pl, cudaStream_t s) {
-  if (pl.stats) {
-    if (pl.block_n == 256) launch_t<256, true>(pl, s);
-    else if (pl.block_n == 128) launch_t<128, true>(pl, s);
-    else launch_t<64, true>(pl, s);
-  } else {
-    if (pl.block_n == 256) launch_t<256, false>(pl, s);
-    else if (pl.block_n == 128) launch_t<128, false>(pl, s);
-    else launch_t<64, false>(pl, s);
-  }
+  if (pl.stats == 1) launch_n<1>(pl, s);
+  else if (pl.stats == 2) launch_n<2>(pl, s);
+  else launch_n<0>(pl, s);
 }
 
 }  // namespace b200

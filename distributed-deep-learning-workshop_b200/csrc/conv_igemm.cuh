@@ -22,26 +22,30 @@
 
 namespace b200 {
 
-template <int BLOCK_N>
+// kStats: 0 = plain epilogue, 1 = forward BatchNorm statistics (sum y, sum y^2), 2 = BatchNorm-backward reduction
+// fused into a dgrad GEMM: the output tile is g = dL/d(activation); with the activation's pre-BN tensor y (extra TMA
+// load per chunk) the statistics warps accumulate sum(dz), sum(dz*y) for dz = g * [y*scale + shift > 0].
+template <int BLOCK_N, int kStats = 0>
 struct ConvSmem {
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 5 : 6);
+  static constexpr int kStages = (BLOCK_N == 256) ? (kStats == 2 ? 3 : 4) : (BLOCK_N == 128 ? 5 : 6);
+  static constexpr int kYBytes = kStats == 2 ? 2 * kBlockM * 128 : 0;  // two 128x64 bf16 tiles of y
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = 2 * kBlockM * 128;  // two 128x64 bf16 store buffers
   static constexpr int kBarBytes = 256;
   static constexpr int kStatBytes = 2 * BLOCK_N * 4;
-  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + kStatBytes;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kYBytes + kBarBytes + kStatBytes;
   static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
 };
 
-template <int BLOCK_N, bool kStats>
+template <int BLOCK_N, int kStats>
 __global__ void __launch_bounds__(kStats ? 384 : 256, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
-                  const __grid_constant__ ConvParams p) {
-  using L = ConvSmem<BLOCK_N>;
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ ConvParams p) {
+  using L = ConvSmem<BLOCK_N, kStats>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 
@@ -51,12 +55,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * L::kABytes;
   uint8_t* sStage = smem + kStages * L::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + L::kStagingBytes);
+  uint8_t* sY = sStage + L::kStagingBytes;  // kStats == 2 only
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + L::kYBytes);
   uint64_t* full_bar = bars;                     // [kStages]
   uint64_t* empty_bar = bars + kStages;          // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;      // [2]
   uint64_t* tempty_bar = bars + 2 * kStages + 2; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* y_bar = bars + 2 * kStages + 4;      // [2] (kStats == 2)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
   float* sStat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::kBarBytes);  // [2][BLOCK_N]
 
   const int warp = threadIdx.x >> 5;
@@ -73,11 +79,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
+      mbar_init(&y_bar[i], 1);
     }
     fence_barrier_init();
   }
   if (kStats) {
     for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) sStat[i] = 0.f;
+  }
+  if (kStats == 2) {
+    // rows past the pixel box are never written by TMA: keep them finite (0 * NaN would poison the sums)
+    for (int i = threadIdx.x; i < L::kYBytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(sY)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemCols);
@@ -194,6 +206,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           named_bar_sync(4 + (chunk_ctr & 1), 256);  // ... and the statistics warps are done reading it
         else
           named_bar_sync(1, 128);
+        if (kStats == 2 && etid == 0) {
+          // pre-BN tensor tile for the fused BatchNorm-backward reduction (same pixels / channels as the output tile)
+          const int b = chunk_ctr & 1;
+          mbar_arrive_expect_tx(&y_bar[b], static_cast<uint32_t>(p.valid_rows) * 128u);
+          if (p.mode == 0)
+            tma_load_2d(sY + b * (kBlockM * 128), &tmY, &y_bar[b], nb * BLOCK_N + c64 * 64, m_tile * kBlockM);
+          else
+            tma_load_4d(sY + b * (kBlockM * 128), &tmY, &y_bar[b], nb * BLOCK_N + c64 * 64, w0, h0, n0);
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t r[32];
@@ -264,15 +285,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const uint8_t* sbuf = sStage + b * (kBlockM * 128);
         named_bar_sync(6 + b, 256);
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        if (kStats == 1) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + xoff[i & 7] + i * 128);
-          const float lo = __uint_as_float(w << 16);
-          const float hi = __uint_as_float(w & 0xFFFF0000u);
-          s0 += lo;
-          s1 += hi;
-          q0 = fmaf(lo, lo, q0);
-          q1 = fmaf(hi, hi, q1);
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + xoff[i & 7] + i * 128);
+            const float lo = __uint_as_float(w << 16);
+            const float hi = __uint_as_float(w & 0xFFFF0000u);
+            s0 += lo;
+            s1 += hi;
+            q0 = fmaf(lo, lo, q0);
+            q1 = fmaf(hi, hi, q1);
+          }
+        } else {
+          // dz = g * [y*scale + shift > 0];  accumulate sum(dz) and sum(dz * y)
+          const int col = nb * BLOCK_N + c64 * 64 + cp * 2;
+          const float sc0 = p.bn_scale[col], sc1 = p.bn_scale[col + 1];
+          const float sh0 = p.bn_shift[col], sh1 = p.bn_shift[col + 1];
+          const uint8_t* ybuf = sY + b * (kBlockM * 128);
+          mbar_wait(&y_bar[b], (chunk_ctr >> 1) & 1);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + xoff[i & 7] + i * 128);
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(ybuf + xoff[i & 7] + i * 128);
+            const float y0 = __uint_as_float(v << 16), y1 = __uint_as_float(v & 0xFFFF0000u);
+            const float g0 = fmaf(y0, sc0, sh0) > 0.f ? __uint_as_float(w << 16) : 0.f;
+            const float g1 = fmaf(y1, sc1, sh1) > 0.f ? __uint_as_float(w & 0xFFFF0000u) : 0.f;
+            s0 += g0;
+            s1 += g1;
+            q0 = fmaf(g0, y0, q0);
+            q1 = fmaf(g1, y1, q1);
+          }
         }
         named_bar_arrive(4 + b, 256);  // done reading the staging buffer
         acc[c64][0] += s0;

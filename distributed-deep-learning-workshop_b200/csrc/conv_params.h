@@ -22,8 +22,10 @@ struct ConvParams {
   int8_t tap_map[kMaxTaps];  // which A tensor map the tap reads
   int8_t tap_dw[kMaxTaps];   // coordinate offsets (in the view's pixel grid)
   int8_t tap_dh[kMaxTaps];
-  float* stat_sum;    // [Cout] or nullptr
-  float* stat_sqsum;  // [Cout] or nullptr
+  float* stat_sum;    // [Cout] or nullptr   (mode 2: sum dz)
+  float* stat_sqsum;  // [Cout] or nullptr   (mode 2: sum dz*y)
+  const float* bn_scale;  // mode 2: forward BN affine of the activation whose gradient this GEMM produces
+  const float* bn_shift;
 };
 
 // Weight-gradient GEMM:  dW[tap][co][ci] += sum_px dY[px, co] * X_tap[px, ci]

@@ -84,10 +84,19 @@ class ResNet50Engine:
 
     def __init__(self, batch: int, num_classes: int = 1000, device: Optional[torch.device] = None,
                  image_size: int = 224, dropout: float = 0.0, bn_momentum: float = 0.1, bn_eps: float = 1e-5,
-                 seed: int = 0, max_ctas: int = 0, zero_init_residual: bool = True, native_stem: bool = True):
+                 seed: int = 0, max_ctas: int = 0, zero_init_residual: bool = True, native_stem: bool = True,
+                 overlap_wgrad: bool = False, wgrad_smem_budget: int = 0, fuse_bwd_reduce: bool = True):
         ops.require_native()
         self.zero_init_residual = zero_init_residual
         self.native_stem = native_stem
+        # experimental: run every weight-gradient GEMM on a side stream so it overlaps the (DRAM-bound) BatchNorm
+        # backward passes of the next layer; needs two dy scratch buffers and event-ordered buffer reuse
+        self.overlap_wgrad = overlap_wgrad
+        # BatchNorm-backward reductions of bn1/bn2 computed inside the dgrad GEMM that produces their input gradient
+        self.fuse_bwd_reduce = fuse_bwd_reduce
+        self._fused_reduce = set()
+        self.wgrad_smem_budget = wgrad_smem_budget
+        self.aux_streams: List[torch.cuda.Stream] = []
         if image_size % 32:
             raise ValueError("image_size must be a multiple of 32")
         self.batch = int(batch)
@@ -265,7 +274,13 @@ class ResNet50Engine:
         max_act = N * (S // 4) * (S // 4) * 256
         max_act = max(max_act, N * H0 * H0 * 64)
         if training:
-            self._scr = {k: torch.zeros(max_act, **bf) for k in ("dy", "da", "dds", "dzA", "dzB")}
+            self._scr = {k: torch.zeros(max_act, **bf) for k in ("dy", "dyB", "da", "dds", "dzA", "dzB")}
+            self._dy_key = {"conv3": "dy", "conv2": "dyB" if self.overlap_wgrad else "dy", "conv1": "dy",
+                            "downsample.0": "dyB" if self.overlap_wgrad else "dy"}
+            self._dy_reader: Dict[str, torch.cuda.Event] = {}
+            if self.overlap_wgrad:
+                self._wg_stream = torch.cuda.Stream(device=dev)
+                self.aux_streams = [self._wg_stream]
 
         # bf16 dgrad copies ([tap][Cin][Cout]) of every stride-1 filter live in one flat buffer refreshed by ONE kernel
         self._wd_table_rows = []
@@ -323,16 +338,25 @@ class ResNet50Engine:
                 y = A[b.name + "." + yk]
                 self._fwd[full] = C.ConvForward(xin, w2d, y, k, k, stride, pad, bw_["sum"], bw_["sqsum"], mc)
                 if training:
-                    dy = scr("dy", y.shape)
+                    dy = scr(self._dy_key[cname], y.shape)
                     gw = self.g(full + ".weight")
                     self._wg[full] = C.ConvWgrad(dy, xin, gw.view(gw.shape[0] * gw.shape[1], gw.shape[2]), k, k,
-                                                 stride, pad, 0, mc)
+                                                 stride, pad, 0, mc, self.wgrad_smem_budget)
                     dx = scr("dds" if cname == "downsample.0" else "da", xin.shape)
                     wview = None
                     if stride == 1:
                         o, nel = self._wd_off[self.spec[full + ".weight"].offset]
                         wview = self._wd16[o:o + nel]
-                    dgr = C.ConvDgrad(dy, self.p(full + ".weight"), dx, k, k, stride, pad, mc, wbuf=wview)
+                    bwd_stats = None
+                    if self.fuse_bwd_reduce and stride == 1 and cname in ("conv2", "conv3"):
+                        # dx is the gradient of a1 (conv2) / a2 (conv3): fuse the reduction of bn1 / bn2
+                        pbn = "bn1" if cname == "conv2" else "bn2"
+                        pw = self.bnw[b.name + "." + pbn]
+                        py = A[b.name + (".y1" if cname == "conv2" else ".y2")]
+                        bwd_stats = (py, pw["scale"], pw["shift"], pw["sum_dz"], pw["sum_dzy"])
+                        self._fused_reduce.add(b.name + "." + pbn)
+                    dgr = C.ConvDgrad(dy, self.p(full + ".weight"), dx, k, k, stride, pad, mc, wbuf=wview,
+                                      bwd_stats=bwd_stats)
                     self._dg[full] = dgr
                     self._dgrads.append(dgr)
             x_in = A[b.name + ".out"]
@@ -422,7 +446,8 @@ class ResNet50Engine:
             # `out` is the 1-bit ReLU mask written by the forward pass (reduce mode 4)
             e.bn_bwd_reduce(4, g1, g2, out, y, None, None, dz, w["sum_dz"], w["sum_dzy"])
         elif mode == 2:
-            e.bn_bwd_reduce(2, g1, None, None, y, w["scale"], w["shift"], None, w["sum_dz"], w["sum_dzy"])
+            if bn not in self._fused_reduce:  # otherwise the dgrad GEMM that produced g1 already accumulated the sums
+                e.bn_bwd_reduce(2, g1, None, None, y, w["scale"], w["shift"], None, w["sum_dz"], w["sum_dzy"])
         else:
             e.bn_bwd_reduce(3, g1, None, None, y, None, None, None, w["sum_dz"], w["sum_dzy"])
         e.bn_bwd_coeffs(w["sum_dz"], w["sum_dzy"], self.p(bn + ".weight"), w["mean"], w["invstd"], float(count),
@@ -434,6 +459,31 @@ class ResNet50Engine:
         else:
             e.bn_bwd_apply(g1, y, None, None, w["cA"], w["cB"], w["cC"], dy)
         self._ready(bn + ".weight", bn + ".bias")
+
+    def _dy_buf(self, cname: str, shape) -> torch.Tensor:
+        """Scratch view that will receive dy of `cname`; waits for the side-stream wgrad that last read the buffer."""
+        key = self._dy_key[cname]
+        if self.overlap_wgrad and key in self._dy_reader:
+            torch.cuda.current_stream().wait_event(self._dy_reader.pop(key))
+        return self._scr[key][:int(math.prod(shape))].view(shape)
+
+    def _conv_bwd(self, full: str, cname: str) -> None:
+        """dgrad on the compute stream; wgrad either in line or on the side stream once dgrad has been issued."""
+        if not self.overlap_wgrad:
+            self._wg[full].run()
+            self._ready(full + ".weight")
+            self._dg[full].run()
+            return
+        self._dg[full].run()
+        ev = torch.cuda.Event()
+        ev.record()
+        self._wg_stream.wait_event(ev)
+        with torch.cuda.stream(self._wg_stream):
+            self._wg[full].run()
+            done = torch.cuda.Event()
+            done.record()
+        self._dy_reader[self._dy_key[cname]] = done
+        self._ready(full + ".weight")
 
     def backward(self) -> None:
         """dlogits -> every parameter gradient (fp32, written into the flat gradient buffer)."""
@@ -457,41 +507,33 @@ class ResNet50Engine:
             x_in = A[self.blocks[bi - 1].name + ".out"] if bi > 0 else self.p0
             cnt_in = N * b.h_in * b.h_in
             cnt_out = N * b.h_out * b.h_out
-            y3, out = A[n + ".y3"], A[n + ".out"]
-            dy3 = self._scr["dy"][:y3.numel()].view(y3.shape)
+            y3 = A[n + ".y3"]
+            dy3 = self._dy_buf("conv3", y3.shape)
             dz = self._scr[dz_keys[bi % 2]][:y3.numel()].view(y3.shape)
             self._bn_bwd(n + ".bn3", 1, g1, g2, A[n + ".mask"], y3, dy3, dz, cnt_out)
-            self._wg[n + ".conv3"].run()
-            self._ready(n + ".conv3.weight")
-            self._dg[n + ".conv3"].run()  # -> da (a2-shaped)
+            self._conv_bwd(n + ".conv3", "conv3")  # dgrad -> da (a2-shaped)
             da2 = self._scr["da"][:A[n + ".a2"].numel()].view(A[n + ".a2"].shape)
-            y2, a2 = A[n + ".y2"], A[n + ".a2"]
-            dy2 = self._scr["dy"][:y2.numel()].view(y2.shape)
+            y2 = A[n + ".y2"]
+            dy2 = self._dy_buf("conv2", y2.shape)
             self._bn_bwd(n + ".bn2", 2, da2, None, None, y2, dy2, None, cnt_out)
-            self._wg[n + ".conv2"].run()
-            self._ready(n + ".conv2.weight")
-            self._dg[n + ".conv2"].run()  # -> da (a1-shaped)
+            self._conv_bwd(n + ".conv2", "conv2")  # dgrad -> da (a1-shaped)
             y1, a1 = A[n + ".y1"], A[n + ".a1"]
             da1 = self._scr["da"][:a1.numel()].view(a1.shape)
-            dy1 = self._scr["dy"][:y1.numel()].view(y1.shape)
+            dy1 = self._dy_buf("conv1", y1.shape)
             self._bn_bwd(n + ".bn1", 2, da1, None, None, y1, dy1, None, cnt_in)
-            self._wg[n + ".conv1"].run()
-            self._ready(n + ".conv1.weight")
-            self._dg[n + ".conv1"].run()  # -> da (x_in-shaped): main-path gradient of the block input
+            self._conv_bwd(n + ".conv1", "conv1")  # dgrad -> da (x_in-shaped): main-path gradient of the block input
             g1 = self._scr["da"][:x_in.numel()].view(x_in.shape)
             if b.downsample:
                 # the downsample branch receives the same masked gradient dz; its BN has no ReLU
                 yd = A[n + ".yd"]
-                dyd = self._scr["dy"][:yd.numel()].view(yd.shape)
+                dyd = self._dy_buf("downsample.0", yd.shape)
                 self._bn_bwd(n + ".downsample.1", 3, dz, None, None, yd, dyd, None, cnt_out)
-                self._wg[n + ".downsample.0"].run()
-                self._ready(n + ".downsample.0.weight")
-                self._dg[n + ".downsample.0"].run()  # -> dds (x_in-shaped)
+                self._conv_bwd(n + ".downsample.0", "downsample.0")  # dgrad -> dds (x_in-shaped)
                 g2 = self._scr["dds"][:x_in.numel()].view(x_in.shape)
             else:
                 g2 = dz
         # stem
-        da0 = self._scr["dy"][:self.a0.numel()].view(self.a0.shape)
+        da0 = self._dy_buf("conv3", self.a0.shape)  # reuses the (by now idle) "dy" scratch
         e.maxpool_bwd(self.pool_idx, g1, g2, da0)
         dy0 = self._scr["dzA"][:self.y0.numel()].view(self.y0.shape)
         cnt0 = N * self.y0.shape[1] * self.y0.shape[2]
@@ -503,6 +545,9 @@ class ResNet50Engine:
                                              stride=2, padding=3)
             self.g("conv1.weight").view(7, 7, 64, 3).copy_(gw.permute(2, 3, 0, 1))
         self._ready("conv1.weight")
+        if self.overlap_wgrad:
+            torch.cuda.current_stream().wait_stream(self._wg_stream)
+            self._dy_reader.clear()
 
     # ------------------------------------------------------------------------------------------------ utilities
     def set_input(self, x_u8: torch.Tensor, labels: Optional[torch.Tensor] = None) -> None:
@@ -569,6 +614,7 @@ class EngineTrainStep:
         self._dist = hasattr(optimizer, "on_grads_ready")
         if self._dist:
             optimizer.timeline = self.timeline
+            optimizer.extra_wait_streams = engine.aux_streams if engine.aux_streams else []
         e = engine
         ranges = [(s.offset, s.offset + _align(s.numel)) for s in e.param_specs]
         if self._dist:
@@ -583,6 +629,8 @@ class EngineTrainStep:
             e.bind_grad_buffer()
             optimizer.attach(e.params, e.grads, e.w16)
         e.build(training=True)
+        if self._dist:
+            optimizer.extra_wait_streams = list(e.aux_streams)
         self._warmup_steps = warmup_steps
         self._host_stats = torch.zeros(2, dtype=torch.float32).pin_memory()
         self.steps = 0

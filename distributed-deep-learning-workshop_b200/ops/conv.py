@@ -128,9 +128,12 @@ class ConvDgrad:
     needs are (re)built by :meth:`refresh_weights` (cheap: filters are tiny next to activations)."""
 
     def __init__(self, dy: torch.Tensor, w_master: torch.Tensor, dx: torch.Tensor, R: int, S: int, stride: int = 1,
-                 pad: int = 0, max_ctas: int = 0, wbuf: Optional[torch.Tensor] = None):
+                 pad: int = 0, max_ctas: int = 0, wbuf: Optional[torch.Tensor] = None, bwd_stats=None):
+        """``bwd_stats=(y, scale, shift, sum_dz, sum_dzy)`` (stride 1 only) fuses the BatchNorm-backward reduction of
+        the activation this gradient belongs to into the GEMM epilogue: dz = dx * [y*scale+shift > 0]."""
         ext = _build.load("_b200_conv")
         self.R, self.S, self.stride, self.pad = R, S, stride, pad
+        self.fused_bwd_stats = bwd_stats is not None and stride == 1
         self.w_master = w_master
         self.external_wbuf = wbuf is not None  # owner refreshes it (e.g. one batched kernel for all layers)
         taps_total, cout, cin = w_master.shape
@@ -155,7 +158,11 @@ class ConvDgrad:
                 wbuf = wbuf.view(len(idx) * cin, cout)
             flat = (R == 1 and S == 1 and pad == 0 and dy.is_contiguous() and dx.is_contiguous())
             box = (0, 0, 0) if flat else pick_box(N, dx.shape[1], dx.shape[2])
-            plan = ext.ConvPlan([dy], wbuf, dx, tm, dw, dh, box[0], box[1], box[2], None, None, max_ctas)
+            if self.fused_bwd_stats:
+                y, sc, sh, s_dz, s_dzy = bwd_stats
+                plan = ext.ConvPlan([dy], wbuf, dx, tm, dw, dh, box[0], box[1], box[2], s_dz, s_dzy, max_ctas, y, sc, sh)
+            else:
+                plan = ext.ConvPlan([dy], wbuf, dx, tm, dw, dh, box[0], box[1], box[2], None, None, max_ctas)
             _plans.add(plan)
             self.parts.append((plan, wbuf, idx))
         else:
@@ -208,7 +215,7 @@ class ConvWgrad:
     """dw[t, co, ci] += sum_px dy[px, co] * x_t[px, ci]  (fp32 accumulation with vector atomics; zero dw first)."""
 
     def __init__(self, dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, R: int, S: int, stride: int = 1,
-                 pad: int = 0, px_chunks: int = 0, max_ctas: int = 0):
+                 pad: int = 0, px_chunks: int = 0, max_ctas: int = 0, smem_budget: int = 0):
         ext = _build.load("_b200_conv")
         taps = make_taps(x, R, S, stride, pad)
         N, Ho, Wo, _ = dy.shape
@@ -222,11 +229,13 @@ class ConvWgrad:
             cb = cin // 64
             g = S * (2 if (cb >= 2 and S * 2 <= 6) else 1) if S > 1 else max(d for d in (1, 2, 3, 4) if cb % d == 0)
             chunks = (1 if cout == 64 else 2) + g
-            rows = min(128, (232192 // (3 * chunks * 128)) // 16 * 16)
+            budget = smem_budget if 0 < smem_budget < 232448 else 232448
+            want_stages = 3 if budget >= 200000 else 2
+            rows = min(128, ((budget - 256) // (want_stages * chunks * 128)) // 16 * 16)
             bw, bh, bn = pick_box(N, Ho, Wo, rows=rows, multiple_of=16)
         self.box = (bw, bh, bn)
         self.plan = ext.WgradPlan(dy, taps.views, dw, R, S, taps.tap_map, taps.tap_dw, taps.tap_dh, bw, bh, bn,
-                                  px_chunks, max_ctas)
+                                  px_chunks, max_ctas, smem_budget)
         _plans.add(self.plan)
 
     def run(self) -> None:

@@ -58,6 +58,7 @@ class DistributedOptimizer:
         self._launched = 0
         self.allreduce_launches = 0
         self.timeline = None  # utils.Timeline: per-bucket all-reduce spans on the comm stream
+        self.extra_wait_streams = []  # streams that also produce gradients (e.g. the engine's wgrad side stream)
 
     # -- forwarded optimizer surface -------------------------------------------------------------------------
     @property
@@ -161,6 +162,9 @@ class DistributedOptimizer:
 
     def _reduce_bucket(self, b: _Bucket) -> None:
         n = b.hi - b.lo
+        if self._comm_stream is not None:
+            for st in self.extra_wait_streams:
+                self._comm_stream.wait_stream(st)
         scale = (1.0 / self.world) if self.average else 1.0
         if self.fused_update:
             cs = self._comm_stream
