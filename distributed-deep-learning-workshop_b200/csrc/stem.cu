@@ -30,18 +30,34 @@ constexpr int kPatchBytes = 7 * kPatchRowMax;  // one output row needs 7 input r
 // Step 2: thread (pixel m, half) converts its half of the 147-byte patch: 6 aligned LDS.32 + funnel shifts per
 //         input row, PRMT into an exact integer float, FADD/FFMA normalisation, bf16 pack, 16-byte smem stores
 //         into the SWIZZLE_128B tile.
-__device__ __forceinline__ void stem_load_patch(const StemParams& p, uint8_t* patch, int tile_idx, int bt) {
+// global -> registers (issued early so the latency overlaps the previous tile's build), registers -> smem
+__device__ __forceinline__ void stem_ldg_patch(const StemParams& p, int tile_idx, int bt, uint4 (&v)[2]) {
   const int n = tile_idx / p.Ho;
   const int ho = tile_idx - n * p.Ho;
   const int row_vec = p.W * 3 / 16;  // W % 16 == 0
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = bt + q * 256;
+    v[q] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < 7 * row_vec) {
+      const int r = i / row_vec;
+      const int c16 = i - r * row_vec;
+      const int h = 2 * ho - 3 + r;
+      if (h >= 0 && h < p.H) v[q] = *reinterpret_cast<const uint4*>(p.x + ((int64_t)(n * p.H + h) * p.W) * 3 + c16 * 16);
+    }
+  }
+}
+__device__ __forceinline__ void stem_sts_patch(const StemParams& p, uint8_t* patch, int bt, const uint4 (&v)[2]) {
+  const int row_vec = p.W * 3 / 16;
   const int stride = 16 + p.W * 3 + 16;
-  for (int i = bt; i < 7 * row_vec; i += 256) {
-    const int r = i / row_vec;
-    const int c16 = i - r * row_vec;
-    const int h = 2 * ho - 3 + r;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (h >= 0 && h < p.H) v = *reinterpret_cast<const uint4*>(p.x + ((int64_t)(n * p.H + h) * p.W) * 3 + c16 * 16);
-    *reinterpret_cast<uint4*>(patch + r * stride + 16 + c16 * 16) = v;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = bt + q * 256;
+    if (i < 7 * row_vec) {
+      const int r = i / row_vec;
+      const int c16 = i - r * row_vec;
+      *reinterpret_cast<uint4*>(patch + r * stride + 16 + c16 * 16) = v[q];
+    }
   }
 }
 
@@ -129,11 +145,14 @@ __device__ __forceinline__ void stem_builder_loop(const StemParams& p, uint8_t* 
                                                   int bt, int lane) {
   int stage = 0;
   uint32_t phase = 0;
+  uint4 pre[2];
+  if (n_my_tiles > 0) stem_ldg_patch(p, tile_at(0), bt, pre);
   for (int i = 0; i < n_my_tiles; ++i) {
     uint8_t* patch = patches + (i & 1) * kPatchBytes;
     const int tile = tile_at(i);
-    stem_load_patch(p, patch, tile, bt);
+    stem_sts_patch(p, patch, bt, pre);
     named_bar_sync(4, 256);  // patch complete; also: every builder is done with the previous tile's patch buffer
+    if (i + 1 < n_my_tiles) stem_ldg_patch(p, tile_at(i + 1), bt, pre);  // prefetch: lands while this tile is built
     mbar_wait(&empty_bar[stage], phase ^ 1);
     stem_build_rows(p, patch, stage_base + stage * STAGE_BYTES, bt, tile % p.Ho);
     fence_proxy_async_smem();
