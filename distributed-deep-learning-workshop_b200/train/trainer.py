@@ -220,7 +220,10 @@ class Trainer:
                     xb, yb = next(it)
                 except StopIteration:
                     it = iter(x)
-                    xb, yb = next(it)
+                    try:
+                        xb, yb = next(it)
+                    except StopIteration:
+                        raise ValueError("fit(): the dataset yields no batches (fewer rows than batch_size?)") from None
                 self.backend.train_batch(xb, yb)
                 for l, a in self.backend.pop_results(keep=1):  # lag one step: keeps H2D/compute overlapped
                     tot_loss += l

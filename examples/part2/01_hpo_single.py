@@ -31,6 +31,7 @@ TRAIN, VAL = to_arrays(train_pdf), to_arrays(val_pdf)
 
 def batches(arrs, bs):
     x, y = arrs
+    bs = max(1, min(bs, len(y)))
     n = len(y) // bs * bs
 
     class DS:
