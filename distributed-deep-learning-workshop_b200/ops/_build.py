@@ -15,6 +15,7 @@ import importlib.util
 import os
 import sys
 import threading
+import time
 from typing import Dict, List
 
 CSRC = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"))
@@ -36,7 +37,14 @@ EXTENSIONS: Dict[str, List[str]] = {
     "_b200_comm": ["allreduce.cu", "comm_bind.cpp"],
     "_b200_loader": ["ring_loader.cpp"],
 }
-HEADERS = ["ptx.cuh", "conv_igemm.cuh", "conv_params.h", "conv_api.h", "ops_api.h", "comm_api.h"]
+# headers each extension actually includes (hashed with its sources): editing one extension's header must not
+# mark the others stale
+HEADERS: Dict[str, List[str]] = {
+    "_b200_conv": ["ptx.cuh", "conv_igemm.cuh", "conv_params.h", "conv_api.h"],
+    "_b200_ops": ["ops_api.h"],
+    "_b200_comm": ["comm_api.h"],
+    "_b200_loader": [],
+}
 
 _loaded: Dict[str, object] = {}
 _lock = threading.Lock()
@@ -44,7 +52,7 @@ _lock = threading.Lock()
 
 def _hash(name: str) -> str:
     h = hashlib.sha256()
-    for rel in EXTENSIONS[name] + HEADERS:
+    for rel in EXTENSIONS[name] + HEADERS[name]:
         p = os.path.join(CSRC, rel)
         if os.path.exists(p):
             with open(p, "rb") as f:
@@ -105,7 +113,13 @@ def load(name: str):
         if name in _loaded:
             return _loaded[name]
         if not is_built(name):
+            # Never silent: a stale in-tree binary on a GPU box costs minutes of nvcc per process (this is how a
+            # source/.so mismatch in a snapshot looks like a hang under a short `timeout`).
+            print(f"[b200ddl] extension {name} is missing or stale (source hash != {so_path(name)}.hash); "
+                  f"rebuilding with nvcc - this takes minutes", file=sys.stderr, flush=True)
+            t0 = time.time()
             build(name)
+            print(f"[b200ddl] rebuilt {name} in {time.time() - t0:.0f}s", file=sys.stderr, flush=True)
         import torch  # noqa: F401  (libtorch symbols must be loaded before the extension)
 
         spec = importlib.util.spec_from_file_location(name, so_path(name))
