@@ -258,6 +258,18 @@ def case_elementwise():
     e.maxpool_bwd(idx, go, go2, dx)
     pr.backward((go.float() + go2.float()).permute(0, 3, 1, 2))
     ok &= report("maxpool_bwd", rel_err(dx, xr.grad.permute(0, 2, 3, 1)), 1e-2)
+    # fused BN + ReLU + max-pool
+    yb = torch.randn(4, 16, 16, 64, device=DEV, generator=g).to(torch.bfloat16)
+    scb = torch.rand(64, device=DEV, generator=g) + 0.5
+    shb = torch.randn(64, device=DEV, generator=g) * 0.3
+    ab = torch.empty_like(yb)
+    e.bn_apply(yb, scb, shb, None, None, None, ab, True)
+    p_ref = torch.empty(4, 8, 8, 64, device=DEV, dtype=torch.bfloat16); i_ref = torch.empty(4, 8, 8, 64, device=DEV, dtype=torch.uint8)
+    e.maxpool_fwd(ab, p_ref, i_ref)
+    p_f = torch.empty_like(p_ref); i_f = torch.empty_like(i_ref)
+    e.bn_relu_maxpool_fwd(yb, scb, shb, p_f, i_f)
+    ok &= report("bn_relu_maxpool_fwd", rel_err(p_f, p_ref), 0.0)
+    ok &= report("bn_relu_maxpool_idx", float((i_f != i_ref).float().mean()), 0.0)
     # gap
     x = torch.randn(8, 7, 7, 2048, device=DEV, generator=g).to(torch.bfloat16)
     out = torch.empty(8, 2048, device=DEV, dtype=torch.bfloat16)

@@ -433,6 +433,68 @@ void maxpool_fwd(const void* x, void* out, void* idx, int N, int H, int W, int C
                                                           N, H, W, C, Ho, Wo);
 }
 
+// Stem tail in one pass: out = maxpool3x3/2( relu( y*scale + shift ) ) + argmax; the 112x112 post-ReLU activation is
+// never materialised (its backward needs only y, the BN affine and the argmax).
+__global__ void __launch_bounds__(256)
+bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                           const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                           uint8_t* __restrict__ idx, int N, int H, int W, int C, int Ho, int Wo) {
+  const int cvec = C / 8;
+  const int64_t total = (int64_t)N * Ho * Wo * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    int64_t p = i / cvec;
+    const int wo = (int)(p % Wo);
+    p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float sc[8], sh[8], m[8];
+    uint32_t am[8];
+    ldf8(scale + cv * 8, sc);
+    ldf8(shift + cv * 8, sh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      m[k] = -3.0e38f;
+      am[k] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * ho - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int w = 2 * wo - 1 + q;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(ld8(y + (((int64_t)n * H + h) * W + w) * C + cv * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // same rounding as the materialised path: bf16(relu(fma))
+          const float a = __bfloat162float(__float2bfloat16(fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f)));
+          if (a > m[k]) {
+            m[k] = a;
+            am[k] = r * 3 + q;
+          }
+        }
+      }
+    }
+    st8(out + i * 8, pack8(m));
+    if (idx != nullptr) {
+      uint2 pk;
+      pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+      pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+      *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    }
+  }
+}
+void bn_relu_maxpool_fwd(const void* y, const float* scale, const float* shift, void* out, void* idx, int N, int H,
+                         int W, int C, cudaStream_t s) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  bn_relu_maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, s>>>((const __nv_bfloat16*)y, scale, shift,
+                                                                  (__nv_bfloat16*)out, (uint8_t*)idx, N, H, W, C, Ho, Wo);
+}
+
 // dx[h, w] = sum over windows (ho, wo) containing (h, w) whose argmax is this position of (g1 [+ g2])[ho, wo].
 __global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ g1,
                                    const __nv_bfloat16* __restrict__ g2, __nv_bfloat16* __restrict__ dx, int N, int H,

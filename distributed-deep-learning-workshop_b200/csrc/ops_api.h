@@ -18,6 +18,8 @@ void bn_bwd_coeffs(float* sum_dz, float* sum_dzy, const float* gamma, const floa
 void bn_bwd_apply(const void* g, const void* y, const float* scale, const float* shift, const float* cA,
                   const float* cB, const float* cC, void* dy, int64_t M, int C, cudaStream_t s);
 void maxpool_fwd(const void* x, void* out, void* idx, int N, int H, int W, int C, cudaStream_t s);
+void bn_relu_maxpool_fwd(const void* y, const float* scale, const float* shift, void* out, void* idx, int N, int H,
+                         int W, int C, cudaStream_t s);
 void maxpool_bwd(const void* idx, const void* g1, const void* g2, void* dx, int N, int H, int W, int C,
                  cudaStream_t s);
 void gap_fwd(const void* x, void* out, int N, int HW, int C, float drop_p, uint64_t seed, cudaStream_t s);

@@ -102,6 +102,17 @@ void maxpool_fwd(Tensor x, Tensor out, OptT idx) {
                     (int)x.size(1), (int)x.size(2), (int)x.size(3), cur());
   after();
 }
+void bn_relu_maxpool_fwd(Tensor y, Tensor scale, Tensor shift, Tensor out, OptT idx) {
+  chk(y, at::kBFloat16, "y");
+  chk(out, at::kBFloat16, "out");
+  chk(scale, at::kFloat, "scale");
+  chk(shift, at::kFloat, "shift");
+  if (idx.has_value()) { chk(*idx, at::kByte, "idx"); TORCH_CHECK(idx->numel() == out.numel()); }
+  b200::bn_relu_maxpool_fwd(y.data_ptr(), scale.data_ptr<float>(), shift.data_ptr<float>(), out.data_ptr(),
+                            idx.has_value() ? idx->data_ptr() : nullptr, (int)y.size(0), (int)y.size(1),
+                            (int)y.size(2), (int)y.size(3), cur());
+  after();
+}
 void maxpool_bwd(Tensor idx, Tensor g1, OptT g2, Tensor dx) {
   chk(idx, at::kByte, "idx");
   chk(g1, at::kBFloat16, "g1");
@@ -208,6 +219,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_bwd_apply", &bn_bwd_apply);
   m.def("maxpool_fwd", &maxpool_fwd);
   m.def("maxpool_bwd", &maxpool_bwd);
+  m.def("bn_relu_maxpool_fwd", &bn_relu_maxpool_fwd);
   m.def("gap_fwd", &gap_fwd);
   m.def("gap_bwd", &gap_bwd);
   m.def("softmax_ce", &softmax_ce);

@@ -260,7 +260,6 @@ class ResNet50Engine:
 
         H0 = S // 2
         self.y0 = torch.zeros(N, H0, H0, 64, **bf)
-        self.a0 = torch.zeros(N, H0, H0, 64, **bf)
         self.p0 = torch.zeros(N, H0 // 2, H0 // 2, 64, **bf)
         self.pool_idx = torch.zeros(N, H0 // 2, H0 // 2, 64, device=dev, dtype=torch.uint8)
         w0 = self.bnw["bn1"]
@@ -394,8 +393,8 @@ class ResNet50Engine:
             e.channel_stats(self.y0, w0["sum"], w0["sqsum"])
         cnt0 = N * self.y0.shape[1] * self.y0.shape[2]
         self._bn_fwd("bn1", cnt0, training)
-        e.bn_apply(self.y0, w0["scale"], w0["shift"], None, None, None, self.a0, True)
-        e.maxpool_fwd(self.a0, self.p0, self.pool_idx)
+        # BN + ReLU + 3x3/2 max-pool in one pass (the 112x112 activation is never written)
+        e.bn_relu_maxpool_fwd(self.y0, w0["scale"], w0["shift"], self.p0, self.pool_idx)
         x_in = self.p0
         for b in self.blocks:
             n = b.name
@@ -533,7 +532,7 @@ class ResNet50Engine:
             else:
                 g2 = dz
         # stem
-        da0 = self._dy_buf("conv3", self.a0.shape)  # reuses the (by now idle) "dy" scratch
+        da0 = self._dy_buf("conv3", self.y0.shape)  # reuses the (by now idle) "dy" scratch
         e.maxpool_bwd(self.pool_idx, g1, g2, da0)
         dy0 = self._scr["dzA"][:self.y0.numel()].view(self.y0.shape)
         cnt0 = N * self.y0.shape[1] * self.y0.shape[2]
