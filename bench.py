@@ -190,6 +190,10 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     ms = float(dist.allreduce(ms, average=False).item()) if world == 1 else float(_max_over_ranks(ms))
     loss, acc = step.result()
+    # outside the timed region: after K data-parallel steps every rank must hold bit-identical fp32 master weights
+    # (a gradient that was all-reduced before its producer finished would show up here)
+    from b200ddl.utils import checksum_across_ranks
+    params_identical = bool(checksum_across_ranks(engine.params)) if world > 1 else None
     global_batch = args.batch * world
     value = global_batch * args.steps / (ms / 1e3)
 
@@ -234,6 +238,7 @@ def main():
                        "l2": "activations per step are several GB (>> 126 MB L2); no explicit flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step), "loss": loss, "accuracy": acc,
+            "params_identical_across_ranks": params_identical,
         }
         print(json.dumps(out), flush=True)
     dist.shutdown()
