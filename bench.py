@@ -121,7 +121,8 @@ def main():
     ap.add_argument("--graph-baseline", action="store_true")
     ap.add_argument("--optimizer", default="sgd", choices=["sgd", "adam"])
     ap.add_argument("--no-fuse-bwd-reduce", action="store_true")
-    ap.add_argument("--overlap-wgrad", action="store_true", help="weight-gradient GEMMs on a side stream")
+    ap.add_argument("--overlap-wgrad", action="store_true", help="(default; kept for old command lines) weight-gradient GEMMs on a side stream")
+    ap.add_argument("--no-overlap-wgrad", action="store_true", help="issue the weight-gradient GEMMs in line on the compute stream")
     ap.add_argument("--wgrad-smem", type=int, default=0)
     ap.add_argument("--fused-update", action="store_true", help="all-reduce + SGD + weight multicast in one kernel")
     args = ap.parse_args()
@@ -149,7 +150,7 @@ def main():
     torch.backends.cudnn.benchmark = True
 
     engine = ResNet50Engine(batch=args.batch, num_classes=args.classes, device=dev, seed=0, max_ctas=0,
-                            overlap_wgrad=args.overlap_wgrad, wgrad_smem_budget=args.wgrad_smem,
+                            overlap_wgrad=not args.no_overlap_wgrad, wgrad_smem_budget=args.wgrad_smem,
                             fuse_bwd_reduce=not args.no_fuse_bwd_reduce)
     lr = 0.1 * world  # LR x world size (reference P1/03:301)
     base_opt = optim.SGD(lr, momentum=0.9, weight_decay=1e-4) if args.optimizer == "sgd" else optim.Adam(1e-3 * world)
@@ -234,7 +235,7 @@ def main():
                        "image": "224x224x3", "classes": args.classes, "parallelism": f"dp{world}",
                        "optimizer": args.optimizer, "allreduce": getattr(opt, "algo", "none") if world > 1 else "none",
                        "fused_allreduce_sgd": bool(getattr(opt, "fused_update", False)),
-                       "cuda_graph": not args.no_graph, "overlap_wgrad": bool(args.overlap_wgrad),
+                       "cuda_graph": not args.no_graph, "overlap_wgrad": not args.no_overlap_wgrad,
                        "l2": "activations per step are several GB (>> 126 MB L2); no explicit flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step), "loss": loss, "accuracy": acc,

@@ -386,15 +386,19 @@ def case_conv_time():
     return True
 
 
-def case_engine():
-    """ResNet-50 engine forward/backward vs torchvision (same weights, fp32 reference and bf16-autocast reference)."""
+def case_engine(overlap_wgrad: bool = True, quick: bool = False):
+    """ResNet-50 engine forward/backward vs torchvision (same weights, fp32 reference and bf16-autocast reference).
+
+    `overlap_wgrad` selects where the weight-gradient GEMMs are issued (side stream = the engine default, or in line);
+    `quick` stops after the gradient / running-statistics checks."""
     import torchvision
     from b200ddl.models.resnet_engine import ResNet50Engine, EngineTrainStep
     from b200ddl import optim
 
     ok = True
     N, K = 32, 10
-    eng = ResNet50Engine(batch=N, num_classes=K, zero_init_residual=False, seed=1)
+    eng = ResNet50Engine(batch=N, num_classes=K, zero_init_residual=False, seed=1, overlap_wgrad=overlap_wgrad)
+    print(f"INFO engine overlap_wgrad={eng.overlap_wgrad} fuse_bwd_reduce={eng.fuse_bwd_reduce}", flush=True)
     opt = optim.SGD(learning_rate=0.1, momentum=0.9)
     step = EngineTrainStep(eng, opt, use_graph=False)
     g = torch.Generator(device=DEV).manual_seed(5)
@@ -471,6 +475,8 @@ def case_engine():
     rm = dict(ref.named_buffers())
     ok &= report("engine/running_mean/bn1", rel_err(eng.running_mean["bn1"], rm["bn1.running_mean"]), 3e-2)
     ok &= report("engine/running_var/layer3.0.bn2", rel_err(eng.running_var["layer3.0.bn2"], rm["layer3.0.bn2.running_var"]), 5e-2)
+    if quick:
+        return ok
     # run-to-run spread of the engine itself (fp32 atomics in the statistics / wgrad reductions are unordered): the same
     # input through forward+backward again, compared with the first run.  Diagnostic only.
     eng.forward(training=True)
@@ -510,7 +516,7 @@ def case_engine():
         print(f"INFO torch_bf16_sensitivity_bn3e-7/{name} rel_diff={((gb - ga).norm() / (ga.norm() + 1e-12)).item():.3e}", flush=True)
     # a few optimisation steps must reduce the loss on a fixed batch (graph path)
     print("STAGE graph steps", flush=True)
-    eng2 = ResNet50Engine(batch=N, num_classes=K, seed=2)
+    eng2 = ResNet50Engine(batch=N, num_classes=K, seed=2, overlap_wgrad=overlap_wgrad)
     step2 = EngineTrainStep(eng2, optim.SGD(learning_rate=0.05, momentum=0.9), use_graph=True)
     losses = []
     for i in range(12):
@@ -598,6 +604,7 @@ CASES = {
     "elementwise": case_elementwise,
     "conv_time": case_conv_time,
     "engine": case_engine,
+    "engine_serial_wgrad": lambda: case_engine(overlap_wgrad=False, quick=True),
     "stem": case_stem,
     "umma_probe": case_umma_probe,
 }

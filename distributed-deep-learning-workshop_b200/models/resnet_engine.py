@@ -85,7 +85,7 @@ class ResNet50Engine:
     def __init__(self, batch: int, num_classes: int = 1000, device: Optional[torch.device] = None,
                  image_size: int = 224, dropout: float = 0.0, bn_momentum: float = 0.1, bn_eps: float = 1e-5,
                  seed: int = 0, max_ctas: int = 0, zero_init_residual: bool = True, native_stem: bool = True,
-                 overlap_wgrad: bool = False, wgrad_smem_budget: int = 0, fuse_bwd_reduce: bool = True):
+                 overlap_wgrad: bool = True, wgrad_smem_budget: int = 0, fuse_bwd_reduce: bool = True):
         ops.require_native()
         self.zero_init_residual = zero_init_residual
         self.native_stem = native_stem

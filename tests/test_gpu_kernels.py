@@ -52,6 +52,11 @@ def test_resnet50_engine_matches_torchvision(checks):
     assert checks.case_engine()
 
 
+def test_resnet50_engine_inline_wgrad_matches_torchvision(checks):
+    """Same gradient criteria with the weight-gradient GEMMs issued in line instead of on the side stream."""
+    assert checks.case_engine(overlap_wgrad=False, quick=True)
+
+
 def test_ring_loader_h2d_roundtrip():
     from b200ddl.loader import SyntheticDataset
 

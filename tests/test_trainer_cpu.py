@@ -47,11 +47,18 @@ def test_fit_evaluate_predict_history_and_callbacks(tmp_path):
 
 
 def test_early_stopping_stops():
+    torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 5))
     tr = Trainer(model, device="cpu").compile(optimizer=optim.SGD(0.0))  # lr 0 => no improvement
     es = EarlyStopping(monitor="val_loss", min_delta=1e-2, patience=2)
-    hist = tr.fit(make_ds(size=8), steps_per_epoch=2, epochs=20, verbose=0, validation_data=make_ds(size=8, seed=1),
+    # A RE-ITERABLE validation set: like Keras, every validation pass starts from the beginning of the dataset, so
+    # with validation_steps < len the same samples are scored each epoch and lr 0 gives a constant val_loss.  (A one-shot
+    # generator would hand a different batch to every epoch and the stopping epoch would depend on luck.)
+    gen = make_ds(size=8, seed=1)
+    val = [next(gen) for _ in range(3)]
+    hist = tr.fit(make_ds(size=8), steps_per_epoch=2, epochs=20, verbose=0, validation_data=val,
                   validation_steps=1, callbacks=[es])
+    assert len(set(hist.history["val_loss"])) == 1          # same validation samples every epoch
     assert len(hist.history["loss"]) == 3 and es.stopped_epoch == 2
 
 
