@@ -65,7 +65,9 @@ static void launch_t(const ConvPlanRaw& pl, cudaStream_t s) {
     if (e != cudaSuccess) throw std::runtime_error(std::string("conv_igemm: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
-  kern<<<pl.grid, ST ? 384 : 256, L::kTotal, s>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmA[3], pl.tmB, pl.tmD, pl.tmY, pl.p);
+  TmapArray4 a;
+  for (int i = 0; i < 4; ++i) a.m[i] = pl.tmA[i];
+  kern<<<pl.grid, ST ? 384 : 256, L::kTotal, s>>>(a, pl.tmB, pl.tmD, pl.tmY, pl.p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("conv_igemm launch: ") + cudaGetErrorString(e));
 }

@@ -25,6 +25,11 @@ namespace b200 {
 // kStats: 0 = plain epilogue, 1 = forward BatchNorm statistics (sum y, sum y^2), 2 = BatchNorm-backward reduction
 // fused into a dgrad GEMM: the output tile is g = dL/d(activation); with the activation's pre-BN tensor y (extra TMA
 // load per chunk) the statistics warps accumulate sum(dz), sum(dz*y) for dz = g * [y*scale + shift > 0].
+// The (up to four) parity views of the A operand as ONE kernel parameter: the per-tap choice is an index.
+struct TmapArray4 {
+  CUtensorMap m[4];
+};
+
 template <int BLOCK_N, int kStats = 0>
 struct ConvSmem {
   static constexpr int kStages = (BLOCK_N == 256) ? (kStats == 2 ? 3 : 4) : (BLOCK_N == 128 ? 5 : 6);
@@ -41,10 +46,9 @@ struct ConvSmem {
 
 template <int BLOCK_N, int kStats>
 __global__ void __launch_bounds__(kStats ? 384 : 256, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
-                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ ConvParams p) {
+conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY,
+                  const __grid_constant__ ConvParams p) {
   using L = ConvSmem<BLOCK_N, kStats>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
@@ -65,11 +69,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
   float* sStat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::kBarBytes);  // [2][BLOCK_N]
 
-  const int warp = threadIdx.x >> 5;
+  // Provably warp-uniform (the compiler cannot see that threadIdx.x >> 5 is): together with elect.sync for the
+  // single-thread roles this keeps tcgen05 / TMA / mbarrier instructions free of per-instruction serialisation loops.
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA.m[0]);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
     for (int i = 0; i < kStages; ++i) {
@@ -104,74 +110,94 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const uint32_t a_bytes = (p.mode == 0 ? kBlockM : p.valid_rows) * 128;
   const uint32_t stage_tx = a_bytes + L::kBBytes;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_blocks;
-      const int nb = tile - m_tile * p.n_blocks;
-      int w0 = 0, h0 = 0, n0 = 0;
-      if (p.mode == 1) {
-        const int tw = m_tile % p.tiles_w;
-        const int rest = m_tile / p.tiles_w;
-        const int th = rest % p.tiles_h;
-        w0 = tw * p.bw;
-        h0 = th * p.bh;
-        n0 = (rest / p.tiles_h) * p.bn;
+  // The two single-thread roles below were the bottleneck of the small-K / small-N layers (ncu, 3x3 64->64 @56^2: tensor
+  // pipe 22 %, L2 32 %, both role threads busy ~90 % of the time executing ~70-100 dependent instructions per 24 KB
+  // stage).  Hence: one elect.sync around each loop, integer smem addresses and UMMA descriptors built once, kernel
+  // parameters hoisted into registers, per-tap work hoisted out of the k-block loop.
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---------------------------------------------------------------- TMA producer (one elected thread)
+      const int taps = p.taps, kblocks = p.kblocks, n_blocks = p.n_blocks, num_tiles = p.num_tiles, cout = p.cout;
+      const bool flat = p.mode == 0;
+      const int tiles_w = p.tiles_w, tiles_h = p.tiles_h, bw = p.bw, bh = p.bh, bn = p.bn;
+      const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / n_blocks;
+        const int nb = tile - m_tile * n_blocks;
+        int w0 = 0, h0 = 0, n0 = 0;
+        if (!flat) {
+          const int tw = m_tile % tiles_w;
+          const int rest = m_tile / tiles_w;
+          const int th = rest % tiles_h;
+          w0 = tw * bw;
+          h0 = th * bh;
+          n0 = (rest / tiles_h) * bn;
+        }
+        const int m0 = m_tile * kBlockM;
+        const int brow = nb * BLOCK_N;
+        for (int t = 0; t < taps; ++t) {
+          const CUtensorMap* am = &tmA.m[p.tap_map[t]];
+          const int cw = w0 + p.tap_dw[t];
+          const int ch = h0 + p.tap_dh[t];
+          const int b1 = t * cout + brow;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+            const uint32_t fb = full0 + stage * 8;
+            mbar_arrive_expect_tx_u32(fb, stage_tx);
+            if (flat)
+              tma_load_2d_u32(sA0 + stage * L::kABytes, am, fb, kb * kBlockK, m0);
+            else
+              tma_load_4d_u32(sA0 + stage * L::kABytes, am, fb, kb * kBlockK, cw, ch, n0);
+            tma_load_2d_u32(sB0 + stage * L::kBBytes, &tmB, fb, kb * kBlockK, b1);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
       }
-      for (int t = 0; t < p.taps; ++t) {
-        const CUtensorMap* am = &tmA0;
-        if (p.tap_map[t] == 1) am = &tmA1;
-        if (p.tap_map[t] == 2) am = &tmA2;
-        if (p.tap_map[t] == 3) am = &tmA3;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-          if (p.mode == 0)
-            tma_load_2d(sA + stage * L::kABytes, am, &full_bar[stage], kb * kBlockK, m_tile * kBlockM);
-          else
-            tma_load_4d(sA + stage * L::kABytes, am, &full_bar[stage], kb * kBlockK, w0 + p.tap_dw[t],
-                        h0 + p.tap_dh[t], n0);
-          tma_load_2d(sB + stage * L::kBBytes, &tmB, &full_bar[stage], kb * kBlockK, t * p.cout + nb * BLOCK_N);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ---------------------------------------------------------------- MMA issuer (one elected thread)
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      const int num_tiles = p.num_tiles;
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
+      // descriptors differ only in the 14-bit start-address field (addr >> 4): build once, add per stage / k-step
+      const uint64_t da0 = umma_desc_sw128(smem_u32(sA), 16, 1024);
+      const uint64_t db0 = umma_desc_sw128(smem_u32(sB), 16, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait_u32(tempty0 + acc * 8, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait_u32(full0 + stage * 8, phase);
+          tc_fence_after();
+          const uint64_t da = da0 + static_cast<uint32_t>(stage * (L::kABytes >> 4));
+          const uint64_t db = db0 + static_cast<uint32_t>(stage * (L::kBBytes >> 4));
+          // 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field per k-step
+          umma_bf16(d_tmem, da, db, idesc, it != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 1; k < kBlockK / 16; ++k) umma_bf16_acc(d_tmem, da + 2 * k, db + 2 * k, idesc);
+          umma_commit_u32(empty0 + stage * 8);  // frees the smem slot when these MMAs retire
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-      }
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      for (int it = 0; it < k_iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * L::kABytes), 16, 1024);
-        const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * L::kBBytes), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        umma_commit_u32(tfull0 + acc * 8);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
       }
     }
   } else if (warp >= 4 && warp < 8) {
