@@ -17,6 +17,7 @@ struct ConvPlanRaw {
   int block_n;
   int grid;
   int stats;  // 0 none, 1 forward BN statistics, 2 fused BN-backward reduction
+  int res_b;  // 1: the CTA's whole filter slice stays resident in shared memory (block_n == 64, n_blocks == 1, <= 9 tiles)
 };
 
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1; SWIZZLE_128B, zero OOB fill.

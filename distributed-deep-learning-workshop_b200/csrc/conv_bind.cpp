@@ -3,6 +3,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <torch/extension.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -111,6 +112,12 @@ struct ConvPlan {
     raw.tmB = map_2d(weight.data_ptr(), taps * cout, cin, cin, 64, raw.block_n);
     p.num_tiles = p.m_tiles * p.n_blocks;
     raw.stats = stat_sum.has_value() ? (bwd_y.has_value() ? 2 : 1) : 0;
+    // Resident filter: one N-block of 64 channels whose taps * kblocks filter tiles (8 KB each) fit in 72 KB.
+    // B200DDL_NO_RESIDENT_FILTER=1 switches it off (A/B measurements).
+    {
+      const char* off = std::getenv("B200DDL_NO_RESIDENT_FILTER");
+      raw.res_b = (raw.block_n == 64 && p.n_blocks == 1 && taps * p.kblocks <= 9 && !(off && off[0] == '1')) ? 1 : 0;
+    }
     raw.tmY = raw.tmD;
     if (raw.stats == 2) {
       // fused BatchNorm-backward reduction: y has exactly the output's shape / layout
@@ -148,6 +155,7 @@ struct ConvPlan {
   }
   int grid() const { return raw.grid; }
   int block_n() const { return raw.block_n; }
+  int res_b() const { return raw.res_b; }
 };
 
 struct WgradPlan {
@@ -345,7 +353,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("run", &b200::ConvPlan::run)
       .def_readonly("launches", &b200::ConvPlan::launches)
       .def_property_readonly("grid", &b200::ConvPlan::grid)
-      .def_property_readonly("block_n", &b200::ConvPlan::block_n);
+      .def_property_readonly("block_n", &b200::ConvPlan::block_n)
+      .def_property_readonly("resident_filter", &b200::ConvPlan::res_b);
   py::class_<b200::WgradPlan>(m, "WgradPlan")
       .def(py::init<at::Tensor, std::vector<at::Tensor>, at::Tensor, int64_t, int64_t, std::vector<int64_t>,
                     std::vector<int64_t>, std::vector<int64_t>, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t>(),

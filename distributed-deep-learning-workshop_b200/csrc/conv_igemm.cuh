@@ -30,26 +30,36 @@ struct TmapArray4 {
   CUtensorMap m[4];
 };
 
-template <int BLOCK_N, int kStats = 0>
+// kResB: the whole filter slice this CTA needs (taps * kblocks tiles of [BLOCK_N x 64]) stays resident in shared memory
+// (loaded once per CTA) and the pipeline stages carry only the A tile.  The 3x3 64->64 @56^2 layer moves ~90 % of the
+// measured L2 -> SM cap (~42.6 B/clk/SM) with a third of those bytes being the same 72 KB of weights re-read per tile.
+constexpr int kResBBytes = 9 * 64 * kBlockK * 2;  // 72 KB: 9 taps of a 64 x 64 filter (or 4 k-blocks x 2 ... any <= 9 tiles)
+
+template <int BLOCK_N, int kStats = 0, bool kResB = false>
 struct ConvSmem {
-  static constexpr int kStages = (BLOCK_N == 256) ? (kStats == 2 ? 3 : 4) : (BLOCK_N == 128 ? 5 : 6);
   static constexpr int kYBytes = kStats == 2 ? 2 * kBlockM * 128 : 0;  // two 128x64 bf16 tiles of y
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = kResB ? kABytes : kABytes + kBBytes;
+  static constexpr int kResBytes = kResB ? kResBBytes : 0;
   static constexpr int kStagingBytes = 2 * kBlockM * 128;  // two 128x64 bf16 store buffers
   static constexpr int kBarBytes = 256;
   static constexpr int kStatBytes = 2 * BLOCK_N * 4;
-  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kYBytes + kBarBytes + kStatBytes;
+  static constexpr int kFixed = kResBytes + kStagingBytes + kYBytes + kBarBytes + kStatBytes;
+  static constexpr int kStages = kResB ? ((232448 - kFixed) / kStageBytes > 8 ? 8 : (232448 - kFixed) / kStageBytes)
+                                       : ((BLOCK_N == 256) ? (kStats == 2 ? 3 : 4) : (BLOCK_N == 128 ? 5 : 6));
+  static constexpr int kTotal = kStages * kStageBytes + kFixed;
+  static_assert(!kResB || BLOCK_N == 64, "resident filter: BLOCK_N == 64 only");
+  static_assert(kStages >= 3 && 2 * kStages + 7 <= kBarBytes / 8, "pipeline depth / barrier area");
   static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
 };
 
-template <int BLOCK_N, int kStats>
+template <int BLOCK_N, int kStats, bool kResB = false>
 __global__ void __launch_bounds__(kStats ? 384 : 256, 1)
 conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY,
                   const __grid_constant__ ConvParams p) {
-  using L = ConvSmem<BLOCK_N, kStats>;
+  using L = ConvSmem<BLOCK_N, kStats, kResB>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 
@@ -57,8 +67,8 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * L::kABytes;
-  uint8_t* sStage = smem + kStages * L::kStageBytes;
+  uint8_t* sB = smem + kStages * L::kABytes;  // per-stage B tiles, or (kResB) the resident filter slice
+  uint8_t* sStage = smem + kStages * L::kStageBytes + L::kResBytes;
   uint8_t* sY = sStage + L::kStagingBytes;  // kStats == 2 only
   uint64_t* bars = reinterpret_cast<uint64_t*>(sY + L::kYBytes);
   uint64_t* full_bar = bars;                     // [kStages]
@@ -66,7 +76,8 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
   uint64_t* tfull_bar = bars + 2 * kStages;      // [2]
   uint64_t* tempty_bar = bars + 2 * kStages + 2; // [2]
   uint64_t* y_bar = bars + 2 * kStages + 4;      // [2] (kStats == 2)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
+  uint64_t* bres_bar = bars + 2 * kStages + 6;   // resident filter loaded (kResB)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 7);
   float* sStat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::kBarBytes);  // [2][BLOCK_N]
 
   // Provably warp-uniform (the compiler cannot see that threadIdx.x >> 5 is): together with elect.sync for the
@@ -87,6 +98,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
       mbar_init(&tempty_bar[i], 4);
       mbar_init(&y_bar[i], 1);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (kStats) {
@@ -108,7 +120,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
 
   const int k_iters = p.taps * p.kblocks;
   const uint32_t a_bytes = (p.mode == 0 ? kBlockM : p.valid_rows) * 128;
-  const uint32_t stage_tx = a_bytes + L::kBBytes;
+  const uint32_t stage_tx = kResB ? a_bytes : a_bytes + L::kBBytes;
 
   // The two single-thread roles below were the bottleneck of the small-K / small-N layers (ncu, 3x3 64->64 @56^2: tensor
   // pipe 22 %, L2 32 %, both role threads busy ~90 % of the time executing ~70-100 dependent instructions per 24 KB
@@ -122,6 +134,14 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
       const int tiles_w = p.tiles_w, tiles_h = p.tiles_h, bw = p.bw, bh = p.bh, bn = p.bn;
       const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      if (kResB && static_cast<int>(blockIdx.x) < num_tiles) {
+        // n_blocks == 1 (host-checked): every tile of this CTA uses the same taps * kblocks filter tiles, tile
+        // (t, kb) at index t * kblocks + kb.
+        mbar_arrive_expect_tx_u32(smem_u32(bres_bar), static_cast<uint32_t>(taps * kblocks) * L::kBBytes);
+        for (int t = 0; t < taps; ++t)
+          for (int kb = 0; kb < kblocks; ++kb)
+            tma_load_2d_u32(sB0 + (t * kblocks + kb) * L::kBBytes, &tmB, smem_u32(bres_bar), kb * kBlockK, t * cout);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -151,7 +171,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
               tma_load_2d_u32(sA0 + stage * L::kABytes, am, fb, kb * kBlockK, m0);
             else
               tma_load_4d_u32(sA0 + stage * L::kABytes, am, fb, kb * kBlockK, cw, ch, n0);
-            tma_load_2d_u32(sB0 + stage * L::kBBytes, &tmB, fb, kb * kBlockK, b1);
+            if (!kResB) tma_load_2d_u32(sB0 + stage * L::kBBytes, &tmB, fb, kb * kBlockK, b1);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -174,6 +194,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (kResB && static_cast<int>(blockIdx.x) < num_tiles) mbar_wait_u32(smem_u32(bres_bar), 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait_u32(tempty0 + acc * 8, acc_phase ^ 1);
         tc_fence_after();
@@ -182,7 +203,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
           mbar_wait_u32(full0 + stage * 8, phase);
           tc_fence_after();
           const uint64_t da = da0 + static_cast<uint32_t>(stage * (L::kABytes >> 4));
-          const uint64_t db = db0 + static_cast<uint32_t>(stage * (L::kBBytes >> 4));
+          const uint64_t db = db0 + static_cast<uint32_t>((kResB ? it : stage) * (L::kBBytes >> 4));
           // 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field per k-step
           umma_bf16(d_tmem, da, db, idesc, it != 0 ? 1u : 0u);
 #pragma unroll
