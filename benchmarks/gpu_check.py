@@ -597,6 +597,50 @@ def case_umma_probe():
     return ok0
 
 
+def case_tma_probe():
+    """TMA load pipeline alone (no MMA, no epilogue): time per box load for the shapes the 3x3 convs use or could use."""
+    ext = ops.ext("_b200_conv")
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    x56 = torch.randn(256, 56, 56, 64, device=DEV).to(torch.bfloat16)
+    x28 = torch.randn(512, 28, 28, 64, device=DEV).to(torch.bfloat16)
+    wlike = torch.randn(1, 1, 576, 64, device=DEV).to(torch.bfloat16)  # 72 KB, read by every CTA: L2-hot, like a filter
+
+    def run(label, x, rows_2d, box, tap, stages, total_mb=1100.0):
+        bw, bh, bn = box
+        nbytes = (rows_2d if rows_2d else bw * bh * bn) * 128
+        loads = max(8, int(total_mb * 1e6 / nbytes / sms))
+        f = lambda: ext.tma_probe(x, rows_2d, bw, bh, bn, tap[0], tap[1], stages, loads, 0)
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 5 * 1e3
+        tot = loads * sms * nbytes
+        print(f"PROBE tma {label:34s} box={nbytes // 128:4d} rows ({nbytes / 1024:5.1f} KB) stages={stages:2d} loads/CTA={loads:5d} "
+              f"{us:8.1f} us  {tot / us / 1e6:7.2f} TB/s  {tot / us / 1e3 / sms:6.1f} GB/s/SM  {us * 1e3 / loads:7.1f} ns/load  "
+              f"{us * 1e3 / loads / (nbytes // 128):6.2f} ns/row", flush=True)
+
+    run("flat 2-D, 128 rows", x56, 128, (0, 0, 0), (0, 0), 6)
+    run("box 56x2x1 (current A tile)", x56, 0, (56, 2, 1), (0, 0), 6)
+    run("box 56x2x1 tap(-1,-1)", x56, 0, (56, 2, 1), (-1, -1), 6)
+    run("box 56x2x1 tap(+1,+1)", x56, 0, (56, 2, 1), (1, 1), 6)
+    run("box 56x2x1 stages 3", x56, 0, (56, 2, 1), (0, 0), 3)
+    run("box 56x2x1 stages 12", x56, 0, (56, 2, 1), (0, 0), 12)
+    run("box 56x4x1 (halo box)", x56, 0, (56, 4, 1), (0, 0), 4)
+    run("box 56x4x1 tap(-1,-1)", x56, 0, (56, 4, 1), (-1, -1), 4)
+    run("box 56x4x1 stages 7", x56, 0, (56, 4, 1), (0, 0), 7)
+    run("box 8x8x2 (square)", x56, 0, (8, 8, 2), (0, 0), 6)
+    run("box 28x4x1 on 28^2", x28, 0, (28, 4, 1), (0, 0), 6)
+    run("box 28x6x1 on 28^2 (halo)", x28, 0, (28, 6, 1), (0, 0), 5)
+    run("filter-like 64 rows, L2-hot", wlike, 64, (0, 0, 0), (0, 0), 6, total_mb=400.0)
+    return True
+
+
 CASES = {
     "conv_fwd": case_conv_fwd,
     "conv_dgrad": case_conv_dgrad,
@@ -604,6 +648,7 @@ CASES = {
     "elementwise": case_elementwise,
     "conv_time": case_conv_time,
     "engine": case_engine,
+    "tma_probe": case_tma_probe,
     "engine_serial_wgrad": lambda: case_engine(overlap_wgrad=False, quick=True),
     "stem": case_stem,
     "umma_probe": case_umma_probe,

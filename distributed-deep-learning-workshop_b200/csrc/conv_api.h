@@ -40,6 +40,18 @@ struct StemPlanRaw {
 };
 void stem_fwd_launch(const StemPlanRaw& plan, cudaStream_t stream);
 void stem_wgrad_launch(const StemPlanRaw& plan, cudaStream_t stream);
+struct TmaProbeParams {
+  int mode;        // 0: 2-D [pixels, C] map, 1: 4-D NHWC map with a (bw, bh, bn) pixel box
+  int box_bytes;   // bytes one load brings in (rows * 128)
+  int stages;
+  int loads_per_cta;
+  int bw, bh, bn;
+  int tiles_w, tiles_h, tiles_n;  // 4-D: how many distinct box positions exist (walked round-robin, offset per CTA)
+  int m_tiles;                    // 2-D: number of 128-row tiles
+  int dw, dh;                     // 4-D: coordinate offset (a filter tap), exercises the out-of-bounds path
+};
+// TMA load-throughput probe (csrc/tma_probe.cu): box loads into a ring of stages, consumer only releases them.
+void tma_probe_launch(const CUtensorMap& tm, const TmaProbeParams& p, int grid, cudaStream_t s);
 void umma_probe_launch(const CUtensorMap& tmT, const CUtensorMap& tmB, float* out, int shift, int use_base_offset,
                        cudaStream_t s);
 
