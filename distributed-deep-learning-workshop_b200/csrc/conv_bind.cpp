@@ -119,6 +119,31 @@ struct ConvPlan {
       const char* off = std::getenv("B200DDL_NO_RESIDENT_FILTER");
       raw.res_b = (raw.block_n == 64 && p.n_blocks == 1 && taps * p.kblocks <= 9 && !(off && off[0] == '1')) ? 1 : 0;
     }
+    // Halo mode: a 3x3 stride-1 conv (9 taps on ONE view forming the full {-1,0,1}^2 offset grid, in any order) over
+    // full-width single-image boxes: one [bw x (bh+2)] load per horizontal offset serves its three vertical taps.
+    // B200DDL_NO_HALO=1 switches it off (A/B measurements).
+    raw.halo = 0;
+    {
+      const char* off = std::getenv("B200DDL_NO_HALO");
+      bool ok = raw.res_b && p.mode == 1 && taps == 9 && views.size() == 1 && bn == 1 && bw == views[0].size(2) &&
+                bw == Wo && bw * (bh + 2) <= 224 && !(off && off[0] == '1');
+      int8_t table[9];
+      for (int i = 0; i < 9; ++i) table[i] = -1;
+      for (int t = 0; ok && t < 9; ++t) {
+        const int dwv = p.tap_dw[t], dhv = p.tap_dh[t];
+        if (p.tap_map[t] != 0 || dwv < -1 || dwv > 1 || dhv < -1 || dhv > 1 || table[(dwv + 1) * 3 + (dhv + 1)] != -1) ok = false;
+        else table[(dwv + 1) * 3 + (dhv + 1)] = (int8_t)t;
+      }
+      if (ok) {
+        raw.halo = 1;
+        p.halo = 1;
+        p.halo_bytes = (int)(bw * (bh + 2) * 128);
+        p.halo_dh0 = -1;
+        for (int hs = 0; hs < 3; ++hs) p.halo_dw[hs] = (int8_t)(hs - 1);
+        for (int i = 0; i < 9; ++i) p.halo_tap[i] = table[i];
+        raw.tmA[1] = map_nhwc(views[0], 64, (int)bw, (int)bh + 2, 1);
+      }
+    }
     raw.tmY = raw.tmD;
     if (raw.stats == 2) {
       // fused BatchNorm-backward reduction: y has exactly the output's shape / layout
@@ -157,6 +182,7 @@ struct ConvPlan {
   int grid() const { return raw.grid; }
   int block_n() const { return raw.block_n; }
   int res_b() const { return raw.res_b; }
+  int halo() const { return raw.halo; }
 };
 
 struct WgradPlan {
@@ -387,7 +413,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readonly("launches", &b200::ConvPlan::launches)
       .def_property_readonly("grid", &b200::ConvPlan::grid)
       .def_property_readonly("block_n", &b200::ConvPlan::block_n)
-      .def_property_readonly("resident_filter", &b200::ConvPlan::res_b);
+      .def_property_readonly("resident_filter", &b200::ConvPlan::res_b)
+      .def_property_readonly("halo", &b200::ConvPlan::halo);
   py::class_<b200::WgradPlan>(m, "WgradPlan")
       .def(py::init<at::Tensor, std::vector<at::Tensor>, at::Tensor, int64_t, int64_t, std::vector<int64_t>,
                     std::vector<int64_t>, std::vector<int64_t>, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t>(),

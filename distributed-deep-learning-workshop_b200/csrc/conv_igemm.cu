@@ -55,10 +55,10 @@ CUtensorMap encode_bf16(void* ptr, int rank, const uint64_t* dims, const uint64_
 }
 
 
-template <int BN, int ST, bool RB = false>
+template <int BN, int ST, bool RB = false, bool HL = false>
 static void launch_t(const ConvPlanRaw& pl, cudaStream_t s) {
-  auto kern = conv_igemm_kernel<BN, ST, RB>;
-  using L = ConvSmem<BN, ST, RB>;
+  auto kern = conv_igemm_kernel<BN, ST, RB, HL>;
+  using L = ConvSmem<BN, ST, RB, HL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -76,6 +76,7 @@ template <int ST>
 static void launch_n(const ConvPlanRaw& pl, cudaStream_t s) {
   if (pl.block_n == 256) launch_t<256, ST>(pl, s);
   else if (pl.block_n == 128) launch_t<128, ST>(pl, s);
+  else if (pl.res_b && pl.halo) launch_t<64, ST, true, true>(pl, s);
   else if (pl.res_b) launch_t<64, ST, true>(pl, s);
   else launch_t<64, ST>(pl, s);
 }

@@ -35,12 +35,15 @@ struct TmapArray4 {
 // measured L2 -> SM cap (~42.6 B/clk/SM) with a third of those bytes being the same 72 KB of weights re-read per tile.
 constexpr int kResBBytes = 9 * 64 * kBlockK * 2;  // 72 KB: 9 taps of a 64 x 64 filter (or 4 k-blocks x 2 ... any <= 9 tiles)
 
-template <int BLOCK_N, int kStats = 0, bool kResB = false>
+constexpr int kHaloRows = 224;  // largest halo box: bw * (bh + 2) pixels (56 x 4); 28 KB per stage
+
+template <int BLOCK_N, int kStats = 0, bool kResB = false, bool kHalo = false>
 struct ConvSmem {
   static constexpr int kYBytes = kStats == 2 ? 2 * kBlockM * 128 : 0;  // two 128x64 bf16 tiles of y
   static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kASlot = kHalo ? kHaloRows * 128 : kABytes;     // bytes of A per pipeline stage
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kResB ? kABytes : kABytes + kBBytes;
+  static constexpr int kStageBytes = kResB ? kASlot : kASlot + kBBytes;
   static constexpr int kResBytes = kResB ? kResBBytes : 0;
   static constexpr int kStagingBytes = 2 * kBlockM * 128;  // two 128x64 bf16 store buffers
   static constexpr int kBarBytes = 256;
@@ -50,16 +53,17 @@ struct ConvSmem {
                                        : ((BLOCK_N == 256) ? (kStats == 2 ? 3 : 4) : (BLOCK_N == 128 ? 5 : 6));
   static constexpr int kTotal = kStages * kStageBytes + kFixed;
   static_assert(!kResB || BLOCK_N == 64, "resident filter: BLOCK_N == 64 only");
+  static_assert(!kHalo || kResB, "halo mode builds on the resident filter");
   static_assert(kStages >= 3 && 2 * kStages + 7 <= kBarBytes / 8, "pipeline depth / barrier area");
   static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
 };
 
-template <int BLOCK_N, int kStats, bool kResB = false>
+template <int BLOCK_N, int kStats, bool kResB = false, bool kHalo = false>
 __global__ void __launch_bounds__(kStats ? 384 : 256, 1)
 conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY,
                   const __grid_constant__ ConvParams p) {
-  using L = ConvSmem<BLOCK_N, kStats, kResB>;
+  using L = ConvSmem<BLOCK_N, kStats, kResB, kHalo>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 
@@ -67,7 +71,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * L::kABytes;  // per-stage B tiles, or (kResB) the resident filter slice
+  uint8_t* sB = smem + kStages * L::kASlot;  // per-stage B tiles, or (kResB) the resident filter slice
   uint8_t* sStage = smem + kStages * L::kStageBytes + L::kResBytes;
   uint8_t* sY = sStage + L::kStagingBytes;  // kStats == 2 only
   uint64_t* bars = reinterpret_cast<uint64_t*>(sY + L::kYBytes);
@@ -120,7 +124,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
 
   const int k_iters = p.taps * p.kblocks;
   const uint32_t a_bytes = (p.mode == 0 ? kBlockM : p.valid_rows) * 128;
-  const uint32_t stage_tx = kResB ? a_bytes : a_bytes + L::kBBytes;
+  const uint32_t stage_tx = kHalo ? static_cast<uint32_t>(p.halo_bytes) : (kResB ? a_bytes : a_bytes + L::kBBytes);
 
   // The two single-thread roles below were the bottleneck of the small-K / small-N layers (ncu, 3x3 64->64 @56^2: tensor
   // pipe 22 %, L2 32 %, both role threads busy ~90 % of the time executing ~70-100 dependent instructions per 24 KB
@@ -156,6 +160,24 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
           h0 = th * bh;
           n0 = (rest / tiles_h) * bn;
         }
+        if (kHalo) {
+          // one [bw x (bh+2)] box per horizontal tap offset; rows above / below / beside the image are zero-filled
+          for (int hs = 0; hs < 3; ++hs) {
+            const int cw = w0 + p.halo_dw[hs];
+            const int ch = h0 + p.halo_dh0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+              mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+              const uint32_t fb = full0 + stage * 8;
+              mbar_arrive_expect_tx_u32(fb, stage_tx);
+              tma_load_4d_u32(sA0 + stage * L::kASlot, &tmA.m[1], fb, kb * kBlockK, cw, ch, n0);
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+          continue;
+        }
         const int m0 = m_tile * kBlockM;
         const int brow = nb * BLOCK_N;
         for (int t = 0; t < taps; ++t) {
@@ -168,9 +190,9 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
             const uint32_t fb = full0 + stage * 8;
             mbar_arrive_expect_tx_u32(fb, stage_tx);
             if (flat)
-              tma_load_2d_u32(sA0 + stage * L::kABytes, am, fb, kb * kBlockK, m0);
+              tma_load_2d_u32(sA0 + stage * L::kASlot, am, fb, kb * kBlockK, m0);
             else
-              tma_load_4d_u32(sA0 + stage * L::kABytes, am, fb, kb * kBlockK, cw, ch, n0);
+              tma_load_4d_u32(sA0 + stage * L::kASlot, am, fb, kb * kBlockK, cw, ch, n0);
             if (!kResB) tma_load_2d_u32(sB0 + stage * L::kBBytes, &tmB, fb, kb * kBlockK, b1);
             if (++stage == kStages) {
               stage = 0;
@@ -199,10 +221,36 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
         mbar_wait_u32(tempty0 + acc * 8, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int it = 0; it < k_iters; ++it) {
+        if (kHalo) {
+          const int kblocks = p.kblocks;
+          const uint32_t shift16 = static_cast<uint32_t>(p.bw) * 8;  // bw rows of 128 B, in the (addr >> 4) field
+          for (int hs = 0; hs < 3; ++hs) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+              mbar_wait_u32(full0 + stage * 8, phase);
+              tc_fence_after();
+              const uint64_t da_s = da0 + static_cast<uint32_t>(stage * (L::kASlot >> 4));
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                // vertical tap r reads the same stage bw * r rows further down (row-shifted SWIZZLE_128B start address
+                // with base_offset 0 is exact - csrc/umma_probe.cu); rows past the pixel box feed discarded lanes
+                const uint64_t da = da_s + r * shift16;
+                const uint64_t db = db0 + static_cast<uint32_t>((p.halo_tap[hs * 3 + r] * kblocks + kb) * (L::kBBytes >> 4));
+                umma_bf16(d_tmem, da, db, idesc, (hs | kb | r) != 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 1; k < kBlockK / 16; ++k) umma_bf16_acc(d_tmem, da + 2 * k, db + 2 * k, idesc);
+              }
+              umma_commit_u32(empty0 + stage * 8);
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+        for (int it = 0; it < (kHalo ? 0 : k_iters); ++it) {
           mbar_wait_u32(full0 + stage * 8, phase);
           tc_fence_after();
-          const uint64_t da = da0 + static_cast<uint32_t>(stage * (L::kABytes >> 4));
+          const uint64_t da = da0 + static_cast<uint32_t>(stage * (L::kASlot >> 4));
           const uint64_t db = db0 + static_cast<uint32_t>((kResB ? it : stage) * (L::kBBytes >> 4));
           // 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field per k-step
           umma_bf16(d_tmem, da, db, idesc, it != 0 ? 1u : 0u);

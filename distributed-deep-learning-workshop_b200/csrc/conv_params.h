@@ -26,6 +26,13 @@ struct ConvParams {
   float* stat_sqsum;  // [Cout] or nullptr   (mode 2: sum dz*y)
   const float* bn_scale;  // mode 2: forward BN affine of the activation whose gradient this GEMM produces
   const float* bn_shift;
+  // Halo mode (3x3 stride 1, full-width pixel boxes, resident filter): ONE [bw x (bh+2)] box per horizontal tap offset
+  // (tensor map 1 of the A array) serves the three vertical taps at row offsets 0, bw, 2*bw of the stage.
+  int halo;              // 0 / 1
+  int halo_bytes;        // bw * (bh + 2) * 128
+  int8_t halo_dw[3];     // horizontal offset of stage s
+  int8_t halo_dh0;       // vertical offset of row-shift 0 (normally -1)
+  int8_t halo_tap[9];    // filter tap index of (stage s, row shift r) at [s * 3 + r]
 };
 
 // Weight-gradient GEMM:  dW[tap][co][ci] += sum_px dY[px, co] * X_tap[px, ci]

@@ -9,6 +9,8 @@ Zero padding is the TMA out-of-bounds fill.  The reference delegates all of this
 """
 from __future__ import annotations
 
+import os
+
 import weakref
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
@@ -54,6 +56,23 @@ def pick_box(n: int, h: int, w: int, rows: int = 128, multiple_of: int = 1) -> T
     if best is None:
         raise ValueError(f"no pixel box for grid {(n, h, w)} rows<={rows} multiple_of={multiple_of}")
     return best[1]
+
+
+def halo_box(h: int, w: int, cin: int, cout: int, R: int, S: int, stride: int, pad: int) -> Optional[Tuple[int, int, int]]:
+    """Full-width single-image box (w, bh, 1) for the kernel's halo mode, or None when the layer does not qualify.
+
+    Halo mode (csrc/conv_igemm.cuh): 3x3 / stride 1 / pad 1 with a resident 64x64 filter; one [w x (bh+2)] load per
+    horizontal tap offset serves the three vertical taps, so a stage (28 KB) must hold w * (bh + 2) <= 224 pixels and the
+    MMA tile w * bh <= 128.  `B200DDL_NO_HALO=1` keeps the generic boxes (A/B measurements)."""
+    if os.environ.get("B200DDL_NO_HALO") == "1" or os.environ.get("B200DDL_NO_RESIDENT_FILTER") == "1":
+        return None
+    if not (R == 3 and S == 3 and stride == 1 and pad == 1 and cin == 64 and cout == 64):
+        return None
+    best = None
+    for bh in _divisors(h):
+        if w * bh <= 128 and w * (bh + 2) <= 224:
+            best = bh if best is None else max(best, bh)
+    return None if best is None else (w, best, 1)
 
 
 @dataclass
@@ -111,7 +130,8 @@ class ConvForward:
         if flat:
             bw = bh = bn = 0
         else:
-            bw, bh, bn = pick_box(N, Ho, Wo)
+            cout_, cin_ = w.shape[0] // (R * S), w.shape[1]
+            bw, bh, bn = halo_box(Ho, Wo, cin_, cout_, R, S, stride, pad) or pick_box(N, Ho, Wo)
         self.box = (bw, bh, bn)
         self.plan = ext.ConvPlan(taps.views, w, y, taps.tap_map, taps.tap_dw, taps.tap_dh, bw, bh, bn,
                                  stat_sum, stat_sqsum, max_ctas)
@@ -157,7 +177,8 @@ class ConvDgrad:
             else:
                 wbuf = wbuf.view(len(idx) * cin, cout)
             flat = (R == 1 and S == 1 and pad == 0 and dy.is_contiguous() and dx.is_contiguous())
-            box = (0, 0, 0) if flat else pick_box(N, dx.shape[1], dx.shape[2])
+            box = (0, 0, 0) if flat else (halo_box(dx.shape[1], dx.shape[2], cout, cin, R, S, 1, R - 1 - pad)
+                                          or pick_box(N, dx.shape[1], dx.shape[2]))
             if self.fused_bwd_stats:
                 y, sc, sh, s_dz, s_dzy = bwd_stats
                 plan = ext.ConvPlan([dy], wbuf, dx, tm, dw, dh, box[0], box[1], box[2], s_dz, s_dzy, max_ctas, y, sc, sh)

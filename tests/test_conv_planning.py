@@ -51,3 +51,19 @@ def test_weight_layout_roundtrip():
     ws = torch.randn(49, 64, 3)
     C.pack_stem_weight(ws, out)
     assert torch.equal(out[5, 3 * 17 + 2], ws[17, 5, 2]) and float(out[:, 147:].abs().sum()) == 0.0
+
+
+def test_halo_box_selection(monkeypatch):
+    """Full-width single-image boxes only for the 3x3 / stride-1 / 64->64 layers whose box + halo fits one 28 KB stage."""
+    from b200ddl.ops import conv as C
+
+    monkeypatch.delenv("B200DDL_NO_HALO", raising=False)
+    monkeypatch.delenv("B200DDL_NO_RESIDENT_FILTER", raising=False)
+    assert C.halo_box(56, 56, 64, 64, 3, 3, 1, 1) == (56, 2, 1)      # 112-pixel tile, 224-pixel halo stage
+    assert C.halo_box(28, 28, 64, 64, 3, 3, 1, 1) == (28, 4, 1)
+    assert C.halo_box(56, 56, 128, 128, 3, 3, 1, 1) is None          # filter does not fit resident
+    assert C.halo_box(56, 56, 64, 64, 3, 3, 2, 1) is None            # strided
+    assert C.halo_box(56, 56, 64, 64, 1, 1, 1, 0) is None
+    assert C.halo_box(112, 112, 64, 64, 3, 3, 1, 1) is None          # one image row + halo exceeds a stage
+    monkeypatch.setenv("B200DDL_NO_HALO", "1")
+    assert C.halo_box(56, 56, 64, 64, 3, 3, 1, 1) is None
