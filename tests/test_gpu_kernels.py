@@ -88,3 +88,16 @@ def test_fused_allreduce_two_gpus():
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
     assert "ALLREDUCE CHECK PASS" in p.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_allreduce_sgd_matches_unfused_two_gpus():
+    """all-reduce + SGD-momentum + weight multicast in ONE kernel == NCCL average followed by a plain fp32 update."""
+    import subprocess
+
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29733",
+                        os.path.join(ROOT, "benchmarks", "fused_update_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "FUSED UPDATE CHECK PASS" in p.stdout or "UNAVAILABLE" in p.stdout
