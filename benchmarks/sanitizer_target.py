@@ -18,3 +18,8 @@ step.optimizer.begin_step()
 step._launch()
 torch.cuda.synchronize()
 print("loss", eng.loss_and_acc())
+from b200ddl.ops import conv as _C
+
+plans = [pl for pl in _C._plans if hasattr(pl, "halo")]
+print(f"conv plans exercised: {len(plans)} total, {sum(pl.resident_filter for pl in plans)} resident-filter, "
+      f"{sum(pl.halo for pl in plans)} halo-mode")
