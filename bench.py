@@ -121,6 +121,7 @@ def main():
     ap.add_argument("--graph-baseline", action="store_true")
     ap.add_argument("--optimizer", default="sgd", choices=["sgd", "adam"])
     ap.add_argument("--no-fuse-bwd-reduce", action="store_true")
+    ap.add_argument("--fuse-bn-coeffs", action="store_true", help="opt-in: BN coefficients inside the apply kernels (measured slower)")
     ap.add_argument("--overlap-wgrad", action="store_true", help="(default; kept for old command lines) weight-gradient GEMMs on a side stream")
     ap.add_argument("--no-overlap-wgrad", action="store_true", help="issue the weight-gradient GEMMs in line on the compute stream")
     ap.add_argument("--wgrad-smem", type=int, default=0)
@@ -151,7 +152,7 @@ def main():
 
     engine = ResNet50Engine(batch=args.batch, num_classes=args.classes, device=dev, seed=0, max_ctas=0,
                             overlap_wgrad=not args.no_overlap_wgrad, wgrad_smem_budget=args.wgrad_smem,
-                            fuse_bwd_reduce=not args.no_fuse_bwd_reduce)
+                            fuse_bwd_reduce=not args.no_fuse_bwd_reduce, fuse_bn_coeffs=args.fuse_bn_coeffs)
     lr = 0.1 * world  # LR x world size (reference P1/03:301)
     base_opt = optim.SGD(lr, momentum=0.9, weight_decay=1e-4) if args.optimizer == "sgd" else optim.Adam(1e-3 * world)
     opt = (dist.DistributedOptimizer(base_opt, bucket_mb=args.bucket_mb, algo=args.algo, fused_update=args.fused_update)

@@ -236,6 +236,50 @@ def case_elementwise():
         yr3 = yf.clone().requires_grad_(True)
         torch.nn.functional.batch_norm(yr3, None, None, gamma, beta, True, 0.1, 1e-5).backward(gout.float())
         ok &= report(f"bn_bwd_dy_mode3/C{C_}", rel_err(dy3, yr3.grad), 2e-2)
+        # ---- fused coefficient variants: same results as finalize + apply / coeffs + apply without the tiny launches
+        def fresh_pack(src, ga, be):
+            s_ = torch.zeros(C_, device=DEV); q_ = torch.zeros(C_, device=DEV)
+            e.channel_stats(src, s_, q_)
+            return [s_, q_, ga, be, torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV), torch.empty(C_, device=DEV),
+                    torch.empty(C_, device=DEV), torch.empty(C_, device=DEV), torch.empty(C_, device=DEV)]
+
+        pk = fresh_pack(y, gamma, beta)
+        out_f = torch.empty_like(y)
+        mask_f = torch.zeros(M * C_ // 8, device=DEV, dtype=torch.uint8)
+        e.bn_apply_fused(y, pk, float(M), 0.1, 1e-5, res, None, out_f, True, mask_f)
+        ok &= report(f"bn_apply_fused_out/C{C_}", rel_err(out_f, out), 4e-3, f"mismatching elements {float((out_f != out).float().mean()):.2e}")
+        ok &= report(f"bn_apply_fused_mask/C{C_}", float((mask_f != mask).float().mean()), 1e-4)
+        for nm, a_, b_ in (("mean", pk[6], mean), ("invstd", pk[7], invstd), ("scale", pk[8], scale), ("shift", pk[9], shift),
+                           ("running_mean", pk[4], rm), ("running_var", pk[5], rv)):
+            ok &= report(f"bn_apply_fused_{nm}/C{C_}", rel_err(a_, b_), 2e-6)
+        ok &= report(f"bn_apply_fused_sums_untouched/C{C_}", float(pk[0].abs().max() == 0), 0.0)
+        # residual with its own BatchNorm (downsample branch)
+        gamma_r = torch.rand(C_, device=DEV, generator=g) + 0.5
+        beta_r = torch.randn(C_, device=DEV, generator=g)
+        pk_m, pk_r = fresh_pack(y, gamma, beta), fresh_pack(res, gamma_r, beta_r)
+        out_f2 = torch.empty_like(y)
+        e.bn_apply_fused(y, pk_m, float(M), 0.1, 1e-5, res, pk_r, out_f2, True, None)
+        sr = torch.zeros(C_, device=DEV); qr = torch.zeros(C_, device=DEV)
+        e.channel_stats(res, sr, qr)
+        r_mean = torch.empty(C_, device=DEV); r_is = torch.empty(C_, device=DEV)
+        r_scale = torch.empty(C_, device=DEV); r_shift = torch.empty(C_, device=DEV)
+        e.bn_finalize(sr, qr, float(M), gamma_r, beta_r, torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV), 0.1, 1e-5,
+                      r_mean, r_is, r_scale, r_shift, True)
+        out_u2 = torch.empty_like(y)
+        e.bn_apply(y, scale, shift, res, r_scale, r_shift, out_u2, True)
+        ok &= report(f"bn_apply_fused_bn_residual/C{C_}", rel_err(out_f2, out_u2), 4e-3)
+        ok &= report(f"bn_apply_fused_res_scale/C{C_}", rel_err(pk_r[8], r_scale), 2e-6)
+        # backward: A, B, C in the apply prologue, dgamma / dbeta written by the kernel
+        s2 = torch.zeros(C_, device=DEV); s2y = torch.zeros(C_, device=DEV)
+        e.bn_bwd_reduce(2, gout, None, None, y, scale, shift, None, s2, s2y)
+        dg_f = torch.empty(C_, device=DEV); db_f = torch.empty(C_, device=DEV); dy_f = torch.empty_like(y)
+        e.bn_bwd_apply_fused(gout, y, scale, shift, s2, s2y, gamma, mean, invstd, float(M), dg_f, db_f, dy_f)
+        dg_u = torch.empty(C_, device=DEV); db_u = torch.empty(C_, device=DEV); dy_u = torch.empty_like(y)
+        e.bn_bwd_coeffs(s2, s2y, gamma, mean, invstd, float(M), dg_u, db_u, cA, cB, cC)
+        e.bn_bwd_apply(gout, y, scale, shift, cA, cB, cC, dy_u)
+        ok &= report(f"bn_bwd_apply_fused_dy/C{C_}", rel_err(dy_f, dy_u), 4e-3)
+        ok &= report(f"bn_bwd_apply_fused_dgamma/C{C_}", rel_err(dg_f, dg_u), 2e-6)
+        ok &= report(f"bn_bwd_apply_fused_dbeta/C{C_}", rel_err(db_f, db_u), 2e-6)
         # autograd reference
         yr = yf.clone().requires_grad_(True)
         gr = gamma.clone().requires_grad_(True); br = beta.clone().requires_grad_(True)
@@ -386,7 +430,7 @@ def case_conv_time():
     return True
 
 
-def case_engine(overlap_wgrad: bool = True, quick: bool = False):
+def case_engine(overlap_wgrad: bool = True, quick: bool = False, fuse_bn_coeffs: bool = False):
     """ResNet-50 engine forward/backward vs torchvision (same weights, fp32 reference and bf16-autocast reference).
 
     `overlap_wgrad` selects where the weight-gradient GEMMs are issued (side stream = the engine default, or in line);
@@ -397,8 +441,10 @@ def case_engine(overlap_wgrad: bool = True, quick: bool = False):
 
     ok = True
     N, K = 32, 10
-    eng = ResNet50Engine(batch=N, num_classes=K, zero_init_residual=False, seed=1, overlap_wgrad=overlap_wgrad)
-    print(f"INFO engine overlap_wgrad={eng.overlap_wgrad} fuse_bwd_reduce={eng.fuse_bwd_reduce}", flush=True)
+    eng = ResNet50Engine(batch=N, num_classes=K, zero_init_residual=False, seed=1, overlap_wgrad=overlap_wgrad,
+                         fuse_bn_coeffs=fuse_bn_coeffs)
+    print(f"INFO engine overlap_wgrad={eng.overlap_wgrad} fuse_bwd_reduce={eng.fuse_bwd_reduce} "
+          f"fuse_bn_coeffs={eng.fuse_bn_coeffs}", flush=True)
     opt = optim.SGD(learning_rate=0.1, momentum=0.9)
     step = EngineTrainStep(eng, opt, use_graph=False)
     g = torch.Generator(device=DEV).manual_seed(5)
@@ -650,6 +696,7 @@ CASES = {
     "engine": case_engine,
     "tma_probe": case_tma_probe,
     "engine_serial_wgrad": lambda: case_engine(overlap_wgrad=False, quick=True),
+    "engine_fused_bn_coeffs": lambda: case_engine(quick=True, fuse_bn_coeffs=True),
     "stem": case_stem,
     "umma_probe": case_umma_probe,
 }

@@ -83,16 +83,64 @@ void bn_finalize(float* sum, float* sqsum, double count, const float* gamma, con
                                                       shift, C, training ? 1 : 0);
 }
 
+// In-kernel versions of bn_finalize_kernel / bn_bwd_coeffs_kernel for 8 consecutive channels (same expressions).
+__device__ __forceinline__ void bn_fwd_coeffs8(const BnFwdFuse& f, int c0, bool writer, float (&sc)[8], float (&sh)[8]) {
+  float su[8], sq[8], ga[8], be[8];
+  ldf8(f.sum + c0, su);
+  ldf8(f.sqsum + c0, sq);
+  ldf8(f.gamma + c0, ga);
+  ldf8(f.beta + c0, be);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float m = su[k] * f.inv_count;
+    const float var = fmaxf(sq[k] * f.inv_count - m * m, 0.f);
+    const float is = rsqrtf(var + f.eps);
+    sc[k] = ga[k] * is;
+    sh[k] = be[k] - m * sc[k];
+    if (writer) {
+      const int c = c0 + k;
+      f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * m;
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * var * f.unbias;
+      f.mean[c] = m;
+      f.invstd[c] = is;
+      f.scale[c] = sc[k];
+      f.shift[c] = sh[k];
+    }
+  }
+}
+__device__ __forceinline__ void bn_bwd_coeffs8(const BnBwdFuse& f, int c0, bool writer, float (&A)[8], float (&B)[8],
+                                               float (&Cc)[8]) {
+  float sz[8], szy[8], ga[8], me[8], is[8];
+  ldf8(f.sum_dz + c0, sz);
+  ldf8(f.sum_dzy + c0, szy);
+  ldf8(f.gamma + c0, ga);
+  ldf8(f.mean + c0, me);
+  ldf8(f.invstd + c0, is);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float db = sz[k];
+    const float dg = is[k] * (szy[k] - me[k] * db);
+    A[k] = ga[k] * is[k];
+    B[k] = -A[k] * is[k] * dg * f.inv_count;
+    Cc[k] = -A[k] * db * f.inv_count - B[k] * me[k];
+    if (writer) {
+      f.dgamma[c0 + k] = dg;
+      f.dbeta[c0 + k] = db;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ BN apply
 // out = [relu]( y*scale + shift  [+ res | + res*res_scale + res_shift] )
 // Column-resident: a thread owns one 8-channel column vector and walks down the rows, so the per-channel
 // parameters are loaded into registers once instead of once per element (L1 traffic was 5x the payload).
-template <bool RELU, int RES>  // RES: 0 none, 1 identity residual, 2 residual with its own BN
+template <bool RELU, int RES, bool FUSED = false>  // RES: 0 none, 1 identity residual, 2 residual with its own BN
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                 const float* __restrict__ res_scale, const float* __restrict__ res_shift,
-                __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ mask, int64_t M, int C) {
+                __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ mask, int64_t M, int C,
+                const BnFwdFuse fz = BnFwdFuse(), const BnFwdFuse rz = BnFwdFuse()) {
   const int cvec = C / 8;
   const int lanes = cvec < (int)blockDim.x ? cvec : blockDim.x;
   const int rpb = blockDim.x / lanes;
@@ -101,11 +149,17 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
   if (ry >= rpb) return;
   for (int cv = cx; cv < cvec; cv += lanes) {
     float sc[8], sh[8], rs[8], rh[8];
-    ldf8(scale + cv * 8, sc);
-    ldf8(shift + cv * 8, sh);
-    if (RES == 2) {
-      ldf8(res_scale + cv * 8, rs);
-      ldf8(res_shift + cv * 8, rh);
+    if (FUSED) {
+      const bool writer = blockIdx.x == 0 && ry == 0;  // one thread per 8-channel column writes the saved statistics
+      bn_fwd_coeffs8(fz, cv * 8, writer, sc, sh);
+      if (RES == 2) bn_fwd_coeffs8(rz, cv * 8, writer, rs, rh);
+    } else {
+      ldf8(scale + cv * 8, sc);
+      ldf8(shift + cv * 8, sh);
+      if (RES == 2) {
+        ldf8(res_scale + cv * 8, rs);
+        ldf8(res_shift + cv * 8, rh);
+      }
     }
     for (int64_t r = (int64_t)blockIdx.x * rpb + ry; r < M; r += (int64_t)gridDim.x * rpb) {
       const int64_t off = r * C + cv * 8;
@@ -159,6 +213,25 @@ void bn_apply(const void* y, const float* scale, const float* shift, const void*
   auto MK = (uint8_t*)mask;
   const int rmode = res == nullptr ? 0 : (res_scale == nullptr ? 1 : 2);
 #define LAUNCH(RL, RM) bn_apply_kernel<RL, RM><<<blocks, threads, 0, s>>>(Y, scale, shift, R, res_scale, res_shift, O, MK, M, C)
+  if (relu) {
+    if (rmode == 0) LAUNCH(true, 0); else if (rmode == 1) LAUNCH(true, 1); else LAUNCH(true, 2);
+  } else {
+    if (rmode == 0) LAUNCH(false, 0); else if (rmode == 1) LAUNCH(false, 1); else LAUNCH(false, 2);
+  }
+#undef LAUNCH
+}
+
+void bn_apply_fused(const void* y, const BnFwdFuse& f, const void* res, const BnFwdFuse* res_f, void* out, void* mask,
+                    int64_t M, int C, bool relu, cudaStream_t s) {
+  const int threads = 256;
+  const int blocks = rows_grid(M, C, threads);
+  auto Y = (const __nv_bfloat16*)y;
+  auto R = (const __nv_bfloat16*)res;
+  auto O = (__nv_bfloat16*)out;
+  auto MK = (uint8_t*)mask;
+  const int rmode = res == nullptr ? 0 : (res_f == nullptr ? 1 : 2);
+  const BnFwdFuse rz = res_f != nullptr ? *res_f : BnFwdFuse();
+#define LAUNCH(RL, RM) bn_apply_kernel<RL, RM, true><<<blocks, threads, 0, s>>>(Y, nullptr, nullptr, R, nullptr, nullptr, O, MK, M, C, f, rz)
   if (relu) {
     if (rmode == 0) LAUNCH(true, 0); else if (rmode == 1) LAUNCH(true, 1); else LAUNCH(true, 2);
   } else {
@@ -329,12 +402,13 @@ void bn_bwd_coeffs(float* sum_dz, float* sum_dzy, const float* gamma, const floa
 
 // dy = A*dz + B*y + Cc  with dz either read as-is (MASK=false: stored dz / BN without ReLU) or recomputed as
 // g * (y*scale + shift > 0) (MASK=true).  Column-resident like bn_apply_kernel.
-template <bool MASK>
+template <bool MASK, bool FUSED = false>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ cA, const float* __restrict__ cB,
-                    const float* __restrict__ cC, __nv_bfloat16* __restrict__ dy, int64_t M, int C) {
+                    const float* __restrict__ cC, __nv_bfloat16* __restrict__ dy, int64_t M, int C,
+                    const BnBwdFuse fz = BnBwdFuse()) {
   const int cvec = C / 8;
   const int lanes = cvec < (int)blockDim.x ? cvec : blockDim.x;
   const int rpb = blockDim.x / lanes;
@@ -343,9 +417,13 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
   if (ry >= rpb) return;
   for (int cv = cx; cv < cvec; cv += lanes) {
     float A[8], B[8], Cc[8], sc[8], sh[8];
-    ldf8(cA + cv * 8, A);
-    ldf8(cB + cv * 8, B);
-    ldf8(cC + cv * 8, Cc);
+    if (FUSED) {
+      bn_bwd_coeffs8(fz, cv * 8, blockIdx.x == 0 && ry == 0, A, B, Cc);
+    } else {
+      ldf8(cA + cv * 8, A);
+      ldf8(cB + cv * 8, B);
+      ldf8(cC + cv * 8, Cc);
+    }
     if (MASK) {
       ldf8(scale + cv * 8, sc);
       ldf8(shift + cv * 8, sh);
@@ -375,6 +453,18 @@ void bn_bwd_apply(const void* g, const void* y, const float* scale, const float*
   else
     bn_bwd_apply_kernel<false><<<blocks, threads, 0, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y, scale,
                                                           shift, cA, cB, cC, (__nv_bfloat16*)dy, M, C);
+}
+
+void bn_bwd_apply_fused(const void* g, const void* y, const float* scale, const float* shift, const BnBwdFuse& f, void* dy,
+                        int64_t M, int C, cudaStream_t s) {
+  const int threads = 256;
+  const int blocks = rows_grid(M, C, threads);
+  if (scale != nullptr)
+    bn_bwd_apply_kernel<true, true><<<blocks, threads, 0, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y, scale,
+                                                               shift, nullptr, nullptr, nullptr, (__nv_bfloat16*)dy, M, C, f);
+  else
+    bn_bwd_apply_kernel<false, true><<<blocks, threads, 0, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y, scale,
+                                                                shift, nullptr, nullptr, nullptr, (__nv_bfloat16*)dy, M, C, f);
 }
 
 // ------------------------------------------------------------------------------------------------ max pool 3x3 s2 p1

@@ -5,6 +5,35 @@
 
 namespace b200 {
 
+// Optional in-kernel BatchNorm coefficient computation (replaces a separate bn_finalize / bn_bwd_coeffs launch on the
+// critical path).  sum == nullptr / sum_dz == nullptr selects the unfused behaviour (coefficients read from arrays).
+struct BnFwdFuse {
+  const float* sum;      // per-channel sum(y), sum(y^2) accumulated by the conv epilogue (zeroed once per step by the engine)
+  const float* sqsum;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;   // updated by the first row-block
+  float* running_var;
+  float* mean;           // written by the first row-block for the backward pass
+  float* invstd;
+  float* scale;
+  float* shift;
+  float inv_count, unbias, momentum, eps;
+};
+struct BnBwdFuse {
+  const float* sum_dz;   // per-channel sum(dz), sum(dz*y) (zeroed once per step by the engine)
+  const float* sum_dzy;
+  const float* gamma;
+  const float* mean;
+  const float* invstd;
+  float* dgamma;         // written by the first row-block
+  float* dbeta;
+  float inv_count;
+};
+void bn_apply_fused(const void* y, const BnFwdFuse& f, const void* res, const BnFwdFuse* res_f, void* out, void* mask,
+                    int64_t M, int C, bool relu, cudaStream_t s);
+void bn_bwd_apply_fused(const void* g, const void* y, const float* scale, const float* shift, const BnBwdFuse& f, void* dy,
+                        int64_t M, int C, cudaStream_t s);
 void bn_finalize(float* sum, float* sqsum, double count, const float* gamma, const float* beta, float* running_mean,
                  float* running_var, float momentum, float eps, float* mean, float* invstd, float* scale,
                  float* shift, int C, bool training, cudaStream_t s);

@@ -2,6 +2,9 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <torch/extension.h>
 
+#include <cstdint>
+#include <vector>
+
 #include "ops_api.h"
 
 namespace {
@@ -91,6 +94,73 @@ void bn_bwd_apply(Tensor g, Tensor y, OptT scale, OptT shift, Tensor cA, Tensor 
   const int C = (int)y.size(-1);
   b200::bn_bwd_apply(g.data_ptr(), y.data_ptr(), fp(scale), fp(shift), cA.data_ptr<float>(), cB.data_ptr<float>(),
                      cC.data_ptr<float>(), dy.data_ptr(), y.numel() / C, C, cur());
+  after();
+}
+
+// ---- fused variants: the BatchNorm coefficients are computed inside the consumer kernel (no bn_finalize / bn_bwd_coeffs
+// launch on the critical path); the caller zeroes the sum accumulators once per step.
+static b200::BnFwdFuse fwd_fuse(const Tensor& sum, const Tensor& sqsum, const Tensor& gamma, const Tensor& beta,
+                                const Tensor& rmean, const Tensor& rvar, const Tensor& mean, const Tensor& invstd,
+                                const Tensor& scale, const Tensor& shift, double count, double momentum, double eps, int C) {
+  for (const Tensor* t : {&sum, &sqsum, &gamma, &beta, &rmean, &rvar, &mean, &invstd, &scale, &shift}) {
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kFloat && t->numel() == C && t->is_contiguous(),
+                "fused BN parameter must be a contiguous fp32 CUDA vector of C elements");
+    TORCH_CHECK(reinterpret_cast<uintptr_t>(t->data_ptr()) % 16 == 0, "fused BN parameter must be 16-byte aligned");
+  }
+  b200::BnFwdFuse f;
+  f.sum = sum.data_ptr<float>(); f.sqsum = sqsum.data_ptr<float>();
+  f.gamma = gamma.data_ptr<float>(); f.beta = beta.data_ptr<float>();
+  f.running_mean = rmean.data_ptr<float>(); f.running_var = rvar.data_ptr<float>();
+  f.mean = mean.data_ptr<float>(); f.invstd = invstd.data_ptr<float>();
+  f.scale = scale.data_ptr<float>(); f.shift = shift.data_ptr<float>();
+  f.inv_count = (float)(1.0 / count);
+  f.unbias = count > 1 ? (float)(count / (count - 1.0)) : 1.f;
+  f.momentum = (float)momentum;
+  f.eps = (float)eps;
+  return f;
+}
+
+// pack order (main BN and `res_pack`): sum, sqsum, gamma, beta, running_mean, running_var, mean, invstd, scale, shift
+void bn_apply_fused(Tensor y, std::vector<Tensor> pack, double count, double momentum, double eps, OptT res,
+                    c10::optional<std::vector<Tensor>> res_pack, Tensor out, bool relu, OptT mask) {
+  chk(y, at::kBFloat16, "y");
+  chk(out, at::kBFloat16, "out");
+  const int C = (int)y.size(-1);
+  const int64_t M = y.numel() / C;
+  TORCH_CHECK(C % 8 == 0 && out.numel() == y.numel() && pack.size() == 10);
+  if (res.has_value()) { chk(*res, at::kBFloat16, "res"); TORCH_CHECK(res->numel() == y.numel()); }
+  if (mask.has_value()) { chk(*mask, at::kByte, "mask"); TORCH_CHECK(mask->numel() * 8 == y.numel()); }
+  TORCH_CHECK(!res_pack.has_value() || res.has_value(), "res_pack needs res");
+  b200::BnFwdFuse f = fwd_fuse(pack[0], pack[1], pack[2], pack[3], pack[4], pack[5], pack[6], pack[7], pack[8], pack[9],
+                               count, momentum, eps, C);
+  b200::BnFwdFuse rf;
+  if (res_pack.has_value()) {
+    const auto& q = *res_pack;
+    TORCH_CHECK(q.size() == 10);
+    rf = fwd_fuse(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], count, momentum, eps, C);
+  }
+  b200::bn_apply_fused(y.data_ptr(), f, vp(res), res_pack.has_value() ? &rf : nullptr, out.data_ptr(),
+                       mask.has_value() ? mask->data_ptr() : nullptr, M, C, relu, cur());
+  after();
+}
+
+// dy = A*dz + B*y + C with A, B, C computed in the kernel from sum_dz, sum_dzy; dgamma / dbeta written by the kernel.
+void bn_bwd_apply_fused(Tensor g, Tensor y, OptT scale, OptT shift, Tensor sum_dz, Tensor sum_dzy, Tensor gamma,
+                        Tensor mean, Tensor invstd, double count, Tensor dgamma, Tensor dbeta, Tensor dy) {
+  chk(g, at::kBFloat16, "g");
+  chk(y, at::kBFloat16, "y");
+  chk(dy, at::kBFloat16, "dy");
+  const int C = (int)y.size(-1);
+  for (const Tensor* t : {&sum_dz, &sum_dzy, &gamma, &mean, &invstd, &dgamma, &dbeta}) {
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kFloat && t->numel() == C && t->is_contiguous());
+    TORCH_CHECK(reinterpret_cast<uintptr_t>(t->data_ptr()) % 16 == 0, "fused BN parameter must be 16-byte aligned");
+  }
+  b200::BnBwdFuse f;
+  f.sum_dz = sum_dz.data_ptr<float>(); f.sum_dzy = sum_dzy.data_ptr<float>();
+  f.gamma = gamma.data_ptr<float>(); f.mean = mean.data_ptr<float>(); f.invstd = invstd.data_ptr<float>();
+  f.dgamma = dgamma.data_ptr<float>(); f.dbeta = dbeta.data_ptr<float>();
+  f.inv_count = (float)(1.0 / count);
+  b200::bn_bwd_apply_fused(g.data_ptr(), y.data_ptr(), fp(scale), fp(shift), f, dy.data_ptr(), y.numel() / C, C, cur());
   after();
 }
 
@@ -217,6 +287,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_bwd_reduce", &bn_bwd_reduce);
   m.def("bn_bwd_coeffs", &bn_bwd_coeffs);
   m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("bn_apply_fused", &bn_apply_fused, py::arg("y"), py::arg("pack"), py::arg("count"), py::arg("momentum"),
+        py::arg("eps"), py::arg("res") = c10::nullopt, py::arg("res_pack") = c10::nullopt, py::arg("out"),
+        py::arg("relu") = true, py::arg("mask") = c10::nullopt);
+  m.def("bn_bwd_apply_fused", &bn_bwd_apply_fused);
   m.def("maxpool_fwd", &maxpool_fwd);
   m.def("maxpool_bwd", &maxpool_bwd);
   m.def("bn_relu_maxpool_fwd", &bn_relu_maxpool_fwd);

@@ -20,6 +20,7 @@ Reference call sites this replaces: `build_model` (P1/03:159-178), `model.fit` i
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -85,7 +86,8 @@ class ResNet50Engine:
     def __init__(self, batch: int, num_classes: int = 1000, device: Optional[torch.device] = None,
                  image_size: int = 224, dropout: float = 0.0, bn_momentum: float = 0.1, bn_eps: float = 1e-5,
                  seed: int = 0, max_ctas: int = 0, zero_init_residual: bool = True, native_stem: bool = True,
-                 overlap_wgrad: bool = True, wgrad_smem_budget: int = 0, fuse_bwd_reduce: bool = True):
+                 overlap_wgrad: bool = True, wgrad_smem_budget: int = 0, fuse_bwd_reduce: bool = True,
+                 fuse_bn_coeffs: bool = False):
         ops.require_native()
         self.zero_init_residual = zero_init_residual
         self.native_stem = native_stem
@@ -94,6 +96,11 @@ class ResNet50Engine:
         self.overlap_wgrad = overlap_wgrad
         # BatchNorm-backward reductions of bn1/bn2 computed inside the dgrad GEMM that produces their input gradient
         self.fuse_bwd_reduce = fuse_bwd_reduce
+        # OPT-IN (B200DDL_FUSE_BN_COEFFS=1): BatchNorm scale/shift (forward) and A/B/C (backward) computed inside the apply
+        # kernels instead of 106 tiny launches.  Numerically equivalent (backward bit-identical), but MEASURED SLOWER:
+        # 19.39 vs 18.89 ms per step in an interleaved A/B at equal clocks (profiles/README.md 2.9) - a tiny dependent
+        # kernel costs only ~1.6 us of step time, the per-CTA coefficient recomputation in 106 streaming kernels more.
+        self.fuse_bn_coeffs = fuse_bn_coeffs or os.environ.get("B200DDL_FUSE_BN_COEFFS") == "1"
         self._fused_reduce = set()
         self.wgrad_smem_budget = wgrad_smem_budget
         self.aux_streams: List[torch.cuda.Stream] = []
@@ -251,12 +258,22 @@ class ResNet50Engine:
         self.loss_rows = torch.zeros(N, **f32)
 
         # BN work buffers (per BN): sum, sqsum, mean, invstd, scale, shift, sum_dz, sum_dzy, cA, cB, cC
+        # The four accumulators of ALL layers live in two contiguous buffers so that one memset per pass zeroes them.
         self.bnw: Dict[str, Dict[str, torch.Tensor]] = {}
+        total_c = sum(self.bn_channels[n] for n in self.bn_names)
+        self._bn_fwd_sums = torch.zeros(2, total_c, **f32)   # [sum | sqsum] filled by the conv epilogues
+        self._bn_bwd_sums = torch.zeros(2, total_c, **f32)   # [sum_dz | sum_dzy] filled by reduce kernels / dgrad epilogues
+        off = 0
         for n in self.bn_names:
             c = self.bn_channels[n]
-            buf = torch.zeros(11, c, **f32)
-            keys = ["sum", "sqsum", "mean", "invstd", "scale", "shift", "sum_dz", "sum_dzy", "cA", "cB", "cC"]
+            buf = torch.zeros(7, c, **f32)
+            keys = ["mean", "invstd", "scale", "shift", "cA", "cB", "cC"]
             self.bnw[n] = {k: buf[i] for i, k in enumerate(keys)}
+            self.bnw[n]["sum"] = self._bn_fwd_sums[0, off:off + c]
+            self.bnw[n]["sqsum"] = self._bn_fwd_sums[1, off:off + c]
+            self.bnw[n]["sum_dz"] = self._bn_bwd_sums[0, off:off + c]
+            self.bnw[n]["sum_dzy"] = self._bn_bwd_sums[1, off:off + c]
+            off += c
 
         H0 = S // 2
         self.y0 = torch.zeros(N, H0, H0, 64, **bf)
@@ -379,10 +396,34 @@ class ResNet50Engine:
                             w["invstd"], w["scale"], w["shift"], training)
         return w
 
+    def _bn_pack(self, bn: str) -> List[torch.Tensor]:
+        """Tensors of one BatchNorm in the order csrc/ops_bind.cpp bn_apply_fused expects (parameter views are taken at
+        call time: the flat parameter buffer may have been moved into symmetric memory after build())."""
+        w = self.bnw[bn]
+        return [w["sum"], w["sqsum"], self.p(bn + ".weight"), self.p(bn + ".bias"), self.running_mean[bn],
+                self.running_var[bn], w["mean"], w["invstd"], w["scale"], w["shift"]]
+
+    def _bn_apply(self, bn: str, count: float, training: bool, y, out, res=None, res_bn: Optional[str] = None,
+                  mask=None) -> None:
+        """out = relu(BN(y) [+ res | + BN_res(res)]); the coefficient computation is fused into the kernel in training."""
+        e = self._e
+        if training and self.fuse_bn_coeffs:
+            e.bn_apply_fused(y, self._bn_pack(bn), float(count), self.bn_momentum, self.bn_eps, res,
+                             self._bn_pack(res_bn) if res_bn is not None else None, out, True, mask)
+            return
+        w = self._bn_fwd(bn, count, training)
+        if res_bn is not None:
+            wd = self._bn_fwd(res_bn, count, training)
+            e.bn_apply(y, w["scale"], w["shift"], res, wd["scale"], wd["shift"], out, True, mask)
+        else:
+            e.bn_apply(y, w["scale"], w["shift"], res, None, None, out, True, mask)
+
     def forward(self, training: bool = True) -> None:
         """x_u8 / labels (static inputs) -> logits, loss stats.  All launches go to the current stream."""
         e, N, A = self._e, self.batch, self.act
         w0 = self.bnw["bn1"]
+        if training and self.fuse_bn_coeffs:
+            self._bn_fwd_sums.zero_()  # nobody zeroes them after use on the fused path
         if self.native_stem:
             # 7x7/2 stem on the tensor cores straight from the uint8 batch (normalisation + BN statistics fused)
             self._stem_fwd.run()
@@ -401,21 +442,17 @@ class ResNet50Engine:
             cnt_in = N * b.h_in * b.h_in
             cnt_out = N * b.h_out * b.h_out
             self._fwd[n + ".conv1"].run()
-            w1 = self._bn_fwd(n + ".bn1", cnt_in, training)
-            e.bn_apply(A[n + ".y1"], w1["scale"], w1["shift"], None, None, None, A[n + ".a1"], True)
+            self._bn_apply(n + ".bn1", cnt_in, training, A[n + ".y1"], A[n + ".a1"])
             self._fwd[n + ".conv2"].run()
-            w2 = self._bn_fwd(n + ".bn2", cnt_out, training)
-            e.bn_apply(A[n + ".y2"], w2["scale"], w2["shift"], None, None, None, A[n + ".a2"], True)
+            self._bn_apply(n + ".bn2", cnt_out, training, A[n + ".y2"], A[n + ".a2"])
             self._fwd[n + ".conv3"].run()
-            w3 = self._bn_fwd(n + ".bn3", cnt_out, training)
+            mask = A.get(n + ".mask") if training else None
             if b.downsample:
                 self._fwd[n + ".downsample.0"].run()
-                wd = self._bn_fwd(n + ".downsample.1", cnt_out, training)
-                e.bn_apply(A[n + ".y3"], w3["scale"], w3["shift"], A[n + ".yd"], wd["scale"], wd["shift"],
-                           A[n + ".out"], True, A.get(n + ".mask") if training else None)
+                self._bn_apply(n + ".bn3", cnt_out, training, A[n + ".y3"], A[n + ".out"], A[n + ".yd"],
+                               n + ".downsample.1", mask)
             else:
-                e.bn_apply(A[n + ".y3"], w3["scale"], w3["shift"], x_in, None, None, A[n + ".out"], True,
-                           A.get(n + ".mask") if training else None)
+                self._bn_apply(n + ".bn3", cnt_out, training, A[n + ".y3"], A[n + ".out"], x_in, None, mask)
             x_in = A[n + ".out"]
         drop = self.dropout if training else 0.0
         self._drop_seed = self.seed * 1000003 + self._step_count
@@ -449,14 +486,16 @@ class ResNet50Engine:
                 e.bn_bwd_reduce(2, g1, None, None, y, w["scale"], w["shift"], None, w["sum_dz"], w["sum_dzy"])
         else:
             e.bn_bwd_reduce(3, g1, None, None, y, None, None, None, w["sum_dz"], w["sum_dzy"])
-        e.bn_bwd_coeffs(w["sum_dz"], w["sum_dzy"], self.p(bn + ".weight"), w["mean"], w["invstd"], float(count),
-                        self.g(bn + ".weight"), self.g(bn + ".bias"), w["cA"], w["cB"], w["cC"])
-        if mode == 1:
-            e.bn_bwd_apply(dz, y, None, None, w["cA"], w["cB"], w["cC"], dy)
-        elif mode == 2:
-            e.bn_bwd_apply(g1, y, w["scale"], w["shift"], w["cA"], w["cB"], w["cC"], dy)
+        src = dz if mode == 1 else g1
+        sc, sh = (w["scale"], w["shift"]) if mode == 2 else (None, None)
+        if self.fuse_bn_coeffs:
+            # A, B, C computed in the apply kernel's prologue; its first row-block writes dgamma / dbeta
+            e.bn_bwd_apply_fused(src, y, sc, sh, w["sum_dz"], w["sum_dzy"], self.p(bn + ".weight"), w["mean"],
+                                 w["invstd"], float(count), self.g(bn + ".weight"), self.g(bn + ".bias"), dy)
         else:
-            e.bn_bwd_apply(g1, y, None, None, w["cA"], w["cB"], w["cC"], dy)
+            e.bn_bwd_coeffs(w["sum_dz"], w["sum_dzy"], self.p(bn + ".weight"), w["mean"], w["invstd"], float(count),
+                            self.g(bn + ".weight"), self.g(bn + ".bias"), w["cA"], w["cB"], w["cC"])
+            e.bn_bwd_apply(src, y, sc, sh, w["cA"], w["cB"], w["cC"], dy)
         self._ready(bn + ".weight", bn + ".bias")
 
     def _dy_buf(self, cname: str, shape) -> torch.Tensor:
@@ -488,6 +527,8 @@ class ResNet50Engine:
         """dlogits -> every parameter gradient (fp32, written into the flat gradient buffer)."""
         e, N, A = self._e, self.batch, self.act
         self.grads.zero_()  # wgrad accumulates with atomics
+        if self.fuse_bn_coeffs:
+            self._bn_bwd_sums.zero_()  # sum(dz), sum(dz*y) of every layer; nobody zeroes them after use on the fused path
         # classifier head
         dl16 = self.dlogits.to(torch.bfloat16)
         torch.matmul(self.dlogits.t(), self.pooled.float(), out=self.g("fc.weight"))

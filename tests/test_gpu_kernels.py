@@ -52,6 +52,11 @@ def test_resnet50_engine_matches_torchvision(checks):
     assert checks.case_engine()
 
 
+def test_resnet50_engine_fused_bn_coefficients_matches_torchvision(checks):
+    """Opt-in path: BatchNorm coefficients computed inside the apply kernels (same gradient criteria)."""
+    assert checks.case_engine(quick=True, fuse_bn_coeffs=True)
+
+
 def test_resnet50_engine_inline_wgrad_matches_torchvision(checks):
     """Same gradient criteria with the weight-gradient GEMMs issued in line instead of on the side stream."""
     assert checks.case_engine(overlap_wgrad=False, quick=True)
