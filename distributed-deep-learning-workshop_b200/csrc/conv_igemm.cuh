@@ -4,18 +4,23 @@
 //
 // * A is an NHWC bf16 activation.  An M-tile is either 128 consecutive pixels of the flattened
 //   [N*H*W, C] view ("flat", 1x1 stride-1 convs) or a TMA box (bw x bh x bn pixels, <=128) of the 4-D tensor
-//   ("box", 3x3 / strided convs).  A filter tap is just a coordinate offset of the box; zero padding is the
-//   TMA out-of-bounds fill, so there is no im2col buffer and no halo handling in the kernel.
-//   Strided convs pass up to 4 "parity" views of the input (each a strided NHWC view) and a tap table that
-//   says which view + offset each tap reads.
+//   ("box", 3x3 / strided convs).  A filter tap is a coordinate offset of the box; zero padding is the TMA
+//   out-of-bounds fill, so there is no im2col buffer.  Strided convs pass up to 4 "parity" views of the input (each a
+//   strided NHWC view) and a tap table that says which view + offset each tap reads.
 // * B is the filter as a [taps*Cout, Cin] K-major matrix.
-// * Warp-specialised, persistent: warp0 = TMA producer, warp1 = tcgen05.mma issuer, warp2 = TMEM allocator,
-//   warps4-7 = epilogue (tcgen05.ld -> bf16 -> swizzled smem -> TMA store), double-buffered TMEM accumulator
-//   so the epilogue of tile i overlaps the main loop of tile i+1.
-// * Optional fused BatchNorm statistics: per-output-channel sum and sum-of-squares of the bf16 output tile
-//   are reduced in the epilogue (staged smem tile -> per-CTA smem accumulators -> one global atomic per channel per
-//   CTA), which removes
-//   the separate statistics pass over the conv output.
+// * Warp-specialised, persistent: warp0 = TMA producer, warp1 = tcgen05.mma issuer (both ONE thread chosen with
+//   elect.sync on a shuffle-broadcast warp index, integer smem addresses, descriptors built once), warp2 = TMEM allocator,
+//   warps4-7 = epilogue (tcgen05.ld -> bf16 -> swizzled smem -> TMA store), double-buffered TMEM accumulator so the
+//   epilogue of tile i overlaps the main loop of tile i+1.
+// * kStats = 1: warps 8-11 reduce per-channel sum / sum-of-squares of the staged bf16 output tile (register accumulators
+//   across tiles, one global atomic per channel per CTA) - no separate BatchNorm statistics pass.
+//   kStats = 2: the same warps do the BatchNorm-BACKWARD reduction inside a dgrad GEMM (sum dz, sum dz*y with
+//   dz = g * [y*scale + shift > 0]; the pre-BN tile y arrives by an extra TMA load).
+// * kResB: the CTA's whole filter slice (<= 9 tiles of 8 KB, single N-block of 64 channels) stays resident in shared
+//   memory.  kHalo (on top of kResB; 3x3 stride 1, full-width single-image boxes): one [bw x (bh+2)] box per
+//   horizontal tap offset; its three vertical taps read the same stage 0 / bw / 2*bw rows in (row-shifted SWIZZLE_128B
+//   descriptors, exact with base_offset 0 - umma_probe.cu).  Why: the stage ring is latency-bound per slot
+//   (tma_probe.cu), so fewer and larger loads win; see profiles/README.md 2.1b.
 #pragma once
 #include "conv_params.h"
 #include "ptx.cuh"
@@ -33,7 +38,7 @@ struct TmapArray4 {
 // kResB: the whole filter slice this CTA needs (taps * kblocks tiles of [BLOCK_N x 64]) stays resident in shared memory
 // (loaded once per CTA) and the pipeline stages carry only the A tile.  The 3x3 64->64 @56^2 layer moves ~90 % of the
 // measured L2 -> SM cap (~42.6 B/clk/SM) with a third of those bytes being the same 72 KB of weights re-read per tile.
-constexpr int kResBBytes = 9 * 64 * kBlockK * 2;  // 72 KB: 9 taps of a 64 x 64 filter (or 4 k-blocks x 2 ... any <= 9 tiles)
+constexpr int kResBBytes = 9 * 64 * kBlockK * 2;  // 72 KB = nine [64 x 64] bf16 filter tiles (taps * kblocks <= 9)
 
 constexpr int kHaloRows = 224;  // largest halo box: bw * (bh + 2) pixels (56 x 4); 28 KB per stage
 
