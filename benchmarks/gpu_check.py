@@ -640,6 +640,18 @@ def case_umma_probe():
         print(f"PROBE shift={shift:2d} err(base_offset=0)={res[0]:.3e} err(base_offset=(addr>>7)&7)={res[1]:.3e}", flush=True)
         if shift == 0:
             ok0 &= res[0] < 1e-2
+    # second question: 8-row groups at a stride other than 1024 bytes (2-D halo tiles need 1280 = a 10-pixel-wide row)
+    T2 = torch.randn(256, 64, device=DEV, generator=g).to(torch.bfloat16)
+    for sbo in (1024, 1152, 1280, 1536, 2048):
+        step = sbo // 128
+        for shift in (0, 1, 11, 22):
+            if shift + 15 * step + 8 > 256:
+                continue
+            rows = torch.cat([torch.arange(shift + gi * step, shift + gi * step + 8, device=DEV) for gi in range(16)])
+            ref = T2[rows].float() @ B.float().t()
+            out = ext.umma_probe(T2, B, shift, False, sbo)
+            torch.cuda.synchronize()
+            print(f"PROBE group_stride={sbo:5d} B ({step:2d} rows) shift={shift:2d} err={rel_err(out, ref):.3e}", flush=True)
     return ok0
 
 
