@@ -34,7 +34,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   uint64_t* tempty_bar = bars + 2 * kWgMaxStages + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxStages + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // provably warp-uniform (see conv_igemm.cuh): keeps the single-thread MMA loop free of per-instruction ELECT loops
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -128,44 +129,51 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = umma_idesc_bf16(128, acc_cols, 1, 1);  // both operands MN-major
-    const uint32_t a_lbo = (p.a_chunks == 2) ? slot_bytes : 0;    // Cout == 64: rows 64..127 mirror rows 0..63
-    // descriptors differ only in the 14-bit start-address field: build one per stage up front, then add offsets
-    const uint64_t da0 = umma_desc_sw128(smem_u32(smem), a_lbo, 1024);
-    const uint64_t db0 = umma_desc_sw128(smem_u32(smem) + p.a_chunks * slot_bytes, slot_bytes, 1024);
-    const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
-    const uint32_t acc_step = static_cast<uint32_t>(p.acc_chunks * slot_bytes) >> 4;
-    const int ksteps = p.P / 16;
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t uphase = 0;
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-      const int pxc = unit / combos;
-      const int it0 = pxc * p.iters_per_chunk;
-      const int it1 = min(it0 + p.iters_per_chunk, p.iters_total);
-      mbar_wait(tempty_bar, uphase ^ 1);
-      tc_fence_after();
-      for (int it = it0; it < it1; ++it) {
-        mbar_wait(&full_bar[stage], phase);
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ---------------------------------------------------------------- MMA issuer (one elected thread)
+      // elect.sync + integer barrier addresses: with `lane == 0` every tcgen05.mma / commit below was wrapped in an
+      // ELECT / PLOP3 / BRA.U.ANY serialisation loop (~10 extra instructions per MMA, 8-24 MMAs per stage).
+      const uint32_t idesc = umma_idesc_bf16(128, acc_cols, 1, 1);  // both operands MN-major
+      const uint32_t a_lbo = (p.a_chunks == 2) ? slot_bytes : 0;    // Cout == 64: rows 64..127 mirror rows 0..63
+      // descriptors differ only in the 14-bit start-address field: build one per stage up front, then add offsets
+      const uint64_t da0 = umma_desc_sw128(smem_u32(smem), a_lbo, 1024);
+      const uint64_t db0 = umma_desc_sw128(smem_u32(smem) + p.a_chunks * slot_bytes, slot_bytes, 1024);
+      const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
+      const uint32_t acc_step = static_cast<uint32_t>(p.acc_chunks * slot_bytes) >> 4;
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      const uint32_t tfull_a = smem_u32(tfull_bar), tempty_a = smem_u32(tempty_bar);
+      const int ksteps = p.P / 16;
+      const int num_units = p.num_units, iters_per_chunk = p.iters_per_chunk, iters_total = p.iters_total, stages = p.stages;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t uphase = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int pxc = unit / combos;
+        const int it0 = pxc * iters_per_chunk;
+        const int it1 = min(it0 + iters_per_chunk, iters_total);
+        mbar_wait_u32(tempty_a, uphase ^ 1);
         tc_fence_after();
-        const uint64_t da_s = da0 + stage * stage_step;
-        const uint64_t db_s = db0 + stage * stage_step;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          // 16 pixels = two 8-row swizzle atoms = 2048 B along the (slow) K dimension -> +128 in the address field
-          const uint32_t acc_flag = (it != it0 || ks != 0) ? 1u : 0u;
-          for (int a = 0; a < n_acc; ++a)
-            umma_bf16(tmem_base + a * acc_cols, da_s + ks * 128, db_s + a * acc_step + ks * 128, idesc, acc_flag);
+        for (int it = it0; it < it1; ++it) {
+          mbar_wait_u32(full0 + stage * 8, phase);
+          tc_fence_after();
+          const uint64_t da_s = da0 + stage * stage_step;
+          const uint64_t db_s = db0 + stage * stage_step;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            // 16 pixels = two 8-row swizzle atoms = 2048 B along the (slow) K dimension -> +128 in the address field
+            const uint32_t acc_flag = (it != it0 || ks != 0) ? 1u : 0u;
+            for (int a = 0; a < n_acc; ++a)
+              umma_bf16(tmem_base + a * acc_cols, da_s + ks * 128, db_s + a * acc_step + ks * 128, idesc, acc_flag);
+          }
+          umma_commit_u32(empty0 + stage * 8);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
-        }
+        umma_commit_u32(tfull_a);
+        uphase ^= 1;
       }
-      umma_commit(tfull_bar);
-      uphase ^= 1;
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: TMEM -> vector atomics
