@@ -89,3 +89,46 @@ def test_distributed_optimizer_averages_gradients_and_keeps_replicas_identical()
     assert out["same"], "replicas diverged"
     assert out["buckets"] >= 2 and out["launches"] >= 40 * out["buckets"] - 1
     assert out["loss"][-1] < out["loss"][0]
+
+
+def test_learning_rate_warmup_ramps_from_lr_over_size_on_two_ranks():
+    """`LearningRateWarmupCallback` (reference P1/03:315-318): with N ranks the LR starts at initial_lr / N, grows every
+    batch, and is exactly initial_lr once the warm-up epochs are over - identically on every rank."""
+    def fn():
+        import torch
+        import b200ddl.parallel as hvd
+        from b200ddl import optim
+        from b200ddl.train import LambdaCallback, Trainer
+
+        hvd.init()
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 4))
+        base_lr = 0.01 * hvd.size()
+        opt = hvd.DistributedOptimizer(optim.SGD(base_lr))
+        tr = Trainer(model, device="cpu").compile(optimizer=opt)
+        seen = []
+        rec = LambdaCallback(on_train_batch_end=lambda b, logs: seen.append(tr.optimizer.learning_rate))
+
+        def ds():
+            g = torch.Generator().manual_seed(hvd.rank())
+            while True:
+                y = torch.randint(0, 4, (8,), generator=g)
+                yield torch.randint(0, 255, (8, 8, 8, 3), generator=g).to(torch.uint8), y
+
+        tr.fit(ds(), steps_per_epoch=5, epochs=4, verbose=0,
+               callbacks=[hvd.callbacks.BroadcastGlobalVariablesCallback(0),
+                          hvd.callbacks.LearningRateWarmupCallback(initial_lr=base_lr, warmup_epochs=2), rec])
+        lrs = torch.tensor(seen, dtype=torch.float64)
+        gathered = [torch.zeros_like(lrs) for _ in range(hvd.size())]
+        import torch.distributed as dist
+        dist.all_gather(gathered, lrs)
+        return {"lrs": seen, "base": base_lr, "size": hvd.size(), "same": all(torch.equal(gathered[0], t) for t in gathered)}
+
+    out = Runner(np=2, driver_log_verbosity="none", force_cpu=True).run(fn)
+    lrs, base = out["lrs"], out["base"]
+    assert out["size"] == 2 and out["same"] and len(lrs) == 20
+    assert abs(lrs[0] - base / 2) < 1e-12                       # first batch: initial_lr / size
+    warm = lrs[:10]
+    assert all(b > a for a, b in zip(warm, warm[1:]))           # strictly increasing during the 2 warm-up epochs
+    assert warm[-1] < base
+    assert all(abs(v - base) < 1e-12 for v in lrs[10:])         # exactly initial_lr afterwards
