@@ -125,8 +125,11 @@ struct ConvPlan {
     raw.halo = 0;
     {
       const char* off = std::getenv("B200DDL_NO_HALO");
-      bool ok = raw.res_b && p.mode == 1 && taps == 9 && views.size() == 1 && bn == 1 && bw == views[0].size(2) &&
-                bw == Wo && bw * (bh + 2) <= 224 && !(off && off[0] == '1');
+      // two-dimensional variant: 8-pixel-wide boxes, ONE [(bw+2) x (bh+2)] load per tile (B200DDL_HALO2D=1 opts in)
+      const char* h2 = std::getenv("B200DDL_HALO2D");
+      const bool two_d = (h2 && h2[0] == '1') && bw == 8 && bh <= 16 && (bw + 2) * (bh + 2) <= 224 && Wo % 8 == 0;
+      bool ok = raw.res_b && p.mode == 1 && taps == 9 && views.size() == 1 && bn == 1 && !(off && off[0] == '1') &&
+                (two_d || (bw == views[0].size(2) && bw == Wo && bw * (bh + 2) <= 224));
       int8_t table[9];
       for (int i = 0; i < 9; ++i) table[i] = -1;
       for (int t = 0; ok && t < 9; ++t) {
@@ -134,7 +137,12 @@ struct ConvPlan {
         if (p.tap_map[t] != 0 || dwv < -1 || dwv > 1 || dhv < -1 || dhv > 1 || table[(dwv + 1) * 3 + (dhv + 1)] != -1) ok = false;
         else table[(dwv + 1) * 3 + (dhv + 1)] = (int8_t)t;
       }
-      if (ok) {
+      if (ok && two_d) {
+        raw.halo = 2;
+        p.halo = 2;
+        p.halo_bytes = (int)((bw + 2) * (bh + 2) * 128);
+        raw.tmA[1] = map_nhwc(views[0], 64, (int)bw + 2, (int)bh + 2, 1);
+      } else if (ok) {
         raw.halo = 1;
         p.halo = 1;
         p.halo_bytes = (int)(bw * (bh + 2) * 128);

@@ -165,6 +165,20 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
           h0 = th * bh;
           n0 = (rest / tiles_h) * bn;
         }
+        if (kHalo && p.halo == 2) {
+          // 2-D halo: ONE [(bw+2) x (bh+2)] box per tile (and k-block) serves all nine taps
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+            const uint32_t fb = full0 + stage * 8;
+            mbar_arrive_expect_tx_u32(fb, stage_tx);
+            tma_load_4d_u32(sA0 + stage * L::kASlot, &tmA.m[1], fb, kb * kBlockK, w0 - 1, h0 - 1, n0);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          continue;
+        }
         if (kHalo) {
           // one [bw x (bh+2)] box per horizontal tap offset; rows above / below / beside the image are zero-filled
           for (int hs = 0; hs < 3; ++hs) {
@@ -226,7 +240,34 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
         mbar_wait_u32(tempty0 + acc * 8, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        if (kHalo) {
+        if (kHalo && p.halo == 2) {
+          // 2-D halo (bw == 8): the stage holds a [(bh+2) x (bw+2)] pixel tile, row-major.  Output pixel (g, r) of the
+          // 8-wide box is accumulator row 8g + r, so the M = 128 operand is 16 groups of 8 consecutive tile rows at a
+          // stride of (bw+2) rows = 1280 B (the descriptor's stride-byte-offset) and tap (dw, dh) starts
+          // (dh+1)*(bw+2) + (dw+1) rows in.  Any 128-byte-multiple group stride and row shift is exact (umma_probe.cu);
+          // groups past bh read rows whose accumulator lanes are discarded.
+          const int kblocks = p.kblocks, taps = p.taps;
+          const uint32_t hw = static_cast<uint32_t>(p.bw) + 2;
+          const uint64_t da2 = umma_desc_sw128(smem_u32(sA), 16, hw * 128);
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait_u32(full0 + stage * 8, phase);
+            tc_fence_after();
+            const uint64_t da_s = da2 + static_cast<uint32_t>(stage * (L::kASlot >> 4));
+            for (int t = 0; t < taps; ++t) {
+              const uint32_t shift16 = ((p.tap_dh[t] + 1) * hw + (p.tap_dw[t] + 1)) * 8;  // rows of 128 B in the (addr >> 4) field
+              const uint64_t da = da_s + shift16;
+              const uint64_t db = db0 + static_cast<uint32_t>((t * kblocks + kb) * (L::kBBytes >> 4));
+              umma_bf16(d_tmem, da, db, idesc, (kb | t) != 0 ? 1u : 0u);
+#pragma unroll
+              for (int k = 1; k < kBlockK / 16; ++k) umma_bf16_acc(d_tmem, da + 2 * k, db + 2 * k, idesc);
+            }
+            umma_commit_u32(empty0 + stage * 8);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        } else if (kHalo) {
           const int kblocks = p.kblocks;
           const uint32_t shift16 = static_cast<uint32_t>(p.bw) * 8;  // bw rows of 128 B, in the (addr >> 4) field
           for (int hs = 0; hs < 3; ++hs) {

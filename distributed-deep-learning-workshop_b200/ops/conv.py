@@ -68,6 +68,11 @@ def halo_box(h: int, w: int, cin: int, cout: int, R: int, S: int, stride: int, p
         return None
     if not (R == 3 and S == 3 and stride == 1 and pad == 1 and cin == 64 and cout == 64):
         return None
+    if os.environ.get("B200DDL_HALO2D") == "1" and w % 8 == 0:
+        # two-dimensional halo (opt-in): 8-pixel-wide boxes, one [(8+2) x (bh+2)] load per tile serves all nine taps
+        cand = [bh for bh in _divisors(h) if bh <= 16 and 10 * (bh + 2) <= 224]
+        if cand:
+            return (8, max(cand), 1)
     best = None
     for bh in _divisors(h):
         if w * bh <= 128 and w * (bh + 2) <= 224:

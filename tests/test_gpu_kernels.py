@@ -40,6 +40,14 @@ def test_conv_dgrad_tcgen05(checks):
     assert checks.case_conv_dgrad()
 
 
+def test_conv_2d_halo_opt_in(checks, monkeypatch):
+    """Opt-in path (B200DDL_HALO2D=1): (8, bh, 1) boxes, one [10 x (bh+2)] halo load per tile, strided row-shifted UMMA
+    descriptors - forward, statistics, dgrad and the fused dgrad reduction against the fp32 references."""
+    monkeypatch.setenv("B200DDL_HALO2D", "1")
+    assert checks.case_conv_fwd()
+    assert checks.case_conv_dgrad()
+
+
 def test_conv_wgrad_tcgen05(checks):
     assert checks.case_conv_wgrad()
 
