@@ -343,6 +343,24 @@ class Trainer:
         torch.save({"weights": self.backend.state_dict(), "optimizer": opt.state_dict() if opt is not None else None,
                     "arch": getattr(self.model, "arch", type(self.model).__name__)}, path)
 
+    def load(self, path: str, load_optimizer: bool = True) -> "Trainer":
+        """Restore what `save()` (or `save_weights()` / `ModelCheckpoint`) wrote: weights and, when present and wanted,
+        the optimizer state and step counter.  Resume recipe (the reference only alludes to it at
+        P1/03:305-307): `compile(...)`, `load(path)` on every rank or on rank 0 followed by
+        `BroadcastGlobalVariablesCallback(0)` / `broadcast_state(0)`, then `fit(..., initial_epoch=k)`."""
+        if self.backend is None:
+            raise RuntimeError("call compile() before load()")
+        ck = torch.load(path, map_location="cpu")
+        weights = ck["weights"] if isinstance(ck, dict) and "weights" in ck else ck
+        self.backend.load_state_dict(weights)
+        if load_optimizer and isinstance(ck, dict) and ck.get("optimizer") is not None and self.optimizer is not None:
+            opt = self.optimizer.opt if hasattr(self.optimizer, "opt") else self.optimizer
+            if ck["optimizer"].get("name") != getattr(opt, "name", None):
+                raise ValueError(f"checkpoint holds {ck['optimizer'].get('name')} state, the trainer was compiled with "
+                                 f"{getattr(opt, 'name', type(opt).__name__)}")
+            opt.load_state_dict(ck["optimizer"])
+        return self
+
     def summary(self) -> str:
         if _is_engine(self.model):
             n = self.model.num_parameters()

@@ -87,3 +87,41 @@ def test_optimizer_lookup_by_name():
     assert optim.get("Adam") is optim.Adam and optim.get("Adadelta") is optim.Adadelta   # reference P2/01:154
     with pytest.raises(ValueError):
         optim.get("Nope")
+
+
+def test_save_load_resume_continues_training(tmp_path):
+    """Checkpoint / resume: `save()` after two epochs, a NEW trainer `load()`s it and continues with
+    `initial_epoch=2`; weights, optimizer moments and the step counter carry over, so the resumed run is the same run."""
+    def make(lr=3e-3):
+        torch.manual_seed(1)
+        model = build_model(32, 32, 3, 5, dropout=0.0, arch="mobilenetv2", freeze_base=False)
+        return Trainer(model, device="cpu").compile(optimizer=optim.Adam(lr), loss="sparse_categorical_crossentropy",
+                                                    metrics=["accuracy"])
+
+    # uninterrupted reference: 4 epochs over a deterministic stream
+    ref = make()
+    h_ref = ref.fit(make_ds(seed=4), steps_per_epoch=6, epochs=4, verbose=0)
+    # interrupted: 2 epochs, save, new process-equivalent trainer, load, 2 more epochs over the rest of the stream
+    a = make()
+    stream = make_ds(seed=4)
+    h_a = a.fit(stream, steps_per_epoch=6, epochs=2, verbose=0)
+    path = str(tmp_path / "resume.pt")
+    a.save(path)
+    b = make(lr=1.0)                      # wrong LR on purpose: load() must restore the saved one
+    b.load(path)
+    opt_b = b.optimizer
+    assert opt_b.t == 12 and abs(opt_b.learning_rate - 3e-3) < 1e-12
+    h_b = b.fit(stream, steps_per_epoch=6, epochs=4, initial_epoch=2, verbose=0)
+    assert len(h_b.history["loss"]) == 2                               # epochs 3 and 4 only
+    assert np.allclose(h_a.history["loss"], h_ref.history["loss"][:2], rtol=1e-4)
+    assert np.allclose(h_b.history["loss"], h_ref.history["loss"][2:], rtol=2e-3), (h_b.history["loss"], h_ref.history["loss"])
+    # weights-only files (ModelCheckpoint / save_weights) load through the same entry point
+    a.save_weights(str(tmp_path / "w.pt"))
+    c = make()
+    c.load(str(tmp_path / "w.pt"))
+    x = np.zeros((2, 32, 32, 3), np.uint8)
+    assert np.allclose(a.predict(x), c.predict(x), atol=1e-5)
+    # optimizer mismatch is an error, not silent garbage
+    d = Trainer(build_model(32, 32, 3, 5, arch="mobilenetv2"), device="cpu").compile(optimizer=optim.SGD(0.1))
+    with pytest.raises(ValueError):
+        d.load(path)
