@@ -132,3 +132,44 @@ def test_learning_rate_warmup_ramps_from_lr_over_size_on_two_ranks():
     assert all(b > a for a, b in zip(warm, warm[1:]))           # strictly increasing during the 2 warm-up epochs
     assert warm[-1] < base
     assert all(abs(v - base) < 1e-12 for v in lrs[10:])         # exactly initial_lr afterwards
+
+
+def test_hung_rank_hits_the_timeout_and_no_worker_survives(tmp_path):
+    """Failure detection: a rank that hangs (not crashes) is caught by `timeout_s`; the error says so and
+    every worker process the Runner started is gone afterwards."""
+    import os
+    import time
+
+    piddir = str(tmp_path)
+
+    def fn():
+        import os
+        import time
+        import b200ddl.parallel as hvd
+
+        hvd.init()
+        with open(os.path.join(piddir, f"pid_{hvd.rank()}"), "w") as f:
+            f.write(str(os.getpid()))
+        if hvd.rank() == 1:
+            time.sleep(3600)          # the hang: rank 0 waits for it in the barrier below
+        hvd.barrier()
+        return "unreachable"
+
+    t0 = time.time()
+    with pytest.raises(RunnerError) as ei:
+        Runner(np=2, driver_log_verbosity="none", force_cpu=True, timeout_s=20).run(fn)
+    assert "timed out after 20" in str(ei.value)
+    assert time.time() - t0 < 90
+    pids = [int(open(os.path.join(piddir, f"pid_{r}")).read()) for r in (0, 1)]
+    deadline = time.time() + 10
+    alive = pids
+    while alive and time.time() < deadline:
+        alive = []
+        for pid in pids:
+            try:
+                os.kill(pid, 0)       # signal 0: existence check only
+                alive.append(pid)
+            except ProcessLookupError:
+                pass
+        time.sleep(0.2)
+    assert not alive, f"worker processes still alive after the timeout: {alive}"
