@@ -68,6 +68,10 @@ class Runner:
                 if self.force_cpu:
                     env["B200DDL_FORCE_CPU"] = "1"
                     env["CUDA_VISIBLE_DEVICES"] = ""
+                # N ranks with full-size OpenMP teams oversubscribe the host (measured: 50x slower CPU steps once the
+                # spinning teams exceed the cores); like torchrun, give each rank its share unless the user chose.
+                if not env.get("OMP_NUM_THREADS"):
+                    env["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // self.np))
                 p = subprocess.Popen([sys.executable, "-m", "b200ddl.parallel._worker", payload, result],
                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, text=True,
                                      cwd=os.getcwd(), start_new_session=True)

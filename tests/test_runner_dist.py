@@ -173,3 +173,24 @@ def test_hung_rank_hits_the_timeout_and_no_worker_survives(tmp_path):
                 pass
         time.sleep(0.2)
     assert not alive, f"worker processes still alive after the timeout: {alive}"
+
+
+def test_workers_get_their_share_of_the_cores(monkeypatch):
+    """Each rank's OpenMP team is sized cores // ranks unless OMP_NUM_THREADS was set by the user (torchrun does the same;
+    full-size teams in every rank oversubscribe the host)."""
+    import os
+
+    def fn():
+        import os
+        import torch
+        import b200ddl.parallel as hvd
+
+        hvd.init()
+        return os.environ.get("OMP_NUM_THREADS"), torch.get_num_threads()
+
+    monkeypatch.delenv("OMP_NUM_THREADS", raising=False)
+    share = max(1, (os.cpu_count() or 1) // 2)
+    env_val, torch_threads = Runner(np=2, driver_log_verbosity="none", force_cpu=True).run(fn)
+    assert env_val == str(share) and torch_threads == share
+    monkeypatch.setenv("OMP_NUM_THREADS", "3")           # an explicit user setting wins
+    assert Runner(np=2, driver_log_verbosity="none", force_cpu=True).run(fn)[0] == "3"
