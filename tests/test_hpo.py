@@ -96,3 +96,38 @@ def test_trials_become_nested_child_runs(tmp_path):
     df = tracking.search_runs(filter_string=f'tags.mlflow.parentRunId = "{pid}"', order_by=["metrics.loss ASC"])
     assert len(df) == 5 and df["metrics.loss"].is_monotonic_increasing
     assert tracking.active_run() is None
+
+
+def test_concurrent_trials_log_intact_child_runs(tmp_path):
+    """SparkTrials(parallelism=4)-style use (reference P2/01:226): many trials logging at once must not interleave or lose
+    records - every child run keeps its own parameters, its full metric history and its artifact, under the right parent."""
+    import json
+    import os
+
+    tracking.set_tracking_uri(str(tmp_path / "mlruns"))
+    tracking.set_experiment("hpo_stress")
+
+    def obj(p):
+        tag = f"{p['x']:.6f}"
+        tracking.log_params({"x": tag, "twice": f"{2 * p['x']:.6f}"})
+        for s in range(40):
+            tracking.log_metric("curve", p["x"] + s, step=s)
+        tracking.log_dict({"x": tag}, "who.json")
+        time.sleep(0.01)
+        return {"loss": p["x"] ** 2, "status": STATUS_OK}
+
+    with tracking.start_run(run_name="parent") as parent:
+        t = ParallelTrials(parallelism=8)
+        fmin(obj, {"x": hp.uniform("x", -1, 1)}, algo=rand.suggest, max_evals=24, trials=t, rstate=3)
+        pid = parent.info.run_id
+    df = tracking.search_runs(filter_string=f'tags.mlflow.parentRunId = "{pid}"')
+    assert len(df) == 24 and df["run_id"].is_unique
+    for rid in df["run_id"]:
+        r = tracking.get_run(rid)
+        x = float(r.data.params["x"])
+        assert abs(float(r.data.params["twice"]) - 2 * x) < 1e-5             # params of ONE trial, not a mixture
+        hist = tracking.metric_history(rid, "curve")
+        assert len(hist) == 40 and all(abs(v - (x + s)) < 1e-5 for s, v in enumerate(hist))   # history of ONE trial, in order
+        assert abs(r.data.metrics["loss"] - x * x) < 1e-5
+        with open(os.path.join(r.info.artifact_uri, "who.json")) as f:
+            assert json.load(f)["x"] == r.data.params["x"]
