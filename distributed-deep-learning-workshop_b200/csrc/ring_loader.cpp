@@ -111,9 +111,13 @@ class RingLoader {
       pybind11::gil_scoped_release nogil;
       std::unique_lock<std::mutex> lk(mu_);
       auto t0 = std::chrono::steady_clock::now();
-      cv_ready_.wait(lk, [&] { return !ready_.empty() || closed_; });
+      cv_ready_.wait(lk, [&] { return !ready_.empty() || closed_ || finished_; });
       wait_ns_ += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
-      if (ready_.empty()) throw std::runtime_error("RingLoader closed");
+      if (ready_.empty()) {
+        // finite producers called finish(): everything committed has been handed out -> end of iteration
+        if (finished_ && !closed_) throw pybind11::stop_iteration();
+        throw std::runtime_error("RingLoader closed");
+      }
       slot = ready_.front();
       ready_.pop_front();
       slots_[slot].state = IN_FLIGHT;
@@ -189,6 +193,15 @@ class RingLoader {
     }
   }
 
+  // Producers are done (finite number of epochs): next() drains the committed batches, then raises StopIteration.
+  void finish() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      finished_ = true;
+    }
+    cv_ready_.notify_all();
+  }
+
   void close() {
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -258,6 +271,7 @@ class RingLoader {
   std::mutex mu_;
   std::condition_variable cv_free_, cv_ready_;
   bool closed_ = false;
+  bool finished_ = false;
   cudaStream_t copy_stream_ = nullptr;
   std::vector<at::Tensor> dev_img_, dev_lab_;
   std::vector<cudaEvent_t> consumed_;
@@ -285,6 +299,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("next", &RingLoader::next)
       .def("start_synthetic", &RingLoader::start_synthetic, py::arg("threads"), py::arg("pool_images"),
            py::arg("num_classes"), py::arg("seed") = 0, py::arg("shard") = 0, py::arg("num_shards") = 1)
+      .def("finish", &RingLoader::finish)
       .def("close", &RingLoader::close)
       .def_property_readonly("batches", &RingLoader::batches)
       .def_property_readonly("h2d_bytes", &RingLoader::h2d_bytes)

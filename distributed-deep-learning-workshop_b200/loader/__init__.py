@@ -94,6 +94,7 @@ class _TableDataset(RingDataset):
         self._stop = threading.Event()
         self._lock = threading.Lock()
         self._row_iter = self._rows()
+        self._active_workers = max(1, workers_count)
         self._threads = [threading.Thread(target=self._worker, daemon=True) for _ in range(max(1, workers_count))]
         for t in self._threads:
             t.start()
@@ -123,6 +124,18 @@ class _TableDataset(RingDataset):
             epoch += 1
 
     def _worker(self):
+        try:
+            self._produce()
+        finally:
+            # the LAST worker to run out of rows ends the stream: the consumer drains what is committed and then gets
+            # StopIteration (without this a `for batch in ds:` over a finite dataset blocked forever)
+            with self._lock:
+                self._active_workers -= 1
+                last = self._active_workers == 0
+            if last and not self._stop.is_set():
+                self.ring.finish()
+
+    def _produce(self):
         while not self._stop.is_set():
             with self._lock:
                 batch = []

@@ -76,6 +76,48 @@ def test_converter_len_sharding_and_infinite_epochs(session):
     assert not os.path.exists(conv.cache_dir)                                      # reference P1/03:425-426
 
 
+def test_finite_epochs_end_the_iteration(session):
+    """`num_epochs=k` must END: the consumer gets every full batch the rows allow, then StopIteration (it used to block
+    forever once the decode workers had run out of rows) - also through `Trainer.evaluate(ds)` without a step count."""
+    import threading
+
+    t = _tables(session, 37).select(["content", "label_idx"])
+    conv = make_converter(t, session.cache_dir)
+    full = sorted(t.to_pandas()["label_idx"].tolist())
+    for epochs, workers, batches in ((1, 2, 4), (2, 3, 9), (1, 1, 4)):      # 37 rows, batch 8: 4 per epoch, 9 over two
+        got = []
+
+        def consume():
+            with conv.make_dataset(batch_size=8, num_epochs=epochs, workers_count=workers, image_size=(IMG, IMG),
+                                   device="cpu") as ds:
+                for x, y in ds:
+                    assert x.shape == (8, IMG, IMG, 3)
+                    got.append(y.tolist())
+
+        th = threading.Thread(target=consume, daemon=True)
+        th.start()
+        th.join(timeout=60)
+        assert not th.is_alive(), f"iteration over a finite dataset did not end (epochs={epochs}, workers={workers})"
+        assert len(got) == batches
+        if epochs == 1 and workers == 1:                                      # one worker: file order, tail of 5 rows dropped
+            assert [l for b in got for l in b] == t.to_pandas()["label_idx"].tolist()[:32]
+        from collections import Counter
+        assert not Counter(l for b in got for l in b) - Counter(full * epochs)   # only rows of the table, each at most `epochs` times
+    model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * IMG * IMG, len(CLASSES)))
+    tr = Trainer(model, device="cpu").compile(optimizer=optim.SGD(0.0))
+    done = []
+
+    def evaluate():
+        with conv.make_dataset(batch_size=8, num_epochs=1, workers_count=2, image_size=(IMG, IMG), device="cpu") as ds:
+            done.append(tr.evaluate(ds))
+
+    th = threading.Thread(target=evaluate, daemon=True)
+    th.start()
+    th.join(timeout=60)
+    assert done and np.isfinite(done[0][0])
+    conv.delete()
+
+
 def test_decoded_pixels_match_pil(session):
     t = _tables(session, 4).select(["content", "label_idx"])
     conv = make_converter(t, session.cache_dir)
