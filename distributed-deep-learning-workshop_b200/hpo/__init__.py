@@ -362,9 +362,33 @@ def _run_trial(fn: Callable, space, trial: dict, catch: bool) -> None:
 
 def fmin(fn: Callable[[Any], Any], space, algo=None, max_evals: int = 10, trials: Optional[Trials] = None,
          rstate=None, catch_eval_exceptions: bool = True, verbose: bool = False, show_progressbar: bool = False,
-         return_argmin: bool = True):
-    """Minimise `fn(params) -> loss | {'loss', 'status'}` over `space` (reference P2/01:229-238, P2/02:360-365)."""
+         return_argmin: bool = True, timeout: Optional[float] = None, loss_threshold: Optional[float] = None,
+         early_stop_fn: Optional[Callable] = None, **hyperopt_kwargs):
+    """Minimise `fn(params) -> loss | {'loss', 'status'}` over `space` (reference P2/01:229-238, P2/02:360-365).
+
+    Hyperopt's stopping arguments are honoured: `timeout` (seconds; no new trial starts after it), `loss_threshold` (stop
+    once the best loss is at or below it) and `early_stop_fn(trials, *state) -> (stop, state)`.  Other Hyperopt keyword
+    arguments (`max_queue_len`, `points_to_evaluate`, ...) are accepted and ignored with a warning."""
     from .. import tracking
+
+    if hyperopt_kwargs:
+        import warnings
+
+        warnings.warn(f"hpo.fmin ignores {sorted(hyperopt_kwargs)}", stacklevel=2)
+    t_start = time.time()
+    stop_state: list = []
+
+    def should_stop() -> bool:
+        nonlocal stop_state
+        if timeout is not None and time.time() - t_start >= timeout:
+            return True
+        done = trials.completed()
+        if loss_threshold is not None and done and min(t["result"]["loss"] for t in done) <= loss_threshold:
+            return True
+        if early_stop_fn is not None and len(trials):
+            stop, stop_state = early_stop_fn(trials, *stop_state)
+            return bool(stop)
+        return False
 
     algo = algo or tpe
     suggest = algo.suggest if hasattr(algo, "suggest") else algo
@@ -387,15 +411,19 @@ def fmin(fn: Callable[[Any], Any], space, algo=None, max_evals: int = 10, trials
             print(f"[hpo] trial {trial['tid']} {r.get('status')} loss={r.get('loss')} vals={trial['misc']['vals']}")
 
     if n_par <= 1:
-        while len(trials) < max_evals:
+        while len(trials) < max_evals and not should_stop():
             evaluate(trials.new_trial(suggest(nodes, trials, rng)))
     else:
         deadline = (time.time() + trials.timeout) if getattr(trials, "timeout", None) else None
         with cf.ThreadPoolExecutor(n_par) as ex:
             pending = set()
-            while len(trials) < max_evals or pending:
-                while len(trials) < max_evals and len(pending) < n_par:
+            stopping = False
+            while (len(trials) < max_evals and not stopping) or pending:
+                stopping = stopping or should_stop()      # running trials finish; no new ones start
+                while len(trials) < max_evals and len(pending) < n_par and not stopping:
                     pending.add(ex.submit(evaluate, trials.new_trial(suggest(nodes, trials, rng))))
+                if not pending:
+                    break
                 done, pending = cf.wait(pending, return_when=cf.FIRST_COMPLETED,
                                         timeout=None if deadline is None else max(0.0, deadline - time.time()))
                 for d in done:

@@ -131,3 +131,29 @@ def test_concurrent_trials_log_intact_child_runs(tmp_path):
         assert abs(r.data.metrics["loss"] - x * x) < 1e-5
         with open(os.path.join(r.info.artifact_uri, "who.json")) as f:
             assert json.load(f)["x"] == r.data.params["x"]
+
+
+def test_hyperopt_stopping_arguments():
+    """`timeout`, `loss_threshold`, `early_stop_fn` (Hyperopt's fmin signature) stop the search; unknown Hyperopt keyword
+    arguments are tolerated with a warning instead of a TypeError."""
+    space = {"x": hp.uniform("x", -1, 1)}
+    t = Trials()
+    fmin(lambda p: (time.sleep(0.05), p["x"] ** 2)[1], space, algo=rand.suggest, max_evals=1000, trials=t, rstate=0, timeout=0.5)
+    assert 2 <= len(t) < 60
+    t = Trials()
+    fmin(lambda p: p["x"] ** 2, space, algo=rand.suggest, max_evals=5000, trials=t, rstate=1, loss_threshold=1e-3)
+    assert len(t) < 5000 and min(l for l in t.losses() if l is not None) <= 1e-3
+
+    def no_progress(trials, best=None, stale=0):          # Hyperopt-style: stop after 5 trials without improvement
+        cur = min(l for l in trials.losses() if l is not None)
+        stale = 0 if best is None or cur < best else stale + 1
+        return stale >= 5, [cur if best is None else min(best, cur), stale]
+
+    t = Trials()
+    fmin(lambda p: 1.0, space, algo=rand.suggest, max_evals=200, trials=t, rstate=2, early_stop_fn=no_progress)
+    assert len(t) == 6                                      # first trial sets the best, five stale ones follow
+    t = ParallelTrials(parallelism=4)
+    fmin(lambda p: (time.sleep(0.05), p["x"] ** 2)[1], space, algo=rand.suggest, max_evals=1000, trials=t, rstate=3, timeout=0.5)
+    assert 4 <= len(t) < 120 and all(tr["result"].get("status") == STATUS_OK for tr in t.trials)
+    with pytest.warns(UserWarning):
+        fmin(lambda p: p["x"], space, algo=rand.suggest, max_evals=2, rstate=4, max_queue_len=4)
