@@ -221,6 +221,33 @@ def set_tag(key: str, value: Any) -> None:
         _write_json(p, d)
 
 
+def set_tags(tags: Dict[str, Any]) -> None:
+    for k, v in tags.items():
+        set_tag(k, v)
+
+
+def log_text(text: str, artifact_file: str) -> None:
+    """`mlflow.log_text('...', 'notes.txt')`."""
+    p = os.path.join(_active_dir(), "artifacts", artifact_file)
+    os.makedirs(os.path.dirname(p), exist_ok=True)
+    with open(p, "w") as f:
+        f.write(text)
+
+
+def log_artifacts(local_dir: str, artifact_path: Optional[str] = None) -> None:
+    """`mlflow.log_artifacts(dir)`: the CONTENTS of `local_dir` go under `artifact_path` (not the directory itself)."""
+    dst = os.path.join(_active_dir(), "artifacts", artifact_path or "")
+    os.makedirs(dst, exist_ok=True)
+    shutil.copytree(local_dir, dst, dirs_exist_ok=True)
+
+
+def get_experiment_by_name(name: str) -> Optional[SimpleNamespace]:
+    for eid, e in _experiments().items():
+        if e["name"] == name:
+            return SimpleNamespace(experiment_id=eid, name=name)
+    return None
+
+
 def log_dict(dictionary: dict, artifact_file: str) -> None:
     """`mlflow.log_dict({'img_height':..,'img_width':..}, 'img_params_dict.json')` (reference P2/03:284-285)."""
     p = os.path.join(_active_dir(), "artifacts", artifact_file)
@@ -405,6 +432,19 @@ class MlflowClient:
     def get_run(self, run_id: str) -> Run:
         return get_run(run_id)
 
+    def get_metric_history(self, run_id: str, key: str) -> List[SimpleNamespace]:
+        """MLflow's `client.get_metric_history`: Metric-like records (key, value, step, timestamp) in logging order."""
+        out = []
+        try:
+            with open(os.path.join(_find_run_dir(run_id), "metrics.jsonl")) as f:
+                for line in f:
+                    r = json.loads(line)
+                    if r["key"] == key:
+                        out.append(SimpleNamespace(key=key, value=r["value"], step=r.get("step"), timestamp=r.get("ts")))
+        except FileNotFoundError:
+            pass
+        return out
+
     def search_runs(self, experiment_ids, filter_string="", order_by=None):
         return search_runs(experiment_ids, filter_string, order_by)
 
@@ -428,6 +468,7 @@ tensorflow = SimpleNamespace(autolog=autolog)
 mlflow = SimpleNamespace(set_tracking_uri=set_tracking_uri)  # reference typo `mlflow.mlflow.set_tracking_uri` (Q9)
 
 __all__ = ["set_tracking_uri", "get_tracking_uri", "set_experiment", "start_run", "active_run", "end_run", "get_run",
-           "log_param", "log_params", "log_metric", "log_metrics", "log_dict", "log_artifact", "set_tag",
+           "log_param", "log_params", "log_metric", "log_metrics", "log_dict", "log_text", "log_artifact", "log_artifacts",
+           "set_tag", "set_tags", "get_experiment_by_name",
            "search_runs", "register_model", "MlflowClient", "autolog", "resolve_uri", "keras", "models",
            "metric_history", "get_artifact_uri"]

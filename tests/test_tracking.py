@@ -73,3 +73,32 @@ def test_registry_stage_transitions(tmp_path):
     assert tracking.resolve_uri("models:/me_flower_classifier/2") == p
     with pytest.raises(ValueError):
         client.transition_model_version_stage("me_flower_classifier", 1, stage="Bogus")
+
+
+def test_small_mlflow_conveniences(tmp_path):
+    """set_tags / log_text / log_artifacts / get_experiment_by_name / client.get_metric_history (MLflow spellings)."""
+    import os
+
+    tracking.set_tracking_uri(str(tmp_path / "mlruns"))
+    exp = tracking.set_experiment("conv")
+    assert tracking.get_experiment_by_name("conv").experiment_id == exp.experiment_id
+    assert tracking.get_experiment_by_name("nope") is None
+    d = tmp_path / "bundle"
+    (d / "sub").mkdir(parents=True)
+    (d / "a.txt").write_text("A")
+    (d / "sub" / "b.txt").write_text("B")
+    with tracking.start_run() as run:
+        tracking.set_tags({"team": "vision", "stage": 2})
+        tracking.log_text("hello", "notes/readme.txt")
+        tracking.log_artifacts(str(d), "bundle")
+        for s, v in enumerate((3.0, 2.0, 1.5)):
+            tracking.log_metric("loss", v, step=s)
+        rid = run.info.run_id
+    r = tracking.get_run(rid)
+    assert r.data.tags["team"] == "vision" and r.data.tags["stage"] == "2"
+    root = r.info.artifact_uri
+    assert open(os.path.join(root, "notes", "readme.txt")).read() == "hello"
+    assert open(os.path.join(root, "bundle", "a.txt")).read() == "A"            # contents, not the directory itself
+    assert open(os.path.join(root, "bundle", "sub", "b.txt")).read() == "B"
+    hist = tracking.MlflowClient().get_metric_history(rid, "loss")
+    assert [(h.step, h.value) for h in hist] == [(0, 3.0), (1, 2.0), (2, 1.5)] and all(h.key == "loss" for h in hist)
