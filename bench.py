@@ -90,6 +90,8 @@ class ClockSampler:
 def run_reference(args):
     # The reference tree holds Databricks notebooks only: no setup.py / pyproject, and its imports (tensorflow,
     # horovod, petastorm, pyspark, mlflow, hyperopt) are absent from the image and the offline wheelhouse.
+    if int(os.environ.get("RANK", "0")) != 0:   # launched under torchrun for N > 1 like our own arm: ONE line, from rank 0
+        return 0
     print(json.dumps({"impl": "reference", "unavailable": "reference is 11 Databricks notebooks with no installable "
                       "package (pip: neither setup.py nor pyproject.toml); TensorFlow/Horovod/Spark/Petastorm/MLflow "
                       "are not in the image or /opt/wheelhouse (see DESIGN.md)"}))
