@@ -158,3 +158,14 @@ def test_train_log_pyfunc_and_batch_inference(session):
     df = out.to_pandas()
     assert len(df) == 20 and list(df["prediction"][:10]) == list(pred)
     assert udf.stats["rows"] == 20
+    # the multi-process branch (one spawned scoring process per GPU on a GPU box): the workers must be able to load the
+    # user's PythonModel class, which lives in THIS module, and the shards must come back in row order
+    udf3 = pyfunc.spark_udf(None, f"runs:/{rid}/pyfunc_model", result_type="string")
+    udf3.num_workers = 3
+    df3 = data.limit(20).withColumn("prediction", udf3("content")).to_pandas()
+    assert udf3.stats["workers"] == 3 and list(df3["prediction"]) == list(df["prediction"])
+    # more workers than rows, and an empty table
+    udf9 = pyfunc.shard_udf(f"runs:/{rid}/pyfunc_model", num_workers=9)
+    assert list(data.limit(2).withColumn("prediction", udf9("content")).to_pandas()["prediction"]) == list(df["prediction"][:2])
+    assert udf9.stats["workers"] == 2
+    assert len(data.limit(0).withColumn("prediction", udf9("content")).to_pandas()) == 0
