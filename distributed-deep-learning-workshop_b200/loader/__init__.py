@@ -88,6 +88,7 @@ class _TableDataset(RingDataset):
                  workers_count, shuffle, seed):
         super().__init__(batch_size, image_size, device, num_slots=max(4, workers_count + 2))
         self.files = files
+        self.total_rows = int(total_rows)
         self.cur_shard, self.shard_count = cur_shard, shard_count
         self.num_epochs = num_epochs
         self.shuffle, self.seed = shuffle, seed
@@ -98,6 +99,12 @@ class _TableDataset(RingDataset):
         self._threads = [threading.Thread(target=self._worker, daemon=True) for _ in range(max(1, workers_count))]
         for t in self._threads:
             t.start()
+
+    def __len__(self) -> int:
+        """Full batches per epoch of THIS shard (global row i belongs to shard i % shard_count), so that
+        `fit(ds)` / `steps_per_epoch=len(ds)` work like they do for a Keras dataset."""
+        rows = (self.total_rows - self.cur_shard + self.shard_count - 1) // self.shard_count if self.total_rows > self.cur_shard else 0
+        return rows // self.batch_size
 
     def _rows(self):
         """Infinite (or `num_epochs`) stream of (content, label) of THIS shard: global row i belongs to shard

@@ -103,8 +103,19 @@ def test_finite_epochs_end_the_iteration(session):
             assert [l for b in got for l in b] == t.to_pandas()["label_idx"].tolist()[:32]
         from collections import Counter
         assert not Counter(l for b in got for l in b) - Counter(full * epochs)   # only rows of the table, each at most `epochs` times
+    # len(ds) = full batches per epoch of the shard: 37 rows -> shards of 19 and 18 rows -> 2 and 2 batches of 8
+    with conv.make_dataset(batch_size=8, cur_shard=0, shard_count=2, num_epochs=1, workers_count=1, image_size=(IMG, IMG),
+                           device="cpu") as d0, \
+         conv.make_dataset(batch_size=8, cur_shard=1, shard_count=2, num_epochs=1, workers_count=1, image_size=(IMG, IMG),
+                           device="cpu") as d1, \
+         conv.make_dataset(batch_size=8, num_epochs=None, workers_count=1, image_size=(IMG, IMG), device="cpu") as dall:
+        assert (len(d0), len(d1), len(dall)) == (2, 2, 4)
+        assert sum(1 for _ in d0) == 2 and sum(1 for _ in d1) == 2
     model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * IMG * IMG, len(CLASSES)))
     tr = Trainer(model, device="cpu").compile(optimizer=optim.SGD(0.0))
+    with conv.make_dataset(batch_size=8, num_epochs=None, workers_count=2, image_size=(IMG, IMG), device="cpu") as ds:
+        h = tr.fit(ds, epochs=2, verbose=0)                                   # steps_per_epoch defaults to len(ds)
+        assert len(h.history["loss"]) == 2 and tr.steps_per_epoch == 4
     done = []
 
     def evaluate():
