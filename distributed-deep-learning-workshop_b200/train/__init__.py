@@ -3,6 +3,8 @@ from .callbacks import (Callback, History, EarlyStopping, ReduceLROnPlateau, Mod
                         CallbackList)
 from .trainer import Trainer
 from .flat import FlatParams
+from . import callbacks, losses
+from .losses import SparseCategoricalCrossentropy
 
 __all__ = ["Trainer", "Callback", "History", "EarlyStopping", "ReduceLROnPlateau", "ModelCheckpoint",
-           "LambdaCallback", "CallbackList", "FlatParams"]
+           "LambdaCallback", "CallbackList", "FlatParams", "losses", "callbacks", "SparseCategoricalCrossentropy"]

@@ -125,3 +125,18 @@ def test_save_load_resume_continues_training(tmp_path):
     d = Trainer(build_model(32, 32, 3, 5, arch="mobilenetv2"), device="cpu").compile(optimizer=optim.SGD(0.1))
     with pytest.raises(ValueError):
         d.load(path)
+
+
+def test_compile_with_keras_style_loss_object():
+    """The reference's spelling: `loss=SparseCategoricalCrossentropy(from_logits=True)`, `metrics=['accuracy']`."""
+    from b200ddl.train import losses
+
+    model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 5))
+    tr = Trainer(model, device="cpu").compile(optimizer=optim.Adam(learning_rate=1e-2),
+                                              loss=losses.SparseCategoricalCrossentropy(from_logits=True), metrics=["accuracy"])
+    h = tr.fit(make_ds(size=8), steps_per_epoch=4, epochs=2, verbose=0)
+    assert set(h.history) >= {"loss", "accuracy"}
+    with pytest.raises(ValueError):
+        losses.SparseCategoricalCrossentropy()                 # probabilities are not what the models output
+    with pytest.raises(ValueError):
+        Trainer(model, device="cpu").compile(optimizer=optim.SGD(0.1), loss="mse")
