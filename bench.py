@@ -98,6 +98,69 @@ def run_reference(args):
     return 0
 
 
+def run_baseline_child(args, rank: int, world: int):
+    """Operative baseline in THE SAME invocation (same box, same lease, same N / steps / warm-up): every rank spawns
+    `baseline/torch_resnet50.py` as its own child process (fresh CUDA context + NCCL group on MASTER_PORT + 23) once our
+    arm has finished; the child samples its own clocks during its timed region.  Returns rank 0's parsed JSON line.
+    First attempt captures the step in a CUDA graph; if that child fails, one retry without the graph."""
+    script = os.path.join(ROOT, "baseline", "torch_resnet50.py")
+    env = dict(os.environ)
+    env["RANK"], env["WORLD_SIZE"] = str(rank), str(world)
+    env["LOCAL_RANK"] = os.environ.get("LOCAL_RANK", str(rank))
+    env.setdefault("MASTER_ADDR", "127.0.0.1")
+    base_port = int(os.environ.get("MASTER_PORT", "29500"))
+    result, notes = None, []
+    for attempt, graph in enumerate((True, False)):
+        env["MASTER_PORT"] = str(base_port + 23 + attempt)
+        cmd = [sys.executable, script, "--steps", str(args.steps), "--warmup", str(args.warmup), "--batch",
+               str(args.batch), "--classes", str(args.classes)] + (["--graph"] if graph else [])
+        try:
+            p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=args.baseline_timeout)
+            rc, out, err = p.returncode, p.stdout, p.stderr
+        except subprocess.TimeoutExpired as ex:
+            rc, out, err = -9, (ex.stdout or ""), "timeout"
+            if isinstance(out, bytes):
+                out = out.decode(errors="replace")
+        ok_all = _all_ranks_ok(rc == 0, world)
+        if rank == 0 and rc == 0:
+            for ln in out.splitlines():
+                if ln.startswith("{"):
+                    result = json.loads(ln)
+        if ok_all and (rank != 0 or result is not None):
+            break
+        notes.append(f"attempt graph={graph} failed rc={rc}: {str(err)[-300:]}")
+        result = None
+    if rank == 0 and result is not None and notes:
+        result["notes"] = notes
+    if rank == 0 and result is None:
+        result = {"unavailable": "; ".join(notes)[-600:]}
+    return result
+
+
+def _all_ranks_ok(ok: bool, world: int) -> bool:
+    """Agreement between the rank processes WITHOUT a live process group (ours is already shut down): files in /tmp."""
+    if world == 1:
+        return ok
+    import tempfile
+
+    # all ranks of one launch share the torchrun agent as parent: unique per launch, equal across ranks
+    tag = os.environ.get("MASTER_PORT", "0") + "_" + str(os.getppid())
+    d = os.path.join(tempfile.gettempdir(), f"b200ddl_bench_{tag}")
+    os.makedirs(d, exist_ok=True)
+    rk = os.environ.get("RANK", "0")
+    seq = getattr(_all_ranks_ok, "seq", 0)
+    _all_ranks_ok.seq = seq + 1
+    with open(os.path.join(d, f"{seq}_{rk}"), "w") as f:
+        f.write("1" if ok else "0")
+    t0 = time.time()
+    while time.time() - t0 < 120:
+        have = [os.path.join(d, f"{seq}_{r}") for r in range(world)]
+        if all(os.path.exists(h) and os.path.getsize(h) > 0 for h in have):
+            return all(open(h).read().strip() == "1" for h in have)
+        time.sleep(0.2)
+    return False
+
+
 def run_torch_baseline(args):
     sys.argv = [sys.argv[0], "--steps", str(args.steps), "--warmup", str(args.warmup), "--batch", str(args.batch),
                 "--classes", str(args.classes)] + (["--graph"] if args.graph_baseline else [])
@@ -128,6 +191,10 @@ def main():
     ap.add_argument("--no-overlap-wgrad", action="store_true", help="issue the weight-gradient GEMMs in line on the compute stream")
     ap.add_argument("--wgrad-smem", type=int, default=0)
     ap.add_argument("--fused-update", action="store_true", help="all-reduce + SGD + weight multicast in one kernel")
+    ap.add_argument("--no-baseline", action="store_true", help="skip the same-lease torch+cuDNN+NCCL baseline child")
+    ap.add_argument("--baseline-timeout", type=int, default=420)
+    ap.add_argument("--no-block-grad", action="store_true", help="A/B: block-gradient merge as separate reduce passes")
+    ap.add_argument("--no-stem-bwd-fuse", action="store_true", help="A/B: unfused max-pool / stem-BN backward")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -154,7 +221,9 @@ def main():
 
     engine = ResNet50Engine(batch=args.batch, num_classes=args.classes, device=dev, seed=0, max_ctas=0,
                             overlap_wgrad=not args.no_overlap_wgrad, wgrad_smem_budget=args.wgrad_smem,
-                            fuse_bwd_reduce=not args.no_fuse_bwd_reduce, fuse_bn_coeffs=args.fuse_bn_coeffs)
+                            fuse_bwd_reduce=not args.no_fuse_bwd_reduce, fuse_bn_coeffs=args.fuse_bn_coeffs,
+                            fuse_block_grad=False if args.no_block_grad else None,
+                            fuse_stem_bwd=False if args.no_stem_bwd_fuse else None)
     lr = 0.1 * world  # LR x world size (reference P1/03:301)
     base_opt = optim.SGD(lr, momentum=0.9, weight_decay=1e-4) if args.optimizer == "sgd" else optim.Adam(1e-3 * world)
     opt = (dist.DistributedOptimizer(base_opt, bucket_mb=args.bucket_mb, algo=args.algo, fused_update=args.fused_update)
@@ -228,17 +297,35 @@ def main():
                    "api": "b200ddl.train.Trainer.fit over loader.SyntheticDataset (pinned ring, side-stream H2D)",
                    "loader_wait_ms": ds.ring.consumer_wait_ms, "final_loss": hist.history["loss"][-1]}
 
+    cfg_flags = {"fuse_block_grad": bool(engine.fuse_block_grad), "fuse_stem_bwd": bool(engine.fuse_stem_bwd)}
+    # ---------------------------------------------------------------- same-lease baseline (torch + cuDNN + NCCL)
+    baseline = None
+    if not args.no_baseline:
+        dist.shutdown()  # our process group / symmetric memory are released before the children start theirs
+        del trainer, step, engine
+        torch.cuda.empty_cache()
+        baseline = run_baseline_child(args, rank, world)
     if rank == 0:
+        vs = None
+        if baseline is not None and baseline.get("value"):
+            vs = value / float(baseline["value"])
         out = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic uint8 224x224x3 images, random-init weights",
+            "vs_baseline": vs,
+            "baseline": (None if baseline is None else {
+                "what": "torchvision ResNet-50, bf16 autocast, channels_last, cuDNN, fused SGD, flat-gradient views, "
+                        "NCCL all_reduce per bucket + div overlapped from grad hooks (Horovod path, reference P1/03:301-302), "
+                        "CUDA graph when capturable; run as a child process in this same invocation",
+                **{k: baseline.get(k) for k in ("value", "ms_per_step", "clocks", "graph", "n_gpus", "steps", "warmup",
+                                                "config", "notes", "unavailable") if k in baseline}}),
+            "dtype": "bf16", "data": "synthetic uint8 224x224x3 images, random-init weights",
             "impl": "b200ddl",
             "config": {"model": "resnet50", "global_batch": global_batch, "per_gpu_batch": args.batch,
                        "image": "224x224x3", "classes": args.classes, "parallelism": f"dp{world}",
                        "optimizer": args.optimizer, "allreduce": getattr(opt, "algo", "none") if world > 1 else "none",
                        "fused_allreduce_sgd": bool(getattr(opt, "fused_update", False)),
-                       "cuda_graph": not args.no_graph, "overlap_wgrad": not args.no_overlap_wgrad,
+                       "cuda_graph": not args.no_graph, "overlap_wgrad": not args.no_overlap_wgrad, **cfg_flags,
                        "l2": "activations per step are several GB (>> 126 MB L2); no explicit flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step), "loss": loss, "accuracy": acc,

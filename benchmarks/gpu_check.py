@@ -430,7 +430,7 @@ def case_conv_time():
     return True
 
 
-def case_engine(overlap_wgrad: bool = True, quick: bool = False, fuse_bn_coeffs: bool = False):
+def case_engine(overlap_wgrad: bool = True, quick: bool = False, fuse_bn_coeffs: bool = False, fuse_block_grad=None):
     """ResNet-50 engine forward/backward vs torchvision (same weights, fp32 reference and bf16-autocast reference).
 
     `overlap_wgrad` selects where the weight-gradient GEMMs are issued (side stream = the engine default, or in line);
@@ -442,9 +442,9 @@ def case_engine(overlap_wgrad: bool = True, quick: bool = False, fuse_bn_coeffs:
     ok = True
     N, K = 32, 10
     eng = ResNet50Engine(batch=N, num_classes=K, zero_init_residual=False, seed=1, overlap_wgrad=overlap_wgrad,
-                         fuse_bn_coeffs=fuse_bn_coeffs)
+                         fuse_bn_coeffs=fuse_bn_coeffs, fuse_block_grad=fuse_block_grad)
     print(f"INFO engine overlap_wgrad={eng.overlap_wgrad} fuse_bwd_reduce={eng.fuse_bwd_reduce} "
-          f"fuse_bn_coeffs={eng.fuse_bn_coeffs}", flush=True)
+          f"fuse_bn_coeffs={eng.fuse_bn_coeffs} fuse_block_grad={eng.fuse_block_grad} fuse_stem_bwd={eng.fuse_stem_bwd}", flush=True)
     opt = optim.SGD(learning_rate=0.1, momentum=0.9)
     step = EngineTrainStep(eng, opt, use_graph=False)
     g = torch.Generator(device=DEV).manual_seed(5)
@@ -486,6 +486,8 @@ def case_engine(overlap_wgrad: bool = True, quick: bool = False, fuse_bn_coeffs:
                  "layer3.0.conv2.weight", "layer2.0.conv2.weight", "layer2.1.conv1.weight", "layer1.0.conv1.weight",
                  "layer1.0.conv2.weight", "layer1.0.bn1.bias", "bn1.weight", "conv1.weight"]:
         ge = eng.g(name).detach().float()
+        if name == "fc.weight":
+            ge = ge[:K]  # the engine stores the class dimension zero-padded to a GEMM-friendly size
         if name.endswith("conv1.weight") or "conv" in name or "downsample.0" in name:
             k = int(round(math.sqrt(ge.shape[0])))
             ge = C.weight_from_kernel_layout(ge, k, k)
@@ -530,6 +532,8 @@ def case_engine(overlap_wgrad: bool = True, quick: bool = False, fuse_bn_coeffs:
     torch.cuda.synchronize()
     for name, g1 in first_run.items():
         g2 = eng.g(name).detach().float()
+        if name == "fc.weight":
+            g2 = g2[:K]
         if g2.shape != g1.shape:
             k = int(round(math.sqrt(g2.shape[0])))
             g2 = C.weight_from_kernel_layout(g2, k, k)
@@ -623,6 +627,240 @@ def case_stem():
     return ok
 
 
+
+def _pack_mask(mask_bool: torch.Tensor) -> torch.Tensor:
+    """[M, C] bool -> uint8 [M * C / 8], bit k of byte cv = channel cv*8 + k (the layout bn_apply writes)."""
+    M, C_ = mask_bool.shape
+    bits = mask_bool.view(M, C_ // 8, 8).to(torch.int32)
+    return (bits * (2 ** torch.arange(8, device=mask_bool.device, dtype=torch.int32))).sum(-1).to(torch.uint8).view(-1).contiguous()
+
+
+BLOCK_GRAD_SHAPES = [
+    # name, N, H, block_cin (dgrad output channels), mid (dgrad K), compact skip
+    ("s1_256_64", 8, 56, 256, 64, False),
+    ("s2_512_128", 8, 28, 512, 128, False),
+    ("s2_first_512_256_compact", 8, 28, 512, 128, True),
+    ("s4_2048_512_partial_tile", 8, 7, 2048, 512, False),   # M = 392: last tile has 8 real rows
+    ("s3_compact_14", 6, 14, 1024, 256, True),
+    ("bench_s1_256_64_b256", 256, 56, 256, 64, False),      # the benchmark shape (M = 802,816)
+    ("bench_s2_first_b256_compact", 256, 28, 512, 128, True),
+]
+
+
+def case_block_grad():
+    """conv1-dgrad with the block-gradient epilogue (kStats = 3): dz = (dgrad + skip) * relu_mask, sum(dz), sum(dz*y3)."""
+    ok = True
+    e = ops.ext("_b200_ops")
+    for name, N, H, cb, mid, compact in BLOCK_GRAD_SHAPES:
+        try:
+            g = torch.Generator(device=DEV).manual_seed(17)
+            dy = torch.randn(N, H, H, mid, device=DEV, generator=g).to(torch.bfloat16)
+            w = torch.randn(1, mid, cb, device=DEV, generator=g) * (1.0 / mid ** 0.5)   # conv1: cb -> mid
+            hs = H // 2 if compact else H
+            skip = torch.randn(N, hs, hs, cb, device=DEV, generator=g).to(torch.bfloat16)
+            y3 = torch.randn(N, H, H, cb, device=DEV, generator=g).to(torch.bfloat16)
+            mbool = torch.rand(N * H * H, cb, device=DEV, generator=g) > 0.45
+            mask = _pack_mask(mbool)
+            s_dz = torch.zeros(cb, device=DEV); s_dzy = torch.zeros(cb, device=DEV)
+            dz = torch.full((N, H, H, cb), 3.0, device=DEV, dtype=torch.bfloat16)
+            op = C.ConvDgrad(dy, w, dz, 1, 1, 1, 0, block_grad=(skip, mask, y3, s_dz, s_dzy))
+            op.run()
+            torch.cuda.synchronize()
+            # reference in fp32 (bf16-rounded weights, like the kernel's operand)
+            ref_g = dy.float().view(-1, mid) @ w[0].to(torch.bfloat16).float()          # [M, cb]
+            if compact:
+                full = torch.zeros(N, H, H, cb, device=DEV)
+                full[:, 0::2, 0::2, :] = skip.float()
+            else:
+                full = skip.float()
+            ref_dz = (ref_g + full.view(-1, cb)) * mbool
+            ok &= report(f"block_grad_dz/{name}", rel_err(dz.view(-1, cb), ref_dz), 1.5e-2,
+                         f"grid={op.parts[0][0].grid} stats_mode={op.parts[0][0].stats_mode}")
+            dzq = dz.float().view(-1, cb)   # the sums are taken over the bf16 values that were stored
+            r0 = dzq.sum(0); r1 = (dzq * y3.float().view(-1, cb)).sum(0)
+            ok &= report(f"block_grad_sum_dz/{name}", float((s_dz - r0).abs().max() / (r0.abs().max() + 1e-6)), 2e-3)
+            ok &= report(f"block_grad_sum_dzy/{name}", float((s_dzy - r1).abs().max() / (r1.abs().max() + 1e-6)), 2e-3)
+            if N >= 256:
+                flush = torch.empty(256 * 1024 * 1024, device=DEV, dtype=torch.uint8)
+                # what it replaces: plain dgrad + reduce pass (mode 4) that also stores dz
+                g1 = torch.empty(N, H, H, cb, device=DEV, dtype=torch.bfloat16)
+                plain = C.ConvDgrad(dy, w, g1, 1, 1, 1, 0)
+                dz2 = torch.empty_like(g1)
+                skipd = full.to(torch.bfloat16).view(N, H, H, cb).contiguous()
+                def old():
+                    plain.run()
+                    e.bn_bwd_reduce(4, g1, skipd, mask, y3, None, None, dz2, s_dz, s_dzy)
+                t_new = time_fn(op.run, flush=flush)
+                t_plain = time_fn(plain.run, flush=flush)
+                t_old = time_fn(old, flush=flush)
+                nbytes = (dy.numel() + skip.numel() + y3.numel() + dz.numel()) * 2 + mask.numel()
+                print(f"TIME block_grad/{name} fused={t_new*1e3:.0f}us ({nbytes/t_new/1e6:.0f} GB/s algorithmic) "
+                      f"plain_dgrad={t_plain*1e3:.0f}us dgrad+reduce(mode4)={t_old*1e3:.0f}us", flush=True)
+        except Exception:
+            ok = False
+            print(f"CHECK block_grad/{name} EXCEPTION FAIL\n{traceback.format_exc()}", flush=True)
+    return ok
+
+
+def case_head():
+    """Classifier head: FC forward / dgrad / wgrad on the tcgen05 GEMMs + softmax_ce_head + fc_bias_grad vs torch fp32."""
+    ok = True
+    e = ops.ext("_b200_ops")
+    for N, K in ((256, 1000), (8, 5), (32, 10), (64, 200)):
+        try:
+            g = torch.Generator(device=DEV).manual_seed(23)
+            ncp = 64 if K <= 64 else (K + 127) // 128 * 128
+            pooled = torch.randn(N, 2048, device=DEV, generator=g).to(torch.bfloat16)
+            wm = torch.zeros(ncp, 2048, device=DEV)
+            wm[:K] = (torch.rand(K, 2048, device=DEV, generator=g) * 2 - 1) / 2048 ** 0.5 * 4
+            bias = torch.randn(K, device=DEV, generator=g) * 0.1
+            labels = torch.randint(0, K, (N,), device=DEV, generator=g)
+            w16 = wm.to(torch.bfloat16)
+            logits16 = torch.zeros(N, ncp, device=DEV, dtype=torch.bfloat16)
+            C.ConvForward(pooled.view(N, 1, 1, 2048), w16, logits16.view(N, 1, 1, ncp), 1, 1, 1, 0).run()
+            logits32 = torch.zeros(N, K, device=DEV); dl16 = torch.full((N, ncp), 9.0, device=DEV, dtype=torch.bfloat16)
+            rows = torch.zeros(N, device=DEV); st = torch.zeros(2, device=DEV)
+            e.softmax_ce_head(logits16, bias, labels, logits32, dl16, rows, st, 1.0 / N)
+            torch.cuda.synchronize()
+            ref_logits = pooled.float() @ w16[:K].float().t() + bias
+            ok &= report(f"head_logits/N{N}_K{K}", rel_err(logits32, ref_logits), 1.5e-2)
+            lg = logits32.clone().requires_grad_(True)   # CE itself is checked on the kernel's own logits
+            loss = torch.nn.functional.cross_entropy(lg, labels)
+            loss.backward()
+            ok &= report(f"head_loss/N{N}_K{K}", abs(st[0].item() / N - loss.item()), 1e-4)
+            ok &= report(f"head_acc/N{N}_K{K}", abs(st[1].item() - (logits32.argmax(1) == labels).float().sum().item()), 0.0)
+            ok &= report(f"head_dlogits/N{N}_K{K}", rel_err(dl16[:, :K], lg.grad), 1e-2)
+            ok &= report(f"head_dlogits_pad_zero/N{N}_K{K}", float(dl16[:, K:].float().abs().max()) if ncp > K else 0.0, 0.0)
+            db = torch.zeros(K, device=DEV)
+            e.fc_bias_grad(dl16, db)
+            ok &= report(f"head_dbias/N{N}_K{K}", rel_err(db, dl16[:, :K].float().sum(0)), 1e-5)
+            # weight gradient and data gradient on the GEMM kernels
+            dw = torch.zeros(ncp, 2048, device=DEV)
+            C.ConvWgrad(dl16.view(N, 1, 1, ncp), pooled.view(N, 1, 1, 2048), dw, 1, 1, 1, 0).run()
+            ok &= report(f"head_wgrad/N{N}_K{K}", rel_err(dw, dl16.float().t() @ pooled.float()), 1e-2)
+            dpooled = torch.zeros(N, 2048, device=DEV, dtype=torch.bfloat16)
+            C.ConvDgrad(dl16.view(N, 1, 1, ncp), wm.view(1, ncp, 2048), dpooled.view(N, 1, 1, 2048), 1, 1, 1, 0).run()
+            torch.cuda.synchronize()
+            ok &= report(f"head_dgrad/N{N}_K{K}", rel_err(dpooled, dl16.float() @ w16.float()), 1.5e-2)
+        except Exception:
+            ok = False
+            print(f"CHECK head/N{N}_K{K} EXCEPTION FAIL\n{traceback.format_exc()}", flush=True)
+    # stem filter pack kernel vs the python permutation
+    w = torch.randn(49, 64, 3, device=DEV)
+    a = torch.zeros(64, 192, device=DEV, dtype=torch.bfloat16); b = torch.full((64, 192), 5.0, device=DEV, dtype=torch.bfloat16)
+    C.pack_stem_weight(w, a)
+    e.pack_stem_weight(w, b)
+    ok &= report("pack_stem_weight", float((a.float() - b.float()).abs().max()), 0.0)
+    return ok
+
+
+def case_stem_bwd():
+    """max-pool backward fused with the stem BN+ReLU backward (head_stem.cu) vs the three-kernel path it replaces."""
+    ok = True
+    e = ops.ext("_b200_ops")
+    for N, Ho in ((4, 16), (3, 56), (256, 56)):
+        g = torch.Generator(device=DEV).manual_seed(31)
+        H = 2 * Ho
+        y0 = torch.randn(N, H, H, 64, device=DEV, generator=g).to(torch.bfloat16)
+        scale = torch.rand(64, device=DEV, generator=g) + 0.5
+        shift = torch.randn(64, device=DEV, generator=g) * 0.3
+        p0 = torch.empty(N, Ho, Ho, 64, device=DEV, dtype=torch.bfloat16)
+        idx = torch.empty(N, Ho, Ho, 64, device=DEV, dtype=torch.uint8)
+        e.bn_relu_maxpool_fwd(y0, scale, shift, p0, idx)
+        g1 = torch.randn(N, Ho, Ho, 64, device=DEV, generator=g).to(torch.bfloat16)
+        g2 = torch.randn(N, Ho, Ho, 64, device=DEV, generator=g).to(torch.bfloat16)
+        gamma = torch.rand(64, device=DEV, generator=g) + 0.5
+        mean = torch.randn(64, device=DEV, generator=g) * 0.1
+        invstd = torch.rand(64, device=DEV, generator=g) + 0.5
+        cnt = float(N * H * H)
+        # old path
+        da0 = torch.empty_like(y0)
+        e.maxpool_bwd(idx, g1, g2, da0)
+        s_o = torch.zeros(64, device=DEV); sy_o = torch.zeros(64, device=DEV)
+        e.bn_bwd_reduce(2, da0, None, None, y0, scale, shift, None, s_o, sy_o)
+        s_keep, sy_keep = s_o.clone(), sy_o.clone()
+        dg = torch.empty(64, device=DEV); db = torch.empty(64, device=DEV)
+        cA = torch.empty(64, device=DEV); cB = torch.empty(64, device=DEV); cC = torch.empty(64, device=DEV)
+        e.bn_bwd_coeffs(s_o, sy_o, gamma, mean, invstd, cnt, dg, db, cA, cB, cC)
+        dy_o = torch.empty_like(y0)
+        e.bn_bwd_apply(da0, y0, scale, shift, cA, cB, cC, dy_o)
+        # fused path
+        s_n = torch.zeros(64, device=DEV); sy_n = torch.zeros(64, device=DEV)
+        e.stem_pool_bn_bwd(0, idx, g1, g2, y0, scale, shift, None, None, None, None, s_n, sy_n)
+        dy_n = torch.full_like(y0, 7.0)
+        e.stem_pool_bn_bwd(1, idx, g1, g2, y0, scale, shift, cA, cB, cC, dy_n, s_n, sy_n)
+        torch.cuda.synchronize()
+        ok &= report(f"stem_bwd_sum_dz/N{N}_Ho{Ho}", float((s_n - s_keep).abs().max() / (s_keep.abs().max() + 1e-6)), 1e-4)
+        ok &= report(f"stem_bwd_sum_dzy/N{N}_Ho{Ho}", float((sy_n - sy_keep).abs().max() / (sy_keep.abs().max() + 1e-6)), 1e-4)
+        ok &= report(f"stem_bwd_dy/N{N}_Ho{Ho}", float((dy_n.float() - dy_o.float()).abs().max()), 0.0, "(bit-identical to the unfused path)")
+        # one-gradient variant (g2 = None)
+        e.maxpool_bwd(idx, g1, None, da0)
+        e.bn_bwd_apply(da0, y0, scale, shift, cA, cB, cC, dy_o)
+        e.stem_pool_bn_bwd(1, idx, g1, None, y0, scale, shift, cA, cB, cC, dy_n, s_n, sy_n)
+        torch.cuda.synchronize()
+        ok &= report(f"stem_bwd_dy_single_grad/N{N}_Ho{Ho}", float((dy_n.float() - dy_o.float()).abs().max()), 0.0)
+        if N >= 256:
+            flush = torch.empty(256 * 1024 * 1024, device=DEV, dtype=torch.uint8)
+            def old():
+                e.maxpool_bwd(idx, g1, g2, da0)
+                e.bn_bwd_reduce(2, da0, None, None, y0, scale, shift, None, s_o, sy_o)
+                e.bn_bwd_apply(da0, y0, scale, shift, cA, cB, cC, dy_o)
+            def new():
+                e.stem_pool_bn_bwd(0, idx, g1, g2, y0, scale, shift, None, None, None, None, s_n, sy_n)
+                e.stem_pool_bn_bwd(1, idx, g1, g2, y0, scale, shift, cA, cB, cC, dy_n, s_n, sy_n)
+            t_o = time_fn(old, flush=flush); t_n = time_fn(new, flush=flush)
+            t_r = time_fn(lambda: e.stem_pool_bn_bwd(0, idx, g1, g2, y0, scale, shift, None, None, None, None, s_n, sy_n), flush=flush)
+            print(f"TIME stem_bwd N{N}: unfused (pool_bwd+reduce+apply)={t_o*1e3:.0f}us fused (reduce+apply)={t_n*1e3:.0f}us "
+                  f"[reduce pass {t_r*1e3:.0f}us]", flush=True)
+    return ok
+
+
+def case_big_numerics():
+    """Numerics at the BENCHMARKED shapes (batch 256: full grids, halo / resident-filter paths, 802,816-pixel M) vs fp32."""
+    ok = True
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    for name, N, H, W, cin, cout, R, stride, pad in BIG_SHAPES:
+        try:
+            x, w, Ho, Wo = make_conv_case(N, H, W, cin, cout, R, stride, pad)
+            w16 = w.to(torch.bfloat16)
+            wk = w16.reshape(R * R * cout, cin).contiguous()
+            y = torch.empty(N, Ho, Wo, cout, device=DEV, dtype=torch.bfloat16)
+            ssum = torch.zeros(cout, device=DEV); ssq = torch.zeros(cout, device=DEV)
+            op = C.ConvForward(x, wk, y, R, R, stride, pad, ssum, ssq)
+            op.run()
+            torch.cuda.synchronize()
+            ref = C.conv_reference(x, w16, R, R, stride, pad)
+            ok &= report(f"big_fwd/{name}", rel_err(y, ref), 1.5e-2, f"box={op.box} halo={op.plan.halo} res={op.plan.resident_filter}")
+            yq = y.float()
+            ok &= report(f"big_fwd_stats_sum/{name}", float((ssum - yq.sum((0, 1, 2))).abs().max() / (yq.sum((0, 1, 2)).abs().max() + 1e-6)), 2e-3)
+            ok &= report(f"big_fwd_stats_sq/{name}", rel_err(ssq, (yq * yq).sum((0, 1, 2))), 2e-3)
+            del yq
+            g = torch.Generator(device=DEV).manual_seed(1)
+            dy = torch.randn(N, Ho, Wo, cout, device=DEV, generator=g).to(torch.bfloat16)
+            dx = torch.full((N, H, W, cin), 7.0, device=DEV, dtype=torch.bfloat16)
+            C.ConvDgrad(dy, w, dx, R, R, stride, pad).run()
+            torch.cuda.synchronize()
+            wt = C.weight_from_kernel_layout(w16.float(), R, R)
+            refd = torch.nn.grad.conv2d_input((N, cin, H, W), wt, dy.float().permute(0, 3, 1, 2), stride=stride,
+                                              padding=pad).permute(0, 2, 3, 1)
+            ok &= report(f"big_dgrad/{name}", rel_err(dx, refd), 1.5e-2)
+            del refd
+            dw = torch.zeros(R * R * cout, cin, device=DEV)
+            C.ConvWgrad(dy, x, dw, R, R, stride, pad).run()
+            torch.cuda.synchronize()
+            refw = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, R, R),
+                                               dy.float().permute(0, 3, 1, 2), stride=stride, padding=pad)
+            refw = C.weight_to_kernel_layout(refw).reshape(R * R * cout, cin)
+            ok &= report(f"big_wgrad/{name}", rel_err(dw, refw), 1.0e-2)
+            del ref, refw, x, y, dy, dx
+            torch.cuda.empty_cache()
+        except Exception:
+            ok = False
+            print(f"CHECK big/{name} EXCEPTION FAIL\n{traceback.format_exc()}", flush=True)
+    return ok
+
+
 def case_umma_probe():
     """Row-shifted SWIZZLE_128B descriptors: which (shift, base_offset) combinations read the right rows?"""
     ext = ops.ext("_b200_conv")
@@ -710,6 +948,11 @@ CASES = {
     "engine_serial_wgrad": lambda: case_engine(overlap_wgrad=False, quick=True),
     "engine_fused_bn_coeffs": lambda: case_engine(quick=True, fuse_bn_coeffs=True),
     "stem": case_stem,
+    "block_grad": case_block_grad,
+    "head": case_head,
+    "stem_bwd": case_stem_bwd,
+    "big_numerics": case_big_numerics,
+    "engine_unfused_block_grad": lambda: case_engine(quick=True, fuse_block_grad=False),
     "umma_probe": case_umma_probe,
 }
 

@@ -16,7 +16,7 @@ struct ConvPlanRaw {
   ConvParams p;
   int block_n;
   int grid;
-  int stats;  // 0 none, 1 forward BN statistics, 2 fused BN-backward reduction
+  int stats;  // 0 none, 1 forward BN statistics, 2 fused BN-backward reduction, 3 block-gradient merge + reduction
   int halo;   // 1: halo mode (needs res_b); tmA[1] is the [bw x (bh+2)] halo map of view 0
   int res_b;  // 1: the CTA's whole filter slice stays resident in shared memory (block_n == 64, n_blocks == 1, <= 9 tiles)
 };

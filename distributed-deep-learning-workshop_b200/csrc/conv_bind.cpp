@@ -50,7 +50,8 @@ struct ConvPlan {
   ConvPlan(std::vector<at::Tensor> views, at::Tensor weight, at::Tensor out, std::vector<int64_t> tap_map,
            std::vector<int64_t> tap_dw, std::vector<int64_t> tap_dh, int64_t bw, int64_t bh, int64_t bn,
            c10::optional<at::Tensor> stat_sum, c10::optional<at::Tensor> stat_sqsum, int64_t max_ctas,
-           c10::optional<at::Tensor> bwd_y, c10::optional<at::Tensor> bn_scale, c10::optional<at::Tensor> bn_shift) {
+           c10::optional<at::Tensor> bwd_y, c10::optional<at::Tensor> bn_scale, c10::optional<at::Tensor> bn_shift,
+           c10::optional<at::Tensor> add_src, c10::optional<at::Tensor> relu_mask) {
     TORCH_CHECK(!views.empty() && views.size() <= 4, "1..4 input views");
     for (auto& v : views) check_nhwc_view(v, "input view");
     check_nhwc_view(out, "out");
@@ -112,12 +113,14 @@ struct ConvPlan {
     }
     raw.tmB = map_2d(weight.data_ptr(), taps * cout, cin, cin, 64, raw.block_n);
     p.num_tiles = p.m_tiles * p.n_blocks;
-    raw.stats = stat_sum.has_value() ? (bwd_y.has_value() ? 2 : 1) : 0;
+    raw.stats = stat_sum.has_value() ? (bwd_y.has_value() ? (relu_mask.has_value() ? 3 : 2) : 1) : 0;
+    p.m_rows = N * Ho * Wo;
     // Resident filter: one N-block of 64 channels whose taps * kblocks filter tiles (8 KB each) fit in 72 KB.
     // B200DDL_NO_RESIDENT_FILTER=1 switches it off (A/B measurements).
     {
       const char* off = std::getenv("B200DDL_NO_RESIDENT_FILTER");
-      raw.res_b = (raw.block_n == 64 && p.n_blocks == 1 && taps * p.kblocks <= 9 && !(off && off[0] == '1')) ? 1 : 0;
+      raw.res_b = (raw.block_n == 64 && p.n_blocks == 1 && taps * p.kblocks <= 9 && !(off && off[0] == '1') &&
+                   raw.stats != 3) ? 1 : 0;
     }
     // Halo mode: a 3x3 stride-1 conv (9 taps on ONE view forming the full {-1,0,1}^2 offset grid, in any order) over
     // full-width single-image boxes: one [bw x (bh+2)] load per horizontal offset serves its three vertical taps.
@@ -153,6 +156,32 @@ struct ConvPlan {
       }
     }
     raw.tmY = raw.tmD;
+    if (raw.stats == 3) {
+      // block-gradient merge: out = dz = (acc + add_src) * relu_mask; sums of dz, dz*y (y = bwd_y, the block's y3)
+      TORCH_CHECK(p.mode == 0, "the block-gradient epilogue needs a flat (dense 1x1) plan");
+      check_nhwc_view(*bwd_y, "bwd_y");
+      TORCH_CHECK(bwd_y->sizes() == out.sizes() && bwd_y->is_contiguous(), "bwd_y must match the (dense) output");
+      TORCH_CHECK(relu_mask->is_cuda() && relu_mask->scalar_type() == at::kByte && relu_mask->is_contiguous() &&
+                      relu_mask->numel() == N * Ho * Wo * cout / 8, "relu_mask must be uint8 [M * Cout / 8]");
+      TORCH_CHECK(add_src.has_value(), "the block-gradient epilogue needs the skip gradient");
+      check_nhwc_view(*add_src, "add_src");
+      TORCH_CHECK(add_src->is_contiguous() && add_src->size(0) == N && add_src->size(3) == cout, "add_src: dense NHWC with Cout channels");
+      if (add_src->size(1) == Ho && add_src->size(2) == Wo) {
+        p.add_mode = 0;
+      } else {
+        TORCH_CHECK(Ho % 2 == 0 && Wo % 2 == 0 && add_src->size(1) == Ho / 2 && add_src->size(2) == Wo / 2,
+                    "add_src must have the output's grid or its stride-2 sub-grid");
+        p.add_mode = 1;
+      }
+      p.add_h = (int)Ho;
+      p.add_w = (int)Wo;
+      p.add_src = reinterpret_cast<const __nv_bfloat16*>(add_src->data_ptr());
+      p.relu_mask = relu_mask->data_ptr<uint8_t>();
+      raw.tmY = map_2d(bwd_y->data_ptr(), N * Ho * Wo, cout, cout, 64, kBlockM);
+      keep.push_back(*bwd_y);
+      keep.push_back(*add_src);
+      keep.push_back(*relu_mask);
+    }
     if (raw.stats == 2) {
       // fused BatchNorm-backward reduction: y has exactly the output's shape / layout
       TORCH_CHECK(bn_scale.has_value() && bn_shift.has_value(), "bwd stats need the forward BN scale/shift");
@@ -191,6 +220,7 @@ struct ConvPlan {
   int block_n() const { return raw.block_n; }
   int res_b() const { return raw.res_b; }
   int halo() const { return raw.halo; }
+  int stats_mode() const { return raw.stats; }
 };
 
 struct WgradPlan {
@@ -417,17 +447,19 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def(py::init<std::vector<at::Tensor>, at::Tensor, at::Tensor, std::vector<int64_t>, std::vector<int64_t>,
                     std::vector<int64_t>, int64_t, int64_t, int64_t, c10::optional<at::Tensor>,
                     c10::optional<at::Tensor>, int64_t, c10::optional<at::Tensor>, c10::optional<at::Tensor>,
-                    c10::optional<at::Tensor>>(),
+                    c10::optional<at::Tensor>, c10::optional<at::Tensor>, c10::optional<at::Tensor>>(),
            py::arg("views"), py::arg("weight"), py::arg("out"), py::arg("tap_map"), py::arg("tap_dw"),
            py::arg("tap_dh"), py::arg("bw"), py::arg("bh"), py::arg("bn"), py::arg("stat_sum") = c10::nullopt,
            py::arg("stat_sqsum") = c10::nullopt, py::arg("max_ctas") = 0, py::arg("bwd_y") = c10::nullopt,
-           py::arg("bn_scale") = c10::nullopt, py::arg("bn_shift") = c10::nullopt)
+           py::arg("bn_scale") = c10::nullopt, py::arg("bn_shift") = c10::nullopt, py::arg("add_src") = c10::nullopt,
+           py::arg("relu_mask") = c10::nullopt)
       .def("run", &b200::ConvPlan::run)
       .def_readonly("launches", &b200::ConvPlan::launches)
       .def_property_readonly("grid", &b200::ConvPlan::grid)
       .def_property_readonly("block_n", &b200::ConvPlan::block_n)
       .def_property_readonly("resident_filter", &b200::ConvPlan::res_b)
-      .def_property_readonly("halo", &b200::ConvPlan::halo);
+      .def_property_readonly("halo", &b200::ConvPlan::halo)
+      .def_property_readonly("stats_mode", &b200::ConvPlan::stats_mode);
   py::class_<b200::WgradPlan>(m, "WgradPlan")
       .def(py::init<at::Tensor, std::vector<at::Tensor>, at::Tensor, int64_t, int64_t, std::vector<int64_t>,
                     std::vector<int64_t>, std::vector<int64_t>, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t>(),

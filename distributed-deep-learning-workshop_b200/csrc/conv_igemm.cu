@@ -84,7 +84,12 @@ static void launch_n(const ConvPlanRaw& pl, cudaStream_t s) {
 void conv_plan_launch(const ConvPlanRaw& pl, cudaStream_t s) {
   if (pl.stats == 1) launch_n<1>(pl, s);
   else if (pl.stats == 2) launch_n<2>(pl, s);
-  else launch_n<0>(pl, s);
+  else if (pl.stats == 3) {
+    // block-gradient merge epilogue: flat 1x1 plans only, no resident-filter / halo variants
+    if (pl.block_n == 256) launch_t<256, 3>(pl, s);
+    else if (pl.block_n == 128) launch_t<128, 3>(pl, s);
+    else launch_t<64, 3>(pl, s);
+  } else launch_n<0>(pl, s);
 }
 
 }  // namespace b200

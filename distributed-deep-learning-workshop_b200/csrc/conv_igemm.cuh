@@ -30,6 +30,10 @@ namespace b200 {
 // kStats: 0 = plain epilogue, 1 = forward BatchNorm statistics (sum y, sum y^2), 2 = BatchNorm-backward reduction
 // fused into a dgrad GEMM: the output tile is g = dL/d(activation); with the activation's pre-BN tensor y (extra TMA
 // load per chunk) the statistics warps accumulate sum(dz), sum(dz*y) for dz = g * [y*scale + shift > 0].
+// kStats = 3 (flat 1x1 dgrad of a residual block's first conv): the whole gradient merge of the PREVIOUS block's output
+// happens in the epilogue - dz = (acc + skip_gradient) * relu_bitmask is what gets stored, and the statistics warps
+// accumulate sum(dz), sum(dz*y3) for that block's final BatchNorm.  The separate reduce pass (4 tensor reads + 1 write of
+// the widest activation of the block) and the store / re-read of the main-path gradient disappear.
 // The (up to four) parity views of the A operand as ONE kernel parameter: the per-tap choice is an index.
 struct TmapArray4 {
   CUtensorMap m[4];
@@ -44,7 +48,7 @@ constexpr int kHaloRows = 224;  // largest halo box: bw * (bh + 2) pixels (56 x 
 
 template <int BLOCK_N, int kStats = 0, bool kResB = false, bool kHalo = false>
 struct ConvSmem {
-  static constexpr int kYBytes = kStats == 2 ? 2 * kBlockM * 128 : 0;  // two 128x64 bf16 tiles of y
+  static constexpr int kYBytes = kStats >= 2 ? 2 * kBlockM * 128 : 0;  // two 128x64 bf16 tiles of y
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kASlot = kHalo ? kHaloRows * 128 : kABytes;     // bytes of A per pipeline stage
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -55,7 +59,7 @@ struct ConvSmem {
   static constexpr int kStatBytes = 2 * BLOCK_N * 4;
   static constexpr int kFixed = kResBytes + kStagingBytes + kYBytes + kBarBytes + kStatBytes;
   static constexpr int kStages = kResB ? ((232448 - kFixed) / kStageBytes > 8 ? 8 : (232448 - kFixed) / kStageBytes)
-                                       : ((BLOCK_N == 256) ? (kStats == 2 ? 3 : 4) : (BLOCK_N == 128 ? 5 : 6));
+                                       : ((BLOCK_N == 256) ? (kStats >= 2 ? 3 : 4) : (BLOCK_N == 128 ? 5 : 6));
   static constexpr int kTotal = kStages * kStageBytes + kFixed;
   static_assert(!kResB || BLOCK_N == 64, "resident filter: BLOCK_N == 64 only");
   static_assert(!kHalo || kResB, "halo mode builds on the resident filter");
@@ -113,7 +117,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
   if (kStats) {
     for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) sStat[i] = 0.f;
   }
-  if (kStats == 2) {
+  if (kStats >= 2) {
     // rows past the pixel box are never written by TMA: keep them finite (0 * NaN would poison the sums)
     for (int i = threadIdx.x; i < L::kYBytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(sY)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
@@ -335,6 +339,37 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
         h0 = th * p.bh;
         n0 = (rest / p.tiles_h) * p.bn;
       }
+      // kStats == 3: this thread's row of the skip gradient / ReLU bitmask (flat mode: tile row == pixel index).
+      // The 64 B + 4 B per 32-column half are prefetched one half ahead (slot = h), the first one before the
+      // accumulator wait, so the global-load latency hides behind the TMEM wait and the previous half's packing.
+      const __nv_bfloat16* arow = nullptr;
+      const uint8_t* mrow = nullptr;
+      uint4 gq[2][4];
+      uint32_t mq[2] = {0u, 0u};
+      if (kStats == 3) {
+        const int64_t grow = static_cast<int64_t>(m_tile) * kBlockM + row;
+        if (grow < p.m_rows) {
+          mrow = p.relu_mask + grow * (p.cout >> 3) + ((nb * BLOCK_N) >> 3);
+          if (p.add_mode == 0) {
+            arow = p.add_src + grow * p.cout + nb * BLOCK_N;
+          } else {
+            // compact skip gradient of a stride-2 1x1 projection: only even (h, w) positions carry a value
+            const int wq = static_cast<int>(grow % p.add_w);
+            const int64_t t = grow / p.add_w;
+            const int hq = static_cast<int>(t % p.add_h);
+            const int64_t nq = t / p.add_h;
+            if (((wq | hq) & 1) == 0)
+              arow = p.add_src + ((nq * (p.add_h >> 1) + (hq >> 1)) * (p.add_w >> 1) + (wq >> 1)) * p.cout + nb * BLOCK_N;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gq[0][j] = gq[1][j] = make_uint4(0u, 0u, 0u, 0u);
+        if (arow != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gq[0][j] = __ldg(reinterpret_cast<const uint4*>(arow) + j);
+        }
+        if (mrow != nullptr) mq[0] = __ldg(reinterpret_cast<const uint32_t*>(mrow));
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
@@ -347,7 +382,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
           named_bar_sync(4 + (chunk_ctr & 1), 256);  // ... and the statistics warps are done reading it
         else
           named_bar_sync(1, 128);
-        if (kStats == 2 && etid == 0) {
+        if (kStats >= 2 && etid == 0) {
           // pre-BN tensor tile for the fused BatchNorm-backward reduction (same pixels / channels as the output tile)
           const int b = chunk_ctr & 1;
           mbar_arrive_expect_tx(&y_bar[b], static_cast<uint32_t>(p.valid_rows) * 128u);
@@ -359,8 +394,33 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t r[32];
+          if (kStats == 3) {
+            // prefetch the next half (h ^ 1 of this chunk or h = 0 of the next chunk) into the other slot
+            const int nxt = c64 * 64 + h * 32 + 32;
+            if (nxt < BLOCK_N) {
+              if (arow != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gq[h ^ 1][j] = __ldg(reinterpret_cast<const uint4*>(arow + nxt) + j);
+              }
+              if (mrow != nullptr) mq[h ^ 1] = __ldg(reinterpret_cast<const uint32_t*>(mrow + (nxt >> 3)));
+            }
+          }
           tmem_ld_32x32b_x32(taddr + c64 * 64 + h * 32, r);
           tmem_ld_wait();
+          if (kStats == 3) {
+            // dz = (main-path gradient + skip gradient) * [block output > 0]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t gw[4] = {gq[h][j].x, gq[h][j].y, gq[h][j].z, gq[h][j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float lo = __uint_as_float(r[8 * j + 2 * e]) + __uint_as_float(gw[e] << 16);
+                const float hi = __uint_as_float(r[8 * j + 2 * e + 1]) + __uint_as_float(gw[e] & 0xFFFF0000u);
+                r[8 * j + 2 * e] = ((mq[h] >> (8 * j + 2 * e)) & 1u) ? __float_as_uint(lo) : 0u;
+                r[8 * j + 2 * e + 1] = ((mq[h] >> (8 * j + 2 * e + 1)) & 1u) ? __float_as_uint(hi) : 0u;
+              }
+            }
+          }
           if (c64 == BLOCK_N / 64 - 1 && h == 1) {
             // all TMEM reads of this accumulator are done: hand it back to the MMA warp
             tc_fence_before();
@@ -436,6 +496,21 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
             s1 += hi;
             q0 = fmaf(lo, lo, q0);
             q1 = fmaf(hi, hi, q1);
+          }
+        } else if (kStats == 3) {
+          // the staged tile already is dz (merged + masked by the epilogue): accumulate sum(dz) and sum(dz * y)
+          const uint8_t* ybuf = sY + b * (kBlockM * 128);
+          mbar_wait(&y_bar[b], (chunk_ctr >> 1) & 1);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + xoff[i & 7] + i * 128);
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(ybuf + xoff[i & 7] + i * 128);
+            const float y0 = __uint_as_float(v << 16), y1 = __uint_as_float(v & 0xFFFF0000u);
+            const float g0 = __uint_as_float(w << 16), g1 = __uint_as_float(w & 0xFFFF0000u);
+            s0 += g0;
+            s1 += g1;
+            q0 = fmaf(g0, y0, q0);
+            q1 = fmaf(g1, y1, q1);
           }
         } else {
           // dz = g * [y*scale + shift > 0];  accumulate sum(dz) and sum(dz * y)

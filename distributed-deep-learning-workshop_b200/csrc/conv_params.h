@@ -1,5 +1,6 @@
 // Kernel parameter blocks shared by device code and the (torch-facing) host code.
 #pragma once
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace b200 {
@@ -33,6 +34,12 @@ struct ConvParams {
   int8_t halo_dw[3];     // horizontal offset of stage s
   int8_t halo_dh0;       // vertical offset of row-shift 0 (normally -1)
   int8_t halo_tap[9];    // filter tap index of (stage s, row shift r) at [s * 3 + r]
+  // kStats == 3 (flat mode): dz = (acc + add_src) * relu_mask is stored; sums of dz, dz*y go to stat_sum / stat_sqsum
+  const __nv_bfloat16* add_src;  // skip gradient: dense [M, Cout] (add_mode 0) or compact [N, H/2, W/2, Cout] (add_mode 1)
+  const uint8_t* relu_mask;      // 1 bit per element, [M, Cout / 8]
+  int add_mode;
+  int add_h, add_w;              // add_mode 1: spatial extent of the OUTPUT grid (rows decode to (n, h, w))
+  int64_t m_rows;                // number of real rows (pixels) of the flat problem
 };
 
 // Weight-gradient GEMM:  dW[tap][co][ci] += sum_px dY[px, co] * X_tap[px, ci]

@@ -836,10 +836,10 @@ void weight_prep(const float* w, void* wf, void* wd, int taps, int cout, int cin
 
 
 // All conv layers in one launch: table rows = (src offset in the flat fp32 master, dst offset in the flat bf16
-// dgrad buffer, taps, cout, cin, first flat element index of the layer); binary search over <= 64 layers in smem.
+// dgrad buffer, taps, cout, cin, first flat element index of the layer); binary search over <= 128 rows in smem.
 __global__ void weight_prep_batched_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ wd,
                                            const int64_t* __restrict__ table, int layers, int64_t total) {
-  __shared__ int64_t t[64 * 6];
+  __shared__ int64_t t[128 * 6];
   for (int i = threadIdx.x; i < layers * 6; i += blockDim.x) t[i] = table[i];
   __syncthreads();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {

@@ -55,6 +55,13 @@ void gap_fwd(const void* x, void* out, int N, int HW, int C, float drop_p, uint6
 void gap_bwd(const void* dout, void* dx, int N, int HW, int C, float drop_p, uint64_t seed, cudaStream_t s);
 void softmax_ce(const float* logits, const int64_t* labels, float* dlogits, float* loss_rows, float* stats, int B,
                 int K, float grad_scale, cudaStream_t s);
+void softmax_ce_head(const void* logits16, int ld, const float* bias, const int64_t* labels, float* logits32,
+                     void* dlogits16, float* loss_rows, float* stats, int B, int K, float grad_scale, cudaStream_t s);
+void fc_bias_grad(const void* dlogits16, int ld, float* dbias, int B, int K, cudaStream_t s);
+void pack_stem_weight(const float* w, void* out, cudaStream_t s);
+void stem_pool_bn_bwd(int pass, const void* idx, const void* g1, const void* g2, const void* y, const float* scale,
+                      const float* shift, const float* cA, const float* cB, const float* cC, void* dy, float* sum_dz,
+                      float* sum_dzy, int N, int Ho, int Wo, cudaStream_t s);
 void preprocess_u8(const uint8_t* x, void* out, int64_t npix, int cpad, float mul, float add, cudaStream_t s);
 void resize_bilinear_u8(const uint8_t* x, uint8_t* out, int N, int H, int W, int OH, int OW, cudaStream_t s);
 void weight_prep(const float* w, void* wf, void* wd, int taps, int cout, int cin, cudaStream_t s);

@@ -215,6 +215,64 @@ void softmax_ce(Tensor logits, Tensor labels, OptT dlogits, OptT loss_rows, Tens
                    (int)logits.size(0), (int)logits.size(1), (float)grad_scale, cur());
   after();
 }
+// classifier head: bf16 logits [B, ld] (first K columns real) + fp32 bias -> loss / accuracy / bf16 dlogits [B, ld]
+void softmax_ce_head(Tensor logits16, Tensor bias, Tensor labels, OptT logits32, OptT dlogits16, OptT loss_rows,
+                     Tensor stats, double grad_scale) {
+  chk(logits16, at::kBFloat16, "logits16");
+  chk(bias, at::kFloat, "bias");
+  chk(labels, at::kLong, "labels");
+  chk(stats, at::kFloat, "stats");
+  TORCH_CHECK(logits16.dim() == 2 && bias.numel() <= logits16.size(1) && labels.numel() == logits16.size(0));
+  const int B = (int)logits16.size(0), ld = (int)logits16.size(1), K = (int)bias.numel();
+  if (logits32.has_value()) { chk(*logits32, at::kFloat, "logits32"); TORCH_CHECK(logits32->numel() == (int64_t)B * K); }
+  if (dlogits16.has_value()) { chk(*dlogits16, at::kBFloat16, "dlogits16"); TORCH_CHECK(dlogits16->numel() == logits16.numel()); }
+  b200::softmax_ce_head(logits16.data_ptr(), ld, bias.data_ptr<float>(), labels.data_ptr<int64_t>(),
+                        logits32.has_value() ? logits32->data_ptr<float>() : nullptr,
+                        dlogits16.has_value() ? dlogits16->data_ptr() : nullptr,
+                        loss_rows.has_value() ? loss_rows->data_ptr<float>() : nullptr, stats.data_ptr<float>(), B, K,
+                        (float)grad_scale, cur());
+  after();
+}
+void fc_bias_grad(Tensor dlogits16, Tensor dbias) {
+  chk(dlogits16, at::kBFloat16, "dlogits16");
+  chk(dbias, at::kFloat, "dbias");
+  TORCH_CHECK(dlogits16.dim() == 2 && dbias.numel() <= dlogits16.size(1));
+  b200::fc_bias_grad(dlogits16.data_ptr(), (int)dlogits16.size(1), dbias.data_ptr<float>(), (int)dlogits16.size(0),
+                     (int)dbias.numel(), cur());
+  after();
+}
+void pack_stem_weight(Tensor w, Tensor out) {
+  chk(w, at::kFloat, "w");
+  chk(out, at::kBFloat16, "out");
+  TORCH_CHECK(w.numel() == 49 * 64 * 3 && out.numel() == 64 * 192);
+  b200::pack_stem_weight(w.data_ptr<float>(), out.data_ptr(), cur());
+  after();
+}
+// max-pool 3x3/2 backward fused with the stem BN+ReLU backward; pass 0 = reduce, pass 1 = apply (see head_stem.cu)
+void stem_pool_bn_bwd(int64_t pass, Tensor idx, Tensor g1, OptT g2, Tensor y, Tensor scale, Tensor shift, OptT cA, OptT cB,
+                      OptT cC, OptT dy, Tensor sum_dz, Tensor sum_dzy) {
+  chk(idx, at::kByte, "idx");
+  chk(g1, at::kBFloat16, "g1");
+  chk(y, at::kBFloat16, "y");
+  chk(scale, at::kFloat, "scale");
+  chk(shift, at::kFloat, "shift");
+  TORCH_CHECK(y.dim() == 4 && y.size(3) == 64 && g1.dim() == 4 && g1.size(3) == 64, "stem tail: 64 channels, NHWC");
+  const int N = (int)g1.size(0), Ho = (int)g1.size(1), Wo = (int)g1.size(2);
+  TORCH_CHECK(y.size(0) == N && y.size(1) == 2 * Ho && y.size(2) == 2 * Wo && idx.numel() == g1.numel());
+  TORCH_CHECK(Ho % 8 == 0 && Wo % 8 == 0, "stem tail: pooled grid must tile by 8");
+  if (g2.has_value()) { chk(*g2, at::kBFloat16, "g2"); TORCH_CHECK(g2->numel() == g1.numel()); }
+  TORCH_CHECK(pass == 0 || (cA.has_value() && cB.has_value() && cC.has_value() && dy.has_value()));
+  if (dy.has_value()) { chk(*dy, at::kBFloat16, "dy"); TORCH_CHECK(dy->numel() == y.numel()); }
+  b200::stem_pool_bn_bwd((int)pass, idx.data_ptr(), g1.data_ptr(), vp(g2), y.data_ptr(), scale.data_ptr<float>(),
+                         shift.data_ptr<float>(), fp(cA), fp(cB), fp(cC), dy.has_value() ? dy->data_ptr() : nullptr,
+                         sum_dz.data_ptr<float>(), sum_dzy.data_ptr<float>(), N, Ho, Wo, cur());
+  after();
+}
+// cudaMemsetAsync on the current stream (a memset node under graph capture, not a kernel)
+void zero_(Tensor t) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous());
+  C10_CUDA_CHECK(cudaMemsetAsync(t.data_ptr(), 0, t.numel() * t.element_size(), cur()));
+}
 void preprocess_u8(Tensor x, Tensor out, double mul, double add) {
   chk(x, at::kByte, "x");
   chk(out, at::kBFloat16, "out");
@@ -241,7 +299,7 @@ void weight_prep_batched(Tensor params, Tensor wd, Tensor table, int64_t total) 
   chk(params, at::kFloat, "params");
   chk(wd, at::kBFloat16, "wd");
   chk(table, at::kLong, "table");
-  TORCH_CHECK(table.dim() == 2 && table.size(1) == 6 && table.size(0) <= 64);
+  TORCH_CHECK(table.dim() == 2 && table.size(1) == 6 && table.size(0) <= 128);
   b200::weight_prep_batched(params.data_ptr<float>(), wd.data_ptr(), table.data_ptr<int64_t>(), (int)table.size(0),
                             total, cur());
   after();
@@ -297,6 +355,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gap_fwd", &gap_fwd);
   m.def("gap_bwd", &gap_bwd);
   m.def("softmax_ce", &softmax_ce);
+  m.def("softmax_ce_head", &softmax_ce_head, py::arg("logits16"), py::arg("bias"), py::arg("labels"),
+        py::arg("logits32") = c10::nullopt, py::arg("dlogits16") = c10::nullopt, py::arg("loss_rows") = c10::nullopt,
+        py::arg("stats"), py::arg("grad_scale") = 1.0);
+  m.def("fc_bias_grad", &fc_bias_grad);
+  m.def("pack_stem_weight", &pack_stem_weight);
+  m.def("stem_pool_bn_bwd", &stem_pool_bn_bwd, py::arg("pass_"), py::arg("idx"), py::arg("g1"), py::arg("g2"), py::arg("y"),
+        py::arg("scale"), py::arg("shift"), py::arg("cA") = c10::nullopt, py::arg("cB") = c10::nullopt,
+        py::arg("cC") = c10::nullopt, py::arg("dy") = c10::nullopt, py::arg("sum_dz"), py::arg("sum_dzy"));
+  m.def("zero_", &zero_);
   m.def("preprocess_u8", &preprocess_u8);
   m.def("resize_bilinear_u8", &resize_bilinear_u8);
   m.def("weight_prep", &weight_prep);

@@ -87,7 +87,8 @@ class ResNet50Engine:
                  image_size: int = 224, dropout: float = 0.0, bn_momentum: float = 0.1, bn_eps: float = 1e-5,
                  seed: int = 0, max_ctas: int = 0, zero_init_residual: bool = True, native_stem: bool = True,
                  overlap_wgrad: bool = True, wgrad_smem_budget: int = 0, fuse_bwd_reduce: bool = True,
-                 fuse_bn_coeffs: bool = False):
+                 fuse_bn_coeffs: bool = False, fuse_block_grad: Optional[bool] = None,
+                 fuse_stem_bwd: Optional[bool] = None):
         ops.require_native()
         self.zero_init_residual = zero_init_residual
         self.native_stem = native_stem
@@ -101,7 +102,13 @@ class ResNet50Engine:
         # 19.39 vs 18.89 ms per step in an interleaved A/B at equal clocks (profiles/README.md 2.9) - a tiny dependent
         # kernel costs only ~1.6 us of step time, the per-CTA coefficient recomputation in 106 streaming kernels more.
         self.fuse_bn_coeffs = fuse_bn_coeffs or os.environ.get("B200DDL_FUSE_BN_COEFFS") == "1"
+        # the gradient merge at every residual-block boundary (main path + skip path, ReLU mask, bn3 reduction) runs in
+        # the epilogue of the next block's conv1 dgrad GEMM (conv_igemm kStats = 3); B200DDL_NO_BLOCK_GRAD=1 disables
+        self.fuse_block_grad = (os.environ.get("B200DDL_NO_BLOCK_GRAD") != "1") if fuse_block_grad is None else bool(fuse_block_grad)
+        # max-pool backward fused with the stem BatchNorm backward (csrc/head_stem.cu); B200DDL_NO_STEM_BWD_FUSE=1 disables
+        self.fuse_stem_bwd = (os.environ.get("B200DDL_NO_STEM_BWD_FUSE") != "1") if fuse_stem_bwd is None else bool(fuse_stem_bwd)
         self._fused_reduce = set()
+        self._block_fused = set()   # bn3 names whose reduction (and dz) come out of a fused dgrad epilogue
         self.wgrad_smem_budget = wgrad_smem_budget
         self.aux_streams: List[torch.cuda.Stream] = []
         if image_size % 32:
@@ -134,20 +141,22 @@ class ResNet50Engine:
             specs.append(ParamSpec(name + ".weight", (c,), "gamma"))
             specs.append(ParamSpec(name + ".bias", (c,), "beta"))
 
-        # backward completion order: fc, blocks reversed (bn3, [bn_ds], conv3, bn2, conv2, bn1, conv1, [conv_ds]), stem
-        specs.append(ParamSpec("fc.weight", (self.num_classes, 2048), "fc_w"))
+        # backward completion order: fc, blocks reversed (bn3, conv3, bn2, conv2, bn1, [bn_ds, conv_ds], conv1), stem.
+        # The FC filter is stored with its class dimension padded to a GEMM-friendly size (zero rows: zero gradient,
+        # so they stay zero under SGD / Adam / Adadelta); state_dict() exposes the real [num_classes, 2048] slice.
+        self.classes_padded = 64 if self.num_classes <= 64 else _align(self.num_classes, 128)
+        specs.append(ParamSpec("fc.weight", (self.classes_padded, 2048), "fc_w"))
         specs.append(ParamSpec("fc.bias", (self.num_classes,), "fc_b"))
         for b in reversed(self.blocks):
             bn(b.name + ".bn3", b.mid * 4)
-            if b.downsample:
-                bn(b.name + ".downsample.1", b.mid * 4)
             conv(b.name + ".conv3", b.mid, b.mid * 4, 1)
             bn(b.name + ".bn2", b.mid)
             conv(b.name + ".conv2", b.mid, b.mid, 3)
             bn(b.name + ".bn1", b.mid)
-            conv(b.name + ".conv1", b.cin, b.mid, 1)
             if b.downsample:
+                bn(b.name + ".downsample.1", b.mid * 4)
                 conv(b.name + ".downsample.0", b.cin, b.mid * 4, 1)
+            conv(b.name + ".conv1", b.cin, b.mid, 1)
         bn("bn1", 64)
         specs.append(ParamSpec("conv1.weight", (49, 64, 3), "conv"))
         off = 0
@@ -176,7 +185,7 @@ class ResNet50Engine:
                 v.fill_(0.0 if (self.zero_init_residual and s.name.endswith("bn3.weight")) else 1.0)
             elif s.kind == "fc_w":
                 bound = 1.0 / math.sqrt(2048)
-                v.copy_((torch.rand(s.shape, generator=g) * 2 - 1) * bound)
+                v[:self.num_classes].copy_((torch.rand((self.num_classes, 2048), generator=g) * 2 - 1) * bound)
             elif s.kind == "fc_b":
                 bound = 1.0 / math.sqrt(2048)
                 v.copy_((torch.rand(s.shape, generator=g) * 2 - 1) * bound)
@@ -219,13 +228,11 @@ class ResNet50Engine:
         tap subsets) and the packed stem filter."""
         if getattr(self, "_wd_total", 0) > 0:
             self._e.weight_prep_batched(self.params, self._wd16, self._wd_table, self._wd_total)
-        for d in self._dgrads:
-            d.refresh_weights()  # no-op for the batched ones
         self._refresh_stem_weight()
 
     def _refresh_stem_weight(self) -> None:
         if self.native_stem:
-            C.pack_stem_weight(self.p("conv1.weight"), self._stem_w16)
+            self._e.pack_stem_weight(self.p("conv1.weight"), self._stem_w16)
         else:
             self._stem_w.copy_(self._stem_oihw_from_flat())
 
@@ -253,8 +260,7 @@ class ResNet50Engine:
         self.labels = torch.zeros(N, device=dev, dtype=torch.int64)
         self.x16 = torch.zeros(N, S, S, 3, **bf)
         self.stats = torch.zeros(2, **f32)          # [sum loss, correct]
-        self.logits = torch.zeros(N, self.num_classes, **f32)
-        self.dlogits = torch.zeros(N, self.num_classes, **f32)
+        self.logits = torch.zeros(N, self.num_classes, **f32)  # fp32 logits (+bias) for predict(); written by the CE kernel
         self.loss_rows = torch.zeros(N, **f32)
 
         # BN work buffers (per BN): sum, sqsum, mean, invstd, scale, shift, sum_dz, sum_dzy, cA, cB, cC
@@ -298,24 +304,51 @@ class ResNet50Engine:
                 self._wg_stream = torch.cuda.Stream(device=dev)
                 self.aux_streams = [self._wg_stream]
 
-        # bf16 dgrad copies ([tap][Cin][Cout]) of every stride-1 filter live in one flat buffer refreshed by ONE kernel
+        # bf16 dgrad copies ([tap][Cin][Cout]) of EVERY filter (stride-1 layers whole, stride-2 layers per output-parity
+        # tap subset, the FC matrix) live in one flat buffer refreshed by ONE kernel (weight_prep_batched).
         self._wd_table_rows = []
+        self._wd_slices: Dict[str, List[Tuple[int, int]]] = {}   # conv name -> [(offset, numel)] per dgrad part
         wd_total = 0
+
+        def add_dgrad_weights(full: str, parts: List[List[int]]):
+            nonlocal wd_total
+            sp = self.spec[full + ".weight"]
+            taps, cout, cin = sp.shape if len(sp.shape) == 3 else (1, sp.shape[0], sp.shape[1])
+            out = []
+            for idx in parts:
+                start = wd_total
+                i = 0
+                while i < len(idx):  # one table row per run of consecutive taps
+                    j = i
+                    while j + 1 < len(idx) and idx[j + 1] == idx[j] + 1:
+                        j += 1
+                    n = j - i + 1
+                    self._wd_table_rows.append([sp.offset + idx[i] * cout * cin, wd_total, n, cout, cin, wd_total])
+                    wd_total += n * cout * cin
+                    i = j + 1
+                out.append((start, wd_total - start))
+            self._wd_slices[full] = out
+
+        fuse_bg = self.fuse_block_grad and training
         if training:
-            for b in self.blocks:
+            add_dgrad_weights("fc", [[0]])
+            for bi, b in enumerate(self.blocks):
                 for cname, k, stride in (("conv1", 1, 1), ("conv2", 3, b.stride), ("conv3", 1, 1),
                                          ("downsample.0", 1, b.stride)):
                     if cname == "downsample.0" and not b.downsample:
                         continue
-                    if stride != 1:
-                        continue
-                    sp = self.spec[b.name + "." + cname + ".weight"]
-                    self._wd_table_rows.append([sp.offset, wd_total, sp.shape[0], sp.shape[1], sp.shape[2], wd_total])
-                    wd_total += sp.numel
+                    if cname == "downsample.0" and stride == 2 and fuse_bg and bi > 0:
+                        parts = [[0]]  # compact dgrad: a dense 1x1 GEMM on the strided grid
+                    else:
+                        parts = C.ConvDgrad.part_taps(k, k, stride, (k - 1) // 2)
+                    add_dgrad_weights(b.name + "." + cname, parts)
+            assert len(self._wd_table_rows) <= 128
             self._wd16 = torch.zeros(max(wd_total, 8), **bf)
             self._wd_total = wd_total
             self._wd_table = torch.tensor(self._wd_table_rows, device=dev, dtype=torch.int64).view(-1, 6)
-            self._wd_off = {r[0]: (r[1], r[2] * r[3] * r[4]) for r in self._wd_table_rows}
+
+        def wd_views(full: str) -> List[torch.Tensor]:
+            return [self._wd16[o:o + n] for o, n in self._wd_slices[full]]
 
         self.act: Dict[str, torch.Tensor] = {}
         self._fwd: Dict[str, C.ConvForward] = {}
@@ -328,8 +361,9 @@ class ResNet50Engine:
             n = int(math.prod(shape))
             return self._scr[key][:n].view(shape)
 
+        dz_keys = ["dzA", "dzB"]
         x_in = self.p0
-        for b in self.blocks:
+        for bi, b in enumerate(self.blocks):
             Hi, Ho, mid, cout = b.h_in, b.h_out, b.mid, b.mid * 4
             A = self.act
             A[b.name + ".y1"] = torch.zeros(N, Hi, Hi, mid, **bf)
@@ -358,12 +392,27 @@ class ResNet50Engine:
                     gw = self.g(full + ".weight")
                     self._wg[full] = C.ConvWgrad(dy, xin, gw.view(gw.shape[0] * gw.shape[1], gw.shape[2]), k, k,
                                                  stride, pad, 0, mc, self.wgrad_smem_budget)
-                    dx = scr("dds" if cname == "downsample.0" else "da", xin.shape)
-                    wview = None
-                    if stride == 1:
-                        o, nel = self._wd_off[self.spec[full + ".weight"].offset]
-                        wview = self._wd16[o:o + nel]
                     bwd_stats = None
+                    block_grad = None
+                    d_stride = stride
+                    if cname == "downsample.0":
+                        if stride == 2 and fuse_bg and bi > 0:
+                            # compact gradient on the strided grid; the fused conv1 epilogue scatters it on the fly
+                            dx = scr("dds", (N, Ho, Ho, b.cin))
+                            d_stride = 1
+                        else:
+                            dx = scr("dds", xin.shape)
+                    elif cname == "conv1" and fuse_bg and bi > 0:
+                        # dx = complete masked gradient dz of the PREVIOUS block's output (+ its bn3 reduction)
+                        pb = self.blocks[bi - 1]
+                        dx = scr(dz_keys[(bi - 1) % 2], xin.shape)
+                        skip = scr("dds", (N, Ho, Ho, b.cin) if b.stride == 2 else xin.shape) if b.downsample \
+                            else scr(dz_keys[bi % 2], xin.shape)
+                        pw = self.bnw[pb.name + ".bn3"]
+                        block_grad = (skip, A[pb.name + ".mask"], A[pb.name + ".y3"], pw["sum_dz"], pw["sum_dzy"])
+                        self._block_fused.add(pb.name + ".bn3")
+                    else:
+                        dx = scr("da", xin.shape)
                     if self.fuse_bwd_reduce and stride == 1 and cname in ("conv2", "conv3"):
                         # dx is the gradient of a1 (conv2) / a2 (conv3): fuse the reduction of bn1 / bn2
                         pbn = "bn1" if cname == "conv2" else "bn2"
@@ -371,15 +420,25 @@ class ResNet50Engine:
                         py = A[b.name + (".y1" if cname == "conv2" else ".y2")]
                         bwd_stats = (py, pw["scale"], pw["shift"], pw["sum_dz"], pw["sum_dzy"])
                         self._fused_reduce.add(b.name + "." + pbn)
-                    dgr = C.ConvDgrad(dy, self.p(full + ".weight"), dx, k, k, stride, pad, mc, wbuf=wview,
-                                      bwd_stats=bwd_stats)
+                    dgr = C.ConvDgrad(dy, self.p(full + ".weight"), dx, k, k, d_stride, pad, mc, wbufs=wd_views(full),
+                                      bwd_stats=bwd_stats, block_grad=block_grad)
                     self._dg[full] = dgr
                     self._dgrads.append(dgr)
             x_in = A[b.name + ".out"]
         self.feat = x_in  # [N, 7, 7, 2048]
         self.pooled = torch.zeros(N, 2048, **bf)
+        # classifier head on the same tcgen05 kernels: a 1x1 "convolution" over a 1x1 image (reference Dense, P1/02:175)
+        ncp = self.classes_padded
+        self.logits16 = torch.zeros(N, ncp, **bf)
+        self._fc_fwd = C.ConvForward(self.pooled.view(N, 1, 1, 2048), self.w16v("fc.weight"), self.logits16.view(N, 1, 1, ncp),
+                                     1, 1, 1, 0, None, None, mc)
         if training:
+            self.dlogits16 = torch.zeros(N, ncp, **bf)
             self.dpooled = torch.zeros(N, 2048, **bf)
+            self._fc_wg = C.ConvWgrad(self.dlogits16.view(N, 1, 1, ncp), self.pooled.view(N, 1, 1, 2048),
+                                      self.g("fc.weight"), 1, 1, 1, 0, 0, mc, 0)
+            self._fc_dg = C.ConvDgrad(self.dlogits16.view(N, 1, 1, ncp), self.p("fc.weight").view(1, ncp, 2048),
+                                      self.dpooled.view(N, 1, 1, 2048), 1, 1, 1, 0, mc, wbufs=wd_views("fc"))
             if self.native_stem:
                 dy0 = self._scr["dzA"][:self.y0.numel()].view(self.y0.shape)
                 self._stem_wg = C.StemWgrad(self.x_u8, dy0, self.g("conv1.weight").view(-1), max_ctas=self.max_ctas)
@@ -423,7 +482,7 @@ class ResNet50Engine:
         e, N, A = self._e, self.batch, self.act
         w0 = self.bnw["bn1"]
         if training and self.fuse_bn_coeffs:
-            self._bn_fwd_sums.zero_()  # nobody zeroes them after use on the fused path
+            e.zero_(self._bn_fwd_sums)  # nobody zeroes them after use on the fused path
         if self.native_stem:
             # 7x7/2 stem on the tensor cores straight from the uint8 batch (normalisation + BN statistics fused)
             self._stem_fwd.run()
@@ -457,11 +516,11 @@ class ResNet50Engine:
         drop = self.dropout if training else 0.0
         self._drop_seed = self.seed * 1000003 + self._step_count
         e.gap_fwd(self.feat, self.pooled, drop, self._drop_seed)
-        wfc = self.w16v("fc.weight")
-        self.logits.copy_(torch.nn.functional.linear(self.pooled, wfc).float() + self.p("fc.bias"))
-        self.stats.zero_()
-        e.softmax_ce(self.logits, self.labels, self.dlogits if training else None, self.loss_rows, self.stats,
-                     1.0 / N)
+        self._fc_fwd.run()  # bf16 logits (class dimension padded) on the tcgen05 GEMM
+        e.zero_(self.stats)
+        # + bias, softmax cross-entropy, accuracy, bf16 dlogits (padded columns zero) in one kernel
+        e.softmax_ce_head(self.logits16, self.p("fc.bias"), self.labels, self.logits,
+                          self.dlogits16 if training else None, self.loss_rows, self.stats, 1.0 / N)
 
     # ------------------------------------------------------------------------------------------------ backward
     def _ready(self, *names: str) -> None:
@@ -479,8 +538,10 @@ class ResNet50Engine:
         mode 3: BN without ReLU (downsample branch): dz = g1."""
         e, w = self._e, self.bnw[bn]
         if mode == 1:
-            # `out` is the 1-bit ReLU mask written by the forward pass (reduce mode 4)
-            e.bn_bwd_reduce(4, g1, g2, out, y, None, None, dz, w["sum_dz"], w["sum_dzy"])
+            # `out` is the 1-bit ReLU mask written by the forward pass (reduce mode 4).  When the next block's conv1
+            # dgrad carried the block-gradient epilogue, dz and both sums already exist (g1 is None).
+            if g1 is not None:
+                e.bn_bwd_reduce(4, g1, g2, out, y, None, None, dz, w["sum_dz"], w["sum_dzy"])
         elif mode == 2:
             if bn not in self._fused_reduce:  # otherwise the dgrad GEMM that produced g1 already accumulated the sums
                 e.bn_bwd_reduce(2, g1, None, None, y, w["scale"], w["shift"], None, w["sum_dz"], w["sum_dzy"])
@@ -509,8 +570,10 @@ class ResNet50Engine:
         """dgrad on the compute stream; wgrad either in line or on the side stream once dgrad has been issued."""
         if not self.overlap_wgrad:
             self._wg[full].run()
-            self._ready(full + ".weight")
             self._dg[full].run()
+            # only after every reader of this layer's weights has been enqueued: with fused_update the bucket kernel
+            # launched from the hook rewrites them
+            self._ready(full + ".weight")
             return
         self._dg[full].run()
         ev = torch.cuda.Event()
@@ -526,15 +589,14 @@ class ResNet50Engine:
     def backward(self) -> None:
         """dlogits -> every parameter gradient (fp32, written into the flat gradient buffer)."""
         e, N, A = self._e, self.batch, self.act
-        self.grads.zero_()  # wgrad accumulates with atomics
+        e.zero_(self.grads)  # wgrad accumulates with atomics
         if self.fuse_bn_coeffs:
-            self._bn_bwd_sums.zero_()  # sum(dz), sum(dz*y) of every layer; nobody zeroes them after use on the fused path
-        # classifier head
-        dl16 = self.dlogits.to(torch.bfloat16)
-        torch.matmul(self.dlogits.t(), self.pooled.float(), out=self.g("fc.weight"))
-        torch.sum(self.dlogits, dim=0, out=self.g("fc.bias"))
+            e.zero_(self._bn_bwd_sums)  # sum(dz), sum(dz*y) of every layer; nobody zeroes them after use on the fused path
+        # classifier head: wgrad + dgrad on the tcgen05 GEMMs, bias gradient = column sums of dlogits
+        self._fc_wg.run()
+        e.fc_bias_grad(self.dlogits16, self.g("fc.bias"))
+        self._fc_dg.run()
         self._ready("fc.weight", "fc.bias")
-        torch.matmul(dl16, self.w16v("fc.weight"), out=self.dpooled)
         drop = self.dropout
         gshape = self.feat.shape
         g1 = self._scr["da"][:self.feat.numel()].view(gshape)
@@ -550,7 +612,11 @@ class ResNet50Engine:
             y3 = A[n + ".y3"]
             dy3 = self._dy_buf("conv3", y3.shape)
             dz = self._scr[dz_keys[bi % 2]][:y3.numel()].view(y3.shape)
-            self._bn_bwd(n + ".bn3", 1, g1, g2, A[n + ".mask"], y3, dy3, dz, cnt_out)
+            if (n + ".bn3") in self._block_fused:
+                # dz and the bn3 sums were produced by the epilogue of the next block's conv1 dgrad
+                self._bn_bwd(n + ".bn3", 1, None, None, A[n + ".mask"], y3, dy3, dz, cnt_out)
+            else:
+                self._bn_bwd(n + ".bn3", 1, g1, g2, A[n + ".mask"], y3, dy3, dz, cnt_out)
             self._conv_bwd(n + ".conv3", "conv3")  # dgrad -> da (a2-shaped)
             da2 = self._scr["da"][:A[n + ".a2"].numel()].view(A[n + ".a2"].shape)
             y2 = A[n + ".y2"]
@@ -561,23 +627,36 @@ class ResNet50Engine:
             da1 = self._scr["da"][:a1.numel()].view(a1.shape)
             dy1 = self._dy_buf("conv1", y1.shape)
             self._bn_bwd(n + ".bn1", 2, da1, None, None, y1, dy1, None, cnt_in)
-            self._conv_bwd(n + ".conv1", "conv1")  # dgrad -> da (x_in-shaped): main-path gradient of the block input
-            g1 = self._scr["da"][:x_in.numel()].view(x_in.shape)
             if b.downsample:
-                # the downsample branch receives the same masked gradient dz; its BN has no ReLU
+                # the downsample branch receives the same masked gradient dz; its BN has no ReLU.  It runs BEFORE the
+                # conv1 dgrad, whose epilogue may consume its output as the skip gradient of the previous block.
                 yd = A[n + ".yd"]
                 dyd = self._dy_buf("downsample.0", yd.shape)
                 self._bn_bwd(n + ".downsample.1", 3, dz, None, None, yd, dyd, None, cnt_out)
-                self._conv_bwd(n + ".downsample.0", "downsample.0")  # dgrad -> dds (x_in-shaped)
-                g2 = self._scr["dds"][:x_in.numel()].view(x_in.shape)
+                self._conv_bwd(n + ".downsample.0", "downsample.0")  # dgrad -> dds (x_in-shaped, or compact)
+                g2 = self._dg[n + ".downsample.0"].dx
             else:
                 g2 = dz
-        # stem
-        da0 = self._dy_buf("conv3", self.y0.shape)  # reuses the (by now idle) "dy" scratch
-        e.maxpool_bwd(self.pool_idx, g1, g2, da0)
+            # dgrad -> main-path gradient of the block input, or (fused) the previous block's complete dz
+            self._conv_bwd(n + ".conv1", "conv1")
+            g1 = self._dg[n + ".conv1"].dx
+        # stem: g1 (main path of layer1.0) + g2 (its projection shortcut) flow through max-pool, ReLU and bn1
         dy0 = self._scr["dzA"][:self.y0.numel()].view(self.y0.shape)
         cnt0 = N * self.y0.shape[1] * self.y0.shape[2]
-        self._bn_bwd("bn1", 2, da0, None, None, self.y0, dy0, None, cnt0)
+        w0 = self.bnw["bn1"]
+        if self.fuse_stem_bwd and not self.fuse_bn_coeffs:
+            # max-pool backward + BN(+ReLU) backward without materialising the 112x112 pooled gradient
+            e.stem_pool_bn_bwd(0, self.pool_idx, g1, g2, self.y0, w0["scale"], w0["shift"], None, None, None, None,
+                               w0["sum_dz"], w0["sum_dzy"])
+            e.bn_bwd_coeffs(w0["sum_dz"], w0["sum_dzy"], self.p("bn1.weight"), w0["mean"], w0["invstd"], float(cnt0),
+                            self.g("bn1.weight"), self.g("bn1.bias"), w0["cA"], w0["cB"], w0["cC"])
+            e.stem_pool_bn_bwd(1, self.pool_idx, g1, g2, self.y0, w0["scale"], w0["shift"], w0["cA"], w0["cB"],
+                               w0["cC"], dy0, w0["sum_dz"], w0["sum_dzy"])
+            self._ready("bn1.weight", "bn1.bias")
+        else:
+            da0 = self._dy_buf("conv3", self.y0.shape)  # reuses the (by now idle) "dy" scratch
+            e.maxpool_bwd(self.pool_idx, g1, g2, da0)
+            self._bn_bwd("bn1", 2, da0, None, None, self.y0, dy0, None, cnt0)
         if self.native_stem:
             self._stem_wg.run()
         else:
@@ -607,6 +686,8 @@ class ResNet50Engine:
             if s.kind == "conv":
                 k = int(round(math.sqrt(s.shape[0])))
                 v = C.weight_from_kernel_layout(v, k, k)
+            elif s.kind == "fc_w":
+                v = v[:self.num_classes].contiguous()  # drop the zero padding rows
             sd[s.name] = v.cpu()
         for n in self.bn_names:
             sd[n + ".running_mean"] = self.running_mean[n].detach().clone().cpu()
@@ -618,6 +699,10 @@ class ResNet50Engine:
             v = sd[s.name].to(self.device, torch.float32)
             if s.kind == "conv":
                 v = C.weight_to_kernel_layout(v)
+            if s.kind == "fc_w":
+                self.p(s.name).zero_()
+                self.p(s.name)[:self.num_classes].copy_(v)
+                continue
             self.p(s.name).copy_(v)
         for n in self.bn_names:
             if n + ".running_mean" in sd:
@@ -626,7 +711,7 @@ class ResNet50Engine:
         self.sync_weights()
 
     def num_parameters(self) -> int:
-        return sum(s.numel for s in self.param_specs)
+        return sum(s.numel for s in self.param_specs) - (self.classes_padded - self.num_classes) * 2048
 
 
 class EngineTrainStep:

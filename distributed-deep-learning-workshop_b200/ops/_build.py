@@ -33,7 +33,7 @@ CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC"]
 # name -> sources (relative to csrc/)
 EXTENSIONS: Dict[str, List[str]] = {
     "_b200_conv": ["conv_igemm.cu", "conv_wgrad.cu", "stem.cu", "umma_probe.cu", "tma_probe.cu", "conv_bind.cpp"],
-    "_b200_ops": ["elementwise.cu", "optim.cu", "ops_bind.cpp"],
+    "_b200_ops": ["elementwise.cu", "head_stem.cu", "optim.cu", "ops_bind.cpp"],
     "_b200_comm": ["allreduce.cu", "comm_bind.cpp"],
     "_b200_loader": ["ring_loader.cpp"],
 }

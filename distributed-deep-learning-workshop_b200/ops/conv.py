@@ -152,15 +152,42 @@ class ConvDgrad:
     ``w_master`` is the fp32 (or bf16) filter ``[R*S, Cout, Cin]``; the transposed/rotated bf16 copies the kernel
     needs are (re)built by :meth:`refresh_weights` (cheap: filters are tiny next to activations)."""
 
+    @staticmethod
+    def part_taps(R: int, S: int, stride: int, pad: int) -> List[List[int]]:
+        """Filter-tap index lists of the GEMMs a dgrad is made of, in plan order: one list with every tap for stride 1,
+        one list per non-empty output-parity class for stride 2.  (Lets an owner lay all weight copies out in one buffer.)"""
+        if stride == 1:
+            return [[r * S + s for r in range(R) for s in range(S)]]
+        parts = []
+        for ph in range(2):
+            for pw in range(2):
+                idx = [r * S + s for r in range(R) for s in range(S) if (r - pad) % 2 == ph and (s - pad) % 2 == pw]
+                if idx:
+                    parts.append(idx)
+        return parts
+
     def __init__(self, dy: torch.Tensor, w_master: torch.Tensor, dx: torch.Tensor, R: int, S: int, stride: int = 1,
-                 pad: int = 0, max_ctas: int = 0, wbuf: Optional[torch.Tensor] = None, bwd_stats=None):
+                 pad: int = 0, max_ctas: int = 0, wbuf: Optional[torch.Tensor] = None, bwd_stats=None,
+                 block_grad=None, wbufs: Optional[List[torch.Tensor]] = None):
         """``bwd_stats=(y, scale, shift, sum_dz, sum_dzy)`` (stride 1 only) fuses the BatchNorm-backward reduction of
-        the activation this gradient belongs to into the GEMM epilogue: dz = dx * [y*scale+shift > 0]."""
+        the activation this gradient belongs to into the GEMM epilogue: dz = dx * [y*scale+shift > 0].
+
+        ``block_grad=(skip_grad, relu_mask, y3, sum_dz, sum_dzy)`` (dense 1x1 stride-1 only): ``dx`` receives
+        dz = (conv_transpose(dy, w) + skip_grad) * relu_mask - the complete masked gradient of the previous residual
+        block's output - and sum(dz), sum(dz * y3) of that block's last BatchNorm are accumulated in the same epilogue.
+        ``skip_grad`` has dx's grid, or its stride-2 sub-grid (compact gradient of a strided 1x1 projection)."""
         ext = _build.load("_b200_conv")
         self.R, self.S, self.stride, self.pad = R, S, stride, pad
         self.fused_bwd_stats = bwd_stats is not None and stride == 1
+        self.block_grad = block_grad is not None
+        if block_grad is not None and (stride != 1 or bwd_stats is not None):
+            raise ValueError("block_grad: stride-1 convs only, and not together with bwd_stats")
         self.w_master = w_master
-        self.external_wbuf = wbuf is not None  # owner refreshes it (e.g. one batched kernel for all layers)
+        if wbufs is not None:
+            assert wbuf is None and len(wbufs) == len(self.part_taps(R, S, stride, pad))
+            if stride == 1:
+                wbuf = wbufs[0]
+        self.external_wbuf = wbuf is not None or wbufs is not None  # owner refreshes them (one batched kernel for all layers)
         taps_total, cout, cin = w_master.shape
         assert taps_total == R * S
         self.parts = []  # (plan, weight buffer, tap index list)
@@ -184,7 +211,13 @@ class ConvDgrad:
             flat = (R == 1 and S == 1 and pad == 0 and dy.is_contiguous() and dx.is_contiguous())
             box = (0, 0, 0) if flat else (halo_box(dx.shape[1], dx.shape[2], cout, cin, R, S, 1, R - 1 - pad)
                                           or pick_box(N, dx.shape[1], dx.shape[2]))
-            if self.fused_bwd_stats:
+            if block_grad is not None:
+                if not flat:
+                    raise ValueError("block_grad needs a dense 1x1 stride-1 convolution")
+                skip, mask, y3, s_dz, s_dzy = block_grad
+                plan = ext.ConvPlan([dy], wbuf, dx, tm, dw, dh, 0, 0, 0, s_dz, s_dzy, max_ctas, y3, None, None,
+                                    skip, mask)
+            elif self.fused_bwd_stats:
                 y, sc, sh, s_dz, s_dzy = bwd_stats
                 plan = ext.ConvPlan([dy], wbuf, dx, tm, dw, dh, box[0], box[1], box[2], s_dz, s_dzy, max_ctas, y, sc, sh)
             else:
@@ -208,8 +241,11 @@ class ConvDgrad:
                     if not idx:
                         self.needs_zero = True
                         continue
-                    wbuf = torch.empty(len(idx) * cin, cout, dtype=torch.bfloat16, device=dy.device)
-                    self._idx_dev[tuple(idx)] = torch.tensor(idx, device=dy.device, dtype=torch.long)
+                    if wbufs is not None:
+                        wbuf = wbufs[len(self.parts)].view(len(idx) * cin, cout)
+                    else:
+                        wbuf = torch.empty(len(idx) * cin, cout, dtype=torch.bfloat16, device=dy.device)
+                        self._idx_dev[tuple(idx)] = torch.tensor(idx, device=dy.device, dtype=torch.long)
                     box = pick_box(N, out_view.shape[1], out_view.shape[2])
                     plan = ext.ConvPlan([dy], wbuf, out_view, tm, dw, dh, box[0], box[1], box[2], None, None, max_ctas)
                     _plans.add(plan)
@@ -232,7 +268,7 @@ class ConvDgrad:
 
     def run(self) -> None:
         if self.needs_zero:
-            self.dx.zero_()
+            _build.load("_b200_ops").zero_(self.dx)  # memset node, not a kernel
         for plan, _, _ in self.parts:
             plan.run()
 

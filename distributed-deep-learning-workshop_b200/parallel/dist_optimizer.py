@@ -55,6 +55,7 @@ class DistributedOptimizer:
         self._comm = None
         self._sym = None
         self._comm_stream = None
+        self._oneshot_tmp = None
         self._launched = 0
         self.allreduce_launches = 0
         self.timeline = None  # utils.Timeline: per-bucket all-reduce spans on the comm stream
@@ -186,7 +187,15 @@ class DistributedOptimizer:
                 elif self.algo == "p2p":
                     self._comm.twoshot_p2p(b.lo, n, "f32", scale, self.comm_blocks)
                 else:
-                    self._comm.oneshot(b.lo, n, "f32", self.grads[b.lo:b.hi], scale, self.comm_blocks)
+                    # one-shot reads every peer's slice and has no barrier between its load and store phases, so it
+                    # must NOT write into the symmetric source buffer: reduce into a private tensor, copy back after
+                    # the kernel's end barrier (same stream)
+                    if self._oneshot_tmp is None or self._oneshot_tmp.numel() < n:
+                        self._oneshot_tmp = torch.empty(max(n, max(bb.total for bb in self.buckets)),
+                                                        device=self.grads.device, dtype=torch.float32)
+                    tmp = self._oneshot_tmp[:n]
+                    self._comm.oneshot(b.lo, n, "f32", tmp, scale, self.comm_blocks)
+                    self.grads[b.lo:b.hi].copy_(tmp)
         elif self.algo == "nccl":
             # baseline: library collective + separate elementwise kernel (what Horovod does)
             cs = self._comm_stream

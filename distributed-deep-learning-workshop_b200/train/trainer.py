@@ -37,12 +37,12 @@ class _EngineBackend:
         self.eval_step = EngineEvalStep(engine, use_graph=use_graph)
         self.batch = engine.batch
         self._pending = deque()
-        self._pinned = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(4)]
-        self._i = 0
+        # one pinned result slot per IN-FLIGHT step: a slot goes back to the free list only after its value has been
+        # read, so queueing many batches before popping (evaluate) can never overwrite an unread result
+        self._free = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(4)]
 
     def _enqueue_result(self) -> None:
-        buf = self._pinned[self._i % len(self._pinned)]
-        self._i += 1
+        buf = self._free.pop() if self._free else torch.zeros(2, dtype=torch.float32).pin_memory()
         buf.copy_(self.engine.stats, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -54,6 +54,7 @@ class _EngineBackend:
             ev, buf = self._pending.popleft()
             ev.synchronize()
             out.append((float(buf[0]) / self.batch, float(buf[1]) / self.batch))
+            self._free.append(buf)
         return out
 
     def train_batch(self, x, y) -> None:
@@ -284,6 +285,10 @@ class Trainer:
                     break  # empty dataset
             self.backend.eval_batch(xb, yb)
             k += 1
+            for l, a in self.backend.pop_results(keep=2):  # bounded queue; lag keeps H2D / compute overlapped
+                tot_loss += l
+                tot_acc += a
+                n += 1
         for l, a in self.backend.pop_results(keep=0):
             tot_loss += l
             tot_acc += a

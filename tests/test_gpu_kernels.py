@@ -56,6 +56,32 @@ def test_stem_conv_tcgen05(checks):
     assert checks.case_stem()
 
 
+def test_block_gradient_epilogue(checks):
+    """conv1 dgrad with the fused block-gradient merge (skip add + ReLU bitmask + bn3 reduction), dense and compact skip,
+    partial last tile, and the benchmark shape at batch 256."""
+    assert checks.case_block_grad()
+
+
+def test_classifier_head_on_tcgen05(checks):
+    """FC forward / dgrad / wgrad on the implicit-GEMM kernels + softmax_ce_head + fc_bias_grad vs torch fp32."""
+    assert checks.case_head()
+
+
+def test_stem_tail_backward_fused(checks):
+    """max-pool backward fused with the stem BN backward == the three-kernel path, bit for bit."""
+    assert checks.case_stem_bwd()
+
+
+def test_conv_numerics_at_benchmark_batch(checks):
+    """forward (+statistics) / dgrad / wgrad vs fp32 at the batch-256 layer shapes the benchmark runs."""
+    assert checks.case_big_numerics()
+
+
+def test_resnet50_engine_unfused_block_gradient_matches_torchvision(checks):
+    """A/B path: block-gradient merge as separate reduce passes (fuse_block_grad=False)."""
+    assert checks.case_engine(quick=True, fuse_block_grad=False)
+
+
 def test_resnet50_engine_matches_torchvision(checks):
     assert checks.case_engine()
 
