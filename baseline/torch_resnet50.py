@@ -68,7 +68,8 @@ def main(argv=None):
     off = 0
     spans = {}
     for p in order:
-        p.grad = flat[off:off + p.numel()].view(p.shape)
+        # same strides as the (channels_last) parameter: the fused / foreach optimizers require matching layouts
+        p.grad = flat[off:off + p.numel()].as_strided(p.shape, p.stride())
         spans[p] = (off, off + p.numel())
         off += p.numel()
     # Horovod-style fusion buckets = contiguous slices of the flat buffer
@@ -128,6 +129,19 @@ def main(argv=None):
             torch.cuda.current_stream().wait_stream(comm)
         opt.step()
         return loss
+
+    # probe step: if the fused optimizer rejects the tensor layout on this torch build, fall back to the foreach one
+    try:
+        step()
+        torch.cuda.synchronize()
+    except RuntimeError as ex:
+        if opt_kind != "fused":
+            raise
+        print(f"# fused SGD unavailable ({str(ex)[:120]}); using foreach", file=sys.stderr)
+        opt = torch.optim.SGD(params, lr=0.1 * world, momentum=0.9, weight_decay=1e-4, foreach=True)
+        opt_kind = "foreach"
+        step()
+        torch.cuda.synchronize()
 
     if args.graph:
         s = torch.cuda.Stream()

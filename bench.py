@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--no-baseline", action="store_true", help="skip the same-lease torch+cuDNN+NCCL baseline child")
     ap.add_argument("--baseline-timeout", type=int, default=420)
     ap.add_argument("--no-block-grad", action="store_true", help="A/B: block-gradient merge as separate reduce passes")
-    ap.add_argument("--no-stem-bwd-fuse", action="store_true", help="A/B: unfused max-pool / stem-BN backward")
+    ap.add_argument("--stem-bwd-fuse", action="store_true", help="A/B (opt-in): max-pool backward fused with the stem-BN backward")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -223,7 +223,7 @@ def main():
                             overlap_wgrad=not args.no_overlap_wgrad, wgrad_smem_budget=args.wgrad_smem,
                             fuse_bwd_reduce=not args.no_fuse_bwd_reduce, fuse_bn_coeffs=args.fuse_bn_coeffs,
                             fuse_block_grad=False if args.no_block_grad else None,
-                            fuse_stem_bwd=False if args.no_stem_bwd_fuse else None)
+                            fuse_stem_bwd=True if args.stem_bwd_fuse else None)
     lr = 0.1 * world  # LR x world size (reference P1/03:301)
     base_opt = optim.SGD(lr, momentum=0.9, weight_decay=1e-4) if args.optimizer == "sgd" else optim.Adam(1e-3 * world)
     opt = (dist.DistributedOptimizer(base_opt, bucket_mb=args.bucket_mb, algo=args.algo, fused_update=args.fused_update)

@@ -141,6 +141,70 @@ def main():
                                  if isinstance(v, dict) and "us" in v)
                 print(f"{name} {nbytes:>11d} B  {parts}  best/roofline900={res.get('best_fraction_of_roofline_900', 0):.2f} "
                       f"vs_nccl={res.get('speedup_vs_nccl', 0):.2f}x", flush=True)
+    # ---- broadcast kernel (K2): hvd.broadcast on CUDA tensors runs csrc/allreduce.cu broadcast_kernel through a symmetric
+    # staging buffer; compare with the value the root holds, for every root, several dtypes / sizes (incl. > 1 staging chunk)
+    bc_sizes = [(torch.float32, 300_000), (torch.bfloat16, 1_000_001), (torch.int64, 4097)]
+    if not args.quick:
+        bc_sizes.append((torch.float32, 20_000_000))  # 80 MB > the 64 MB staging buffer
+    for root in range(min(world, 3)):
+        for dt, n in bc_sizes:
+            gen = torch.Generator(device=dev).manual_seed(7 + rank * 31 + n)
+            mine = (torch.randn(n, device=dev, generator=gen) * 100).to(dt)
+            want = mine.clone()
+            dist.broadcast(want, root)          # library result
+            got = mine.clone()
+            hvd.broadcast(got, root)            # our kernel
+            torch.cuda.synchronize()
+            same = bool(torch.equal(got, want))
+            ok_all &= same
+            if rank == 0:
+                print(f"broadcast root={root} {str(dt).split('.')[-1]} n={n}: {'ok' if same else 'FAIL'}", flush=True)
+    big = torch.randn(64 << 20, device=dev) if not args.quick else torch.randn(4 << 20, device=dev)
+    t_k = time_op(lambda: hvd.broadcast(big, 0), 5, warmup=2)
+    t_n = time_op(lambda: dist.broadcast(big, 0), 5, warmup=2)
+    if rank == 0:
+        print(f"broadcast {big.numel() * 4 / 2**20:.0f} MiB: kernel (staged) {t_k * 1e3:.2f} ms  NCCL {t_n * 1e3:.2f} ms", flush=True)
+    # ---- CTA-count sweep at the gradient-bucket size (what DistributedOptimizer.comm_blocks should be)
+    nb = min(16 << 20, max_bytes)
+    view32 = buf.tensor.view(torch.float32)
+    blk = {}
+    for blocks in (8, 16, 32, 64):
+        for algo in (("p2p", "nvls") if buf.has_multicast else ("p2p",)):
+            fn = (lambda: comm.twoshot_p2p(0, nb // 4, "f32", 1.0 / world, blocks)) if algo == "p2p" else \
+                 (lambda: comm.twoshot_nvls(0, nb // 4, "f32", 1.0 / world, blocks))
+            blk[f"{algo}_{blocks}"] = time_op(fn, 20) * 1e6
+    if rank == 0:
+        print("bucket-size (16 MB f32) CTA sweep, us: " + " ".join(f"{k}={v:.1f}" for k, v in blk.items()), flush=True)
+    rows.append({"cta_sweep_16MB_f32_us": blk, "world": world})
+    # ---- DistributedOptimizer end to end on every algorithm (incl. one-shot writing back into the symmetric buffer)
+    from b200ddl import optim
+    for algo in ("auto", "p2p", "oneshot") + (("nvls",) if buf.has_multicast else ()):
+        nparam = 3_000_000
+        params = torch.zeros(nparam, device=dev)
+        opt = hvd.DistributedOptimizer(optim.SGD(0.1), bucket_mb=4.0, algo=algo)
+        grads = opt.allocate_grads(nparam, dev)
+        ranges = [(i, min(i + 250_000, nparam)) for i in range(0, nparam, 250_000)]
+        opt.attach(params, ranges, None, grads)
+        gen = torch.Generator(device=dev).manual_seed(99 + rank)
+        local = torch.randn(nparam, device=dev, generator=gen) * (rank + 1)
+        ref = local.clone()
+        dist.all_reduce(ref)
+        ref /= world
+        grads.copy_(local)
+        torch.cuda.synchronize()
+        dist.barrier()
+        opt.start_backward()
+        for a, b in ranges:
+            opt.on_grads_ready(a, b)
+        opt.finish_backward()
+        torch.cuda.synchronize()
+        err = float((grads - ref).abs().max() / ref.abs().max())
+        same = checksum_across_ranks(grads)
+        good = err <= 1e-5 and same
+        ok_all &= good
+        if rank == 0:
+            print(f"DistributedOptimizer algo={algo} ({opt.algo}) buckets={len(opt.buckets)} tail={opt.buckets[-1].total}: "
+                  f"err={err:.2e} identical={same} {'ok' if good else 'FAIL'}", flush=True)
     if rank == 0:
         os.makedirs(args.out, exist_ok=True)
         with open(os.path.join(args.out, f"allreduce_sweep_w{world}.json"), "w") as f:

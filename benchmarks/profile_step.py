@@ -11,7 +11,8 @@ from b200ddl import optim
 from b200ddl.models.resnet_engine import EngineTrainStep, ResNet50Engine
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-eng = ResNet50Engine(batch=N, num_classes=1000)
+inline = len(sys.argv) > 2 and sys.argv[2] == "inline"   # weight-gradient GEMMs in line: clean per-kernel durations
+eng = ResNet50Engine(batch=N, num_classes=1000, overlap_wgrad=not inline)
 step = EngineTrainStep(eng, optim.SGD(0.1, momentum=0.9), use_graph=False)
 x = torch.randint(0, 256, (N, 224, 224, 3), device="cuda", dtype=torch.uint8)
 y = torch.randint(0, 1000, (N,), device="cuda")

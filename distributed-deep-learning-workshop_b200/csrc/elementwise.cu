@@ -835,32 +835,51 @@ void weight_prep(const float* w, void* wf, void* wd, int taps, int cout, int cin
 }
 
 
-// All conv layers in one launch: table rows = (src offset in the flat fp32 master, dst offset in the flat bf16
-// dgrad buffer, taps, cout, cin, first flat element index of the layer); binary search over <= 128 rows in smem.
-__global__ void weight_prep_batched_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ wd,
-                                           const int64_t* __restrict__ table, int layers, int64_t total) {
+// All filters in one launch: table rows = (src offset in the flat fp32 master, dst offset in the flat bf16 dgrad buffer,
+// taps, cout, cin, first TILE index of the row).  Every tap matrix [cout, cin] fp32 is transposed to [cin, cout] bf16
+// through 64x32 shared-memory tiles: 128-byte coalesced reads (32 floats of one co row) and 128-byte coalesced writes
+// (64 bf16 of one ci row).  The element-wise version it replaces wrote 2-byte values at a cout-element stride and spent
+// ~0.29 ms per step on 141 MB of traffic (~20 us at HBM speed).  cout % 64 == 0 and cin % 32 == 0 (host-checked).
+__global__ void __launch_bounds__(256)
+weight_prep_batched_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ wd,
+                           const int64_t* __restrict__ table, int layers, int64_t total_tiles) {
   __shared__ int64_t t[128 * 6];
+  __shared__ float tile[64][33];
   for (int i = threadIdx.x; i < layers * 6; i += blockDim.x) t[i] = table[i];
   __syncthreads();
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int64_t tid = blockIdx.x; tid < total_tiles; tid += gridDim.x) {
     int lo = 0, hi = layers - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (t[mid * 6 + 5] <= i) lo = mid; else hi = mid - 1;
+      if (t[mid * 6 + 5] <= tid) lo = mid; else hi = mid - 1;
     }
     const int64_t* L = t + lo * 6;
-    const int64_t j = i - L[5];
-    const int cin = (int)L[4], cout = (int)L[3];
-    const int ci = (int)(j % cin);
-    const int co = (int)((j / cin) % cout);
-    const int tp = (int)(j / ((int64_t)cin * cout));
-    wd[L[1] + ((int64_t)tp * cin + ci) * cout + co] = __float2bfloat16(params[L[0] + j]);
+    const int cout = (int)L[3], cin = (int)L[4];
+    const int tiles_ci = cin >> 5, tiles_co = cout >> 6;
+    int64_t j = tid - L[5];
+    const int tci = (int)(j % tiles_ci);
+    j /= tiles_ci;
+    const int tco = (int)(j % tiles_co);
+    const int tp = (int)(j / tiles_co);
+    const float* src = params + L[0] + ((int64_t)tp * cout + tco * 64) * cin + tci * 32;
+    __nv_bfloat16* dst = wd + L[1] + ((int64_t)tp * cin + tci * 32) * cout + tco * 64;
+    __syncthreads();  // previous tile fully written out
+#pragma unroll
+    for (int r = ty; r < 64; r += 8) tile[r][tx] = src[(int64_t)r * cin + tx];
+    __syncthreads();
+#pragma unroll
+    for (int c = ty; c < 32; c += 8) {
+      const __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * tx][c], tile[2 * tx + 1][c]);
+      *reinterpret_cast<__nv_bfloat162*>(dst + (int64_t)c * cout + 2 * tx) = v;
+    }
   }
 }
-void weight_prep_batched(const float* params, void* wd, const int64_t* table, int layers, int64_t total,
+void weight_prep_batched(const float* params, void* wd, const int64_t* table, int layers, int64_t total_tiles,
                          cudaStream_t s) {
-  weight_prep_batched_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, s>>>(params, (__nv_bfloat16*)wd, table, layers,
-                                                                          total);
+  int64_t grid = total_tiles < 148 * 16 ? total_tiles : 148 * 16;
+  if (grid < 1) grid = 1;
+  weight_prep_batched_kernel<<<(int)grid, 256, 0, s>>>(params, (__nv_bfloat16*)wd, table, layers, total_tiles);
 }
 
 }  // namespace b200

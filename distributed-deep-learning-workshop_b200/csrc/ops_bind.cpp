@@ -294,7 +294,7 @@ void weight_prep(Tensor w, OptT wf, OptT wd, int64_t taps, int64_t cout, int64_t
                     wd.has_value() ? wd->data_ptr() : nullptr, (int)taps, (int)cout, (int)cin, cur());
   after();
 }
-// table: int64 [layers, 6] on the device = (src_off, dst_off, taps, cout, cin, first_flat_index)
+// table: int64 [layers, 6] on the device = (src_off, dst_off, taps, cout, cin, first_tile_index); a tile = 64 co x 32 ci
 void weight_prep_batched(Tensor params, Tensor wd, Tensor table, int64_t total) {
   chk(params, at::kFloat, "params");
   chk(wd, at::kBFloat16, "wd");

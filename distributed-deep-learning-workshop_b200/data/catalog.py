@@ -134,6 +134,17 @@ class Catalog:
         t = pa.concat_tables(parts) if parts else pa.table({})
         return Table(t, max(1, len(parts)), self)
 
+    def scan(self, name: str):
+        """The table as a lazily read `ScanTable` (one fragment per parquet row group): nothing is loaded here; readers
+        such as `pyfunc.spark_udf` workers or `loader.make_converter` open the row groups they own."""
+        from .scan import scan_parquet_files
+
+        tdir = self._table_dir(name)
+        commit = self._latest_commit(tdir)
+        if commit is None:
+            raise FileNotFoundError(f"table {name} not found")
+        return scan_parquet_files([os.path.join(tdir, fn) for fn in commit["files"]], self)
+
     def table_history(self, name: str) -> List[dict]:
         log = os.path.join(self._table_dir(name), "_log")
         out = []

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import concurrent.futures as cf
 import math
+import os
 import threading
 import time
 import traceback
@@ -180,19 +181,40 @@ class Trials:
 
 
 class ParallelTrials(Trials):
-    """`SparkTrials(parallelism=k)`: k trials in flight.  `device_for(tid)` round-robins the visible GPUs so a
-    single-GPU objective can pin itself (`torch.cuda.set_device(ParallelTrials.device_for(...))`)."""
+    """`SparkTrials(parallelism=k)`: k trials in flight (reference P2/01:226-238).
 
-    def __init__(self, parallelism: int = 4, timeout: Optional[float] = None):
+    ``executor='process'`` (the default on a GPU box, ``'auto'``): every slot is a persistent worker PROCESS pinned to
+    GPU ``slot % device_count`` - its own CUDA context, its own CUDA-graph captures, its own extension state - that
+    evaluates one trial at a time, like a Spark executor running one Hyperopt task; the objective travels by value
+    (cloudpickle) once per worker.  ``executor='thread'`` evaluates in threads of the driver process (CPU objectives).
+    `device_for(tid)` names the GPU a trial should use (inside a process worker: the worker's own device)."""
+
+    def __init__(self, parallelism: int = 4, timeout: Optional[float] = None, executor: str = "auto"):
         super().__init__()
         self.parallelism = max(1, int(parallelism))
         self.timeout = timeout
+        if executor not in ("auto", "thread", "process"):
+            raise ValueError("executor must be 'auto', 'thread' or 'process'")
+        self.executor = executor
+
+    def uses_processes(self) -> bool:
+        if self.executor == "auto":
+            try:
+                import torch
+
+                return torch.cuda.is_available() and os.environ.get("B200DDL_FORCE_CPU", "0") != "1"
+            except Exception:
+                return False
+        return self.executor == "process"
 
     @staticmethod
     def device_for(tid: int) -> int:
         import torch
 
         n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+        slot = os.environ.get("B200DDL_TRIAL_SLOT")
+        if slot is not None:
+            return int(slot) % n if n else -1
         return tid % n if n else -1
 
 
@@ -314,6 +336,108 @@ tpe = _AlgoModule(_TPE)
 rand = _AlgoModule(_Rand)
 
 
+# ------------------------------------------------------------------------------------------------ process workers
+def _trial_worker(slot: int, conn) -> None:
+    """Persistent trial process: pinned to one GPU, receives the objective once, then (params, tracking context) per trial."""
+    os.environ["B200DDL_TRIAL_SLOT"] = str(slot)
+    try:
+        import torch
+
+        if torch.cuda.is_available() and os.environ.get("B200DDL_FORCE_CPU", "0") != "1":
+            torch.cuda.set_device(slot % torch.cuda.device_count())
+    except Exception:
+        pass
+    import cloudpickle
+
+    from .. import tracking
+
+    fn = None
+    while True:
+        try:
+            msg = conn.recv()
+        except EOFError:
+            return
+        if msg is None:
+            return
+        if msg[0] == "fn":
+            fn = cloudpickle.loads(msg[1])
+            continue
+        _, params, uri, run_id, trial = msg
+        opened = False
+        try:
+            if uri:
+                tracking.set_tracking_uri(uri)
+            if run_id is not None:
+                tracking.start_run(run_id=run_id)  # re-open the trial's child run: the objective's logging lands there
+                opened = True
+            _trial_ctx.trial = trial
+            res = fn(params)
+            conn.send(("ok", cloudpickle.dumps(res)))
+        except BaseException as e:  # the driver decides (catch_eval_exceptions) what a failed objective means
+            conn.send(("err", repr(e), traceback.format_exc()))
+        finally:
+            _trial_ctx.trial = None
+            if opened:
+                try:
+                    tracking._stack().pop()  # detach without ending: the driver ends the run
+                except Exception:
+                    pass
+
+
+class _TrialProcessPool:
+    def __init__(self, n: int, fn: Callable):
+        import multiprocessing as mp
+        import queue
+
+        import cloudpickle
+
+        ctx = mp.get_context("spawn")
+        blob = cloudpickle.dumps(fn)
+        self.procs, self.conns = [], []
+        self.idle: "queue.Queue[int]" = queue.Queue()
+        for i in range(n):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_trial_worker, args=(i, b), daemon=True)
+            p.start()
+            b.close()
+            a.send(("fn", blob))
+            self.procs.append(p)
+            self.conns.append(a)
+            self.idle.put(i)
+
+    def call(self, params, trial: dict):
+        import cloudpickle
+
+        from .. import tracking
+
+        i = self.idle.get()
+        try:
+            active = tracking.active_run()
+            light = {"tid": trial["tid"], "misc": trial["misc"]}
+            self.conns[i].send(("eval", params, tracking.get_tracking_uri(), active.info.run_id if active else None, light))
+            try:
+                msg = self.conns[i].recv()
+            except EOFError:
+                raise RuntimeError(f"trial worker {i} died (exit code {self.procs[i].exitcode})") from None
+            if msg[0] == "ok":
+                return cloudpickle.loads(msg[1])
+            raise RuntimeError(f"objective failed in trial worker {i}: {msg[1]}\n{msg[2]}")
+        finally:
+            self.idle.put(i)
+
+    def close(self) -> None:
+        for c in self.conns:
+            try:
+                c.send(None)
+                c.close()
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.kill()
+
+
 # ------------------------------------------------------------------------------------------------ fmin
 def _run_trial(fn: Callable, space, trial: dict, catch: bool) -> None:
     from .. import tracking
@@ -403,9 +527,17 @@ def fmin(fn: Callable[[Any], Any], space, algo=None, max_evals: int = 10, trials
     parent_id = active.info.run_id if active is not None else None
     n_par = getattr(trials, "parallelism", 1)
 
+    pool = None
+    call = fn
+    if n_par > 1 and hasattr(trials, "uses_processes") and trials.uses_processes():
+        pool = _TrialProcessPool(n_par, fn)
+
+        def call(params):  # runs in a driver thread; the objective itself runs in a pinned worker process
+            return pool.call(params, current_trial())
+
     def evaluate(trial):
         _trial_ctx.parent_run_id = parent_id
-        _run_trial(fn, space, trial, catch_eval_exceptions)
+        _run_trial(call, space, trial, catch_eval_exceptions)
         if verbose:
             r = trial["result"]
             print(f"[hpo] trial {trial['tid']} {r.get('status')} loss={r.get('loss')} vals={trial['misc']['vals']}")
@@ -430,6 +562,8 @@ def fmin(fn: Callable[[Any], Any], space, algo=None, max_evals: int = 10, trials
                     d.result()
                 if deadline is not None and time.time() > deadline:
                     break
+        if pool is not None:
+            pool.close()
     if not trials.completed():
         raise RuntimeError("all trials failed:\n" + "\n".join(str(t["result"].get("error")) for t in trials.trials))
     return trials.argmin if return_argmin else trials

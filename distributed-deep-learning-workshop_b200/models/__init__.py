@@ -14,7 +14,7 @@ from typing import Optional
 
 import torch
 
-from .preprocess import (IMG_CHANNELS, IMG_HEIGHT, IMG_WIDTH, decode_image, preprocess, preprocess_tensor)
+from .preprocess import (IMG_CHANNELS, IMG_HEIGHT, IMG_WIDTH, decode_batch, decode_image, preprocess, preprocess_tensor)
 
 CLASSES = ["daisy", "dandelion", "roses", "sunflowers", "tulips"]  # reference P2/03:62
 
@@ -50,5 +50,5 @@ def build_model(img_height: int = IMG_HEIGHT, img_width: int = IMG_WIDTH, img_ch
     raise ValueError(f"unknown arch {arch!r}")
 
 
-__all__ = ["build_model", "preprocess", "preprocess_tensor", "decode_image", "CLASSES", "IMG_HEIGHT", "IMG_WIDTH",
+__all__ = ["build_model", "preprocess", "preprocess_tensor", "decode_image", "decode_batch", "CLASSES", "IMG_HEIGHT", "IMG_WIDTH",
            "IMG_CHANNELS"]

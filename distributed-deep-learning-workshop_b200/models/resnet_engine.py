@@ -105,8 +105,9 @@ class ResNet50Engine:
         # the gradient merge at every residual-block boundary (main path + skip path, ReLU mask, bn3 reduction) runs in
         # the epilogue of the next block's conv1 dgrad GEMM (conv_igemm kStats = 3); B200DDL_NO_BLOCK_GRAD=1 disables
         self.fuse_block_grad = (os.environ.get("B200DDL_NO_BLOCK_GRAD") != "1") if fuse_block_grad is None else bool(fuse_block_grad)
-        # max-pool backward fused with the stem BatchNorm backward (csrc/head_stem.cu); B200DDL_NO_STEM_BWD_FUSE=1 disables
-        self.fuse_stem_bwd = (os.environ.get("B200DDL_NO_STEM_BWD_FUSE") != "1") if fuse_stem_bwd is None else bool(fuse_stem_bwd)
+        # max-pool backward fused with the stem BatchNorm backward (csrc/head_stem.cu); B200DDL_STEM_BWD_FUSE=1 enables
+        # MEASURED SLOWER in its first version (profiles/README.md r2: 1,162 vs 884 us per step at batch 256), so opt-in:
+        self.fuse_stem_bwd = (os.environ.get("B200DDL_STEM_BWD_FUSE") == "1") if fuse_stem_bwd is None else bool(fuse_stem_bwd)
         self._fused_reduce = set()
         self._block_fused = set()   # bn3 names whose reduction (and dz) come out of a fused dgrad epilogue
         self.wgrad_smem_budget = wgrad_smem_budget
@@ -227,7 +228,7 @@ class ResNet50Engine:
         """bf16 copies in layouts other than the master's: dgrad filters (one batched kernel + the few stride-2
         tap subsets) and the packed stem filter."""
         if getattr(self, "_wd_total", 0) > 0:
-            self._e.weight_prep_batched(self.params, self._wd16, self._wd_table, self._wd_total)
+            self._e.weight_prep_batched(self.params, self._wd16, self._wd_table, self._wd_tiles)
         self._refresh_stem_weight()
 
     def _refresh_stem_weight(self) -> None:
@@ -309,9 +310,10 @@ class ResNet50Engine:
         self._wd_table_rows = []
         self._wd_slices: Dict[str, List[Tuple[int, int]]] = {}   # conv name -> [(offset, numel)] per dgrad part
         wd_total = 0
+        wd_tiles = 0   # 64 (co) x 32 (ci) transpose tiles, the unit of work of weight_prep_batched
 
         def add_dgrad_weights(full: str, parts: List[List[int]]):
-            nonlocal wd_total
+            nonlocal wd_total, wd_tiles
             sp = self.spec[full + ".weight"]
             taps, cout, cin = sp.shape if len(sp.shape) == 3 else (1, sp.shape[0], sp.shape[1])
             out = []
@@ -323,8 +325,10 @@ class ResNet50Engine:
                     while j + 1 < len(idx) and idx[j + 1] == idx[j] + 1:
                         j += 1
                     n = j - i + 1
-                    self._wd_table_rows.append([sp.offset + idx[i] * cout * cin, wd_total, n, cout, cin, wd_total])
+                    assert cout % 64 == 0 and cin % 32 == 0
+                    self._wd_table_rows.append([sp.offset + idx[i] * cout * cin, wd_total, n, cout, cin, wd_tiles])
                     wd_total += n * cout * cin
+                    wd_tiles += n * (cout // 64) * (cin // 32)
                     i = j + 1
                 out.append((start, wd_total - start))
             self._wd_slices[full] = out
@@ -345,6 +349,7 @@ class ResNet50Engine:
             assert len(self._wd_table_rows) <= 128
             self._wd16 = torch.zeros(max(wd_total, 8), **bf)
             self._wd_total = wd_total
+            self._wd_tiles = wd_tiles
             self._wd_table = torch.tensor(self._wd_table_rows, device=dev, dtype=torch.int64).view(-1, 6)
 
         def wd_views(full: str) -> List[torch.Tensor]:

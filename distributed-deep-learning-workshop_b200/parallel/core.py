@@ -101,8 +101,23 @@ def allreduce(t: torch.Tensor, average: bool = True) -> torch.Tensor:
 
 
 def broadcast(t: torch.Tensor, root: int = 0) -> torch.Tensor:
-    """In-place broadcast (initial weights, K2)."""
+    """In-place broadcast (initial weights / optimizer state / BN statistics, K2).  CUDA tensors on the NCCL backend go
+    through our multicast broadcast kernel over symmetric memory (`symm.broadcast_tensor`); everything else (CPU / gloo,
+    non-contiguous or tiny tensors, `B200DDL_BROADCAST=nccl`) uses the library collective."""
     if size() > 1:
+        use_kernel = (t.is_cuda and _state["backend"] == "nccl" and t.is_contiguous() and t.numel() * t.element_size() >= 1024
+                      and os.environ.get("B200DDL_BROADCAST", "sym") != "nccl")
+        if use_kernel:
+            try:
+                from . import symm
+
+                symm.broadcast_tensor(t, root)
+                return t
+            except (RuntimeError, AttributeError, ImportError) as ex:  # no symmetric memory on this platform
+                if not _state.get("warned_bcast"):
+                    _state["warned_bcast"] = True
+                    print(f"[b200ddl] symmetric broadcast unavailable ({type(ex).__name__}: {str(ex)[:120]}); using NCCL",
+                          flush=True)
         dist.broadcast(t, root)
     return t
 

@@ -35,9 +35,16 @@ class DistributedOptimizer:
     """Wraps a fused flat optimizer; averages gradients over all ranks before every update."""
 
     def __init__(self, optimizer: FlatOptimizer, bucket_mb: float = 16.0, overlap: bool = True, algo: str = "auto",
-                 comm_blocks: int = 16, average: bool = True, fused_update: bool = False):
+                 comm_blocks: int = 16, average: bool = True, fused_update: bool = False, tail_mb: float = 1.0,
+                 nvls_min_mb: float = 32.0):
         self.opt = optimizer
         self.bucket_bytes = int(bucket_mb * 2 ** 20)
+        # The LAST bucket to complete is the only all-reduce nothing can hide (backward has ended): keep it small.  The
+        # final `tail_mb` of the gradient buffer (the layers that finish last: stem + first stage) become their own bucket.
+        self.tail_bytes = int(tail_mb * 2 ** 20)
+        # 'auto' picks the kernel PER BUCKET from the measured sweeps (profiles/): the P2P two-shot wins below ~32 MB
+        # (8 GPUs, 16 MB: 92 vs 115 us), the in-switch NVLS reduction above
+        self.nvls_min_bytes = int(nvls_min_mb * 2 ** 20)
         self.overlap = overlap
         self.algo = algo
         self.comm_blocks = comm_blocks
@@ -88,7 +95,7 @@ class DistributedOptimizer:
             self._comm = symm.make_comm(self._sym)
             self.grads = self._sym.tensor
             if self.algo == "auto":
-                self.algo = "nvls" if self._sym.has_multicast else "p2p"
+                self.algo = "auto-sym" if self._sym.has_multicast else "p2p"
             if self.algo == "nvls" and not self._sym.has_multicast:
                 raise RuntimeError("algo='nvls' requested but the symmetric buffer has no multicast mapping")
         else:
@@ -139,6 +146,18 @@ class DistributedOptimizer:
                 lo = None
         if lo is not None:
             self.buckets.append(_Bucket(lo, hi))
+        # split a small tail off the last bucket (ranges are in readiness order, so the tail completes last)
+        tail_elems = self.tail_bytes // 4
+        if tail_elems > 0 and self.buckets and spec_ranges:
+            last = self.buckets[-1]
+            cut = last.hi
+            for a, b in reversed(spec_ranges):
+                if a < last.lo or last.hi - a > tail_elems:
+                    break
+                cut = a
+            if last.lo < cut < last.hi:
+                self.buckets[-1] = _Bucket(last.lo, cut)
+                self.buckets.append(_Bucket(cut, last.hi))
         return grads
 
     # -- hot path ------------------------------------------------------------------------------------------
@@ -176,15 +195,18 @@ class DistributedOptimizer:
                 self._comm.allreduce_sgd(self._wcomm, b.lo, n, self.opt.state["momentum"],
                                          self._w16sym.mc_ptr if self._w16sym is not None else 0, scale,
                                          self.opt._hyper, self.comm_blocks)
-        elif self.algo in ("nvls", "p2p", "oneshot"):
+        elif self.algo in ("nvls", "p2p", "oneshot", "auto-sym"):
             cs = self._comm_stream
             cs.wait_stream(torch.cuda.current_stream())
-            span = (self.timeline.device_span(f"allreduce[{b.lo}:{b.hi}] {self.algo}", "comm", stream=cs)
+            algo = self.algo
+            if algo == "auto-sym":
+                algo = "nvls" if n * 4 >= self.nvls_min_bytes else "p2p"
+            span = (self.timeline.device_span(f"allreduce[{b.lo}:{b.hi}] {algo}", "comm", stream=cs)
                     if self.timeline is not None else contextlib.nullcontext())
             with torch.cuda.stream(cs), span:
-                if self.algo == "nvls":
+                if algo == "nvls":
                     self._comm.twoshot_nvls(b.lo, n, "f32", scale, self.comm_blocks)
-                elif self.algo == "p2p":
+                elif algo == "p2p":
                     self._comm.twoshot_p2p(b.lo, n, "f32", scale, self.comm_blocks)
                 else:
                     # one-shot reads every peer's slice and has no barrier between its load and store phases, so it

@@ -12,9 +12,10 @@
     udf = pyfunc.shard_udf(model_uri, result_type='string')                            # mlflow.pyfunc.spark_udf
     table.with_column('prediction', udf('content'))                                    # P2/03:466-472
 
-`shard_udf` executes as a map over shards of the table: with several GPUs each shard is scored by its own worker
-process pinned to one GPU (model loaded once per worker, like a Spark executor's python worker); otherwise the
-shards are scored in-process.  Inputs reach `predict` as real `bytes` (no stringified values, unlike the
+`shard_udf` executes as a map over the table's fragments (parquet row groups, memory-mapped Arrow batches, generated
+synthetic fragments): with several GPUs the fragments are pulled by persistent worker processes, one per GPU (model
+loaded once per worker, like a Spark executor's python worker), each READING ITS OWN BYTES - the driver only moves
+fragment descriptors and predictions; otherwise the fragments are scored in-process.  Inputs reach `predict` as real `bytes` (no stringified values, unlike the
 reference's `ast.literal_eval` workaround at P2/03:228-229, which we also tolerate).
 """
 from __future__ import annotations
@@ -23,7 +24,7 @@ import json
 import os
 import shutil
 from types import SimpleNamespace
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
 import pandas as pd
@@ -105,20 +106,193 @@ _RESULT_TYPES = {"string": pa.string(), "int": pa.int32(), "long": pa.int64(), "
                  "float": pa.float32()}
 
 
-def _score_shard(args):
-    """Worker entry (spawned process): pin a GPU, load the model once, score the shard."""
-    model_uri, tracking_uri, shard_index, gpu, values = args
-    if gpu is not None and gpu >= 0:
+def _series_of(arr: pa.ChunkedArray) -> pd.Series:
+    """Arrow column -> pandas Series WITHOUT touching the payload: the Series wraps the Arrow buffers
+    (`pd.ArrowDtype`), so `models.decode_batch` can hand fixed-size image payloads to the device as one view."""
+    try:
+        return pd.Series(pd.arrays.ArrowExtensionArray(arr))
+    except Exception:  # very old pandas: fall back to objects
+        return pd.Series(arr.to_pylist())
+
+
+class _FragmentScorer:
+    """Scores fragments with ONE loaded model; reads fragment k+1 on a helper thread while fragment k is on the GPU.
+    Image payloads of generated fragments are written straight into pinned host buffers (two, alternating)."""
+
+    def __init__(self, model_uri: str, column: str, gpu: Optional[int]):
+        self.column = column
+        self.cuda = False
+        if gpu is not None and gpu >= 0:
+            try:
+                import torch
+
+                if torch.cuda.is_available():
+                    torch.cuda.set_device(gpu % torch.cuda.device_count())
+                    self.cuda = True
+            except Exception:
+                pass
+        self.model = load_model(model_uri)
+        self._pinned = [None, None]
+        self._slot = 0
+        self.read_s = 0.0
+        self.predict_s = 0.0
+
+    def _alloc(self, nbytes: int):
+        if not self.cuda:
+            return np.empty(nbytes, dtype=np.uint8)
         import torch
 
-        if torch.cuda.is_available():
-            torch.cuda.set_device(gpu % torch.cuda.device_count())
-    from .. import tracking
+        i = self._slot
+        self._slot ^= 1
+        buf = self._pinned[i]
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            self._pinned[i] = buf
+        return buf.numpy()
 
-    tracking.set_tracking_uri(tracking_uri)
-    model = load_model(model_uri)
-    out = model.predict(pd.Series(values))
-    return shard_index, list(np.asarray(out).tolist())
+    def _read(self, frag):
+        import time
+
+        t0 = time.perf_counter()
+        t = frag.read([self.column], pinned_alloc=self._alloc)
+        self.read_s += time.perf_counter() - t0
+        return t
+
+    def score(self, frags_iter):
+        """Generator: yields (fragment position, predictions ndarray) for (position, fragment) pairs from `frags_iter`."""
+        import concurrent.futures as cf
+        import time
+
+        with cf.ThreadPoolExecutor(1) as ex:
+            nxt = None
+            it = iter(frags_iter)
+
+            def submit():
+                try:
+                    pos, frag = next(it)
+                except StopIteration:
+                    return None
+                return pos, ex.submit(self._read, frag)
+
+            nxt = submit()
+            while nxt is not None:
+                pos, fut = nxt
+                table = fut.result()
+                nxt = submit()  # the helper thread reads / generates the next fragment while this one is scored
+                t0 = time.perf_counter()
+                out = np.asarray(self.model.predict(_series_of(table.column(self.column))))
+                self.predict_s += time.perf_counter() - t0
+                yield pos, out
+
+
+def _pool_worker(rank: int, model_uri: str, tracking_uri: str, column: str, tasks, results) -> None:
+    """Persistent scoring process: pinned to GPU `rank`, model loaded ONCE, fragments pulled from a shared queue."""
+    try:
+        from .. import tracking
+
+        tracking.set_tracking_uri(tracking_uri)
+        scorer = _FragmentScorer(model_uri, column, rank)
+        results.put(("ready", rank, None))
+
+        def pull():
+            while True:
+                item = tasks.get()
+                if item is None or item[0] == "end":
+                    return
+                yield item[1], item[2]
+
+        while True:
+            # a job = a stream of ('frag', pos, fragment) items terminated by ('end',); None shuts the worker down
+            first = tasks.get()
+            if first is None:
+                return
+            if first[0] == "end":
+                results.put(("done", rank, {"read_s": scorer.read_s, "predict_s": scorer.predict_s}))
+                continue
+
+            def chain(first_item):
+                yield first_item[1], first_item[2]
+                yield from pull()
+
+            for pos, out in scorer.score(chain(first)):
+                results.put(("res", pos, out))
+            results.put(("done", rank, {"read_s": scorer.read_s, "predict_s": scorer.predict_s}))
+    except BaseException as ex:  # surface the failure instead of leaving the driver waiting
+        import traceback
+
+        results.put(("error", rank, f"{type(ex).__name__}: {ex}\n{traceback.format_exc()}"))
+
+
+class _WorkerPool:
+    """One spawned process per GPU, alive for the life of the UDF (like a Spark executor's python worker)."""
+
+    def __init__(self, model_uri: str, column: str, workers: int):
+        import multiprocessing as mp
+
+        from .. import tracking
+
+        ctx = mp.get_context("spawn")
+        self.tasks = ctx.Queue()
+        self.results = ctx.Queue()
+        self.column = column
+        self.procs = [ctx.Process(target=_pool_worker, args=(i, model_uri, tracking.get_tracking_uri(), column, self.tasks,
+                                                              self.results), daemon=True) for i in range(workers)]
+        for p in self.procs:
+            p.start()
+        ready = 0
+        while ready < workers:
+            kind, who, payload = self._get()
+            if kind == "ready":
+                ready += 1
+
+    def _get(self, timeout: float = 1800.0):
+        import queue
+
+        waited = 0.0
+        while True:
+            try:
+                item = self.results.get(timeout=2.0)
+            except queue.Empty:
+                waited += 2.0
+                dead = [p for p in self.procs if not p.is_alive()]
+                if dead and self.results.empty():
+                    raise RuntimeError(f"a scoring worker died (exit code {dead[0].exitcode})")
+                if waited > timeout:
+                    raise TimeoutError("scoring workers did not answer")
+                continue
+            if item[0] == "error":
+                raise RuntimeError(f"scoring worker {item[1]} failed:\n{item[2]}")
+            return item
+
+    def run(self, frags) -> Tuple[Dict[int, np.ndarray], List[dict]]:
+        n = len(self.procs)
+        for pos, f in enumerate(frags):
+            self.tasks.put(("frag", pos, f))
+        for _ in range(n):
+            self.tasks.put(("end",))
+        out: Dict[int, np.ndarray] = {}
+        stats: List[dict] = []
+        done = 0
+        while done < n:
+            kind, a, b = self._get()
+            if kind == "res":
+                out[a] = b
+            elif kind == "done":
+                done += 1
+                stats.append({"worker": a, **b})
+        return out, stats
+
+    def close(self) -> None:
+        for _ in self.procs:
+            try:
+                self.tasks.put(None)
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.kill()
+        self.procs = []
 
 
 class ShardUDFExpr:
@@ -130,13 +304,23 @@ class ShardUDFExpr:
 
 
 class ShardUDF:
+    """`mlflow.pyfunc.spark_udf` (reference P2/03:466): a map of `PythonModel.predict` over the table's fragments.
+
+    * the driver only handles fragment DESCRIPTORS and predictions; image bytes are read (parquet row groups, memory-mapped
+      Arrow batches) or generated (synthetic fragments) inside the worker that scores them;
+    * workers are persistent - one process per GPU, model loaded once, reused by every later call of this UDF - and pull
+      fragments from a shared queue (dynamic load balancing); each overlaps reading fragment k+1 with scoring fragment k;
+    * `stats` after a call: rows, workers, seconds, rows_per_sec, per-worker read / predict seconds."""
+
     def __init__(self, model_uri: str, result_type: str = "string", num_workers: Optional[int] = None,
-                 batch_rows: int = 1024):
+                 batch_rows: int = 4096):
         self.model_uri = model_uri
         self.result_type = result_type
         self.num_workers = num_workers
         self.batch_rows = batch_rows
-        self._local: Optional[PyFuncModel] = None
+        self._local: Optional[_FragmentScorer] = None
+        self._pool: Optional[_WorkerPool] = None
+        self._tmp: List[str] = []
         self.stats: Dict[str, Any] = {}
 
     def __call__(self, column) -> ShardUDFExpr:
@@ -152,35 +336,75 @@ class ShardUDF:
         except Exception:
             return 1
 
+    def _fragments_of(self, table, column: str):
+        """Fragment descriptors of `table`: its own for a ScanTable; for an in-memory table the column is written ONCE to a
+        memory-mappable Arrow IPC file (no per-row python objects, no pickled payloads) and sliced into record batches."""
+        from ..data.scan import Fragment, ScanTable
+
+        if isinstance(table, ScanTable) and column in table._schema.names:
+            return table.fragments()
+        import tempfile
+
+        arrow = table.to_arrow().select([column])
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+        fd, path = tempfile.mkstemp(prefix="b200ddl_udf_", suffix=".arrow", dir=base)
+        os.close(fd)
+        self._tmp.append(path)
+        frags = []
+        with pa.OSFile(path, "wb") as sink, pa.ipc.new_file(sink, arrow.schema) as w:
+            # at least one fragment per worker (small tables), at most batch_rows rows per fragment
+            rows = max(1, min(self.batch_rows, -(-arrow.num_rows // max(1, self._workers()))))
+            for i, b in enumerate(arrow.combine_chunks().to_batches(max_chunksize=rows)):
+                w.write_batch(b)
+                frags.append(Fragment("ipc", b.num_rows, path=path, row_group=i))
+        return frags
+
     def evaluate(self, table, column: str) -> pa.ChunkedArray:
         import time
 
-        from .. import tracking
-
         typ = _RESULT_TYPES.get(self.result_type, pa.string())
-        values = table.to_arrow().column(column).to_pylist()
-        n = len(values)
-        workers = min(self._workers(), max(1, n))
         t0 = time.time()
-        if workers <= 1:
-            if self._local is None:
-                self._local = load_model(self.model_uri)
-            outs: List[Any] = []
-            for i in range(0, n, self.batch_rows):  # pandas-UDF style: Arrow batch -> Series -> predict
-                outs.extend(np.asarray(self._local.predict(pd.Series(values[i:i + self.batch_rows]))).tolist())
-        else:
-            import multiprocessing as mp
+        frags = self._fragments_of(table, column)
+        n = sum(f.rows for f in frags)
+        workers = min(self._workers(), max(1, len(frags)))
+        per_worker: List[dict] = []
+        try:
+            if workers <= 1:
+                if self._local is None or self._local.column != column:
+                    self._local = _FragmentScorer(self.model_uri, column, 0)
+                res = dict(self._local.score(enumerate(frags)))
+                per_worker = [{"worker": 0, "read_s": self._local.read_s, "predict_s": self._local.predict_s}]
+            else:
+                if self._pool is None or self._pool.column != column or len(self._pool.procs) != workers:
+                    if self._pool is not None:
+                        self._pool.close()
+                    self._pool = _WorkerPool(self.model_uri, column, workers)
+                t0 = time.time()  # worker start-up (process spawn + model load) is a one-off, reported separately
+                res, per_worker = self._pool.run(frags)
+        finally:
+            for p in self._tmp:
+                try:
+                    os.remove(p)
+                except OSError:
+                    pass
+            self._tmp = []
+        arrays = [pa.array(np.asarray(res[i]).tolist() if typ == pa.string() else np.asarray(res[i]), type=typ)
+                  for i in range(len(frags))]
+        dt = time.time() - t0
+        self.stats = {"rows": n, "workers": workers, "fragments": len(frags), "seconds": dt,
+                      "rows_per_sec": n / max(dt, 1e-9), "per_worker": per_worker}
+        return pa.chunked_array(arrays, type=typ)
 
-            bounds = [round(i * n / workers) for i in range(workers + 1)]
-            jobs = [(self.model_uri, tracking.get_tracking_uri(), i, i, values[bounds[i]:bounds[i + 1]])
-                    for i in range(workers) if bounds[i + 1] > bounds[i]]
-            ctx = mp.get_context("spawn")
-            with ctx.Pool(len(jobs)) as pool:
-                res = dict(pool.map(_score_shard, jobs))
-            outs = [v for i in sorted(res) for v in res[i]]
-        self.stats = {"rows": n, "workers": workers, "seconds": time.time() - t0,
-                      "rows_per_sec": n / max(time.time() - t0, 1e-9)}
-        return pa.chunked_array([pa.array(outs, type=typ)])
+    def close(self) -> None:
+        if self._pool is not None:
+            self._pool.close()
+            self._pool = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def shard_udf(model_uri: str, result_type: str = "string", num_workers: Optional[int] = None) -> ShardUDF:

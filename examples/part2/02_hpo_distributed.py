@@ -62,10 +62,19 @@ def train_and_evaluate_hvd(learning_rate=0.001, dropout=0.5, batch_size=32, chec
     return val_loss, val_accuracy
 
 
+# One gang of rank processes for ALL trials (HVD_PERSISTENT=0 restores a fresh HorovodRunner per trial, as in the reference):
+# CUDA contexts, loaded extensions, the NCCL group and the symmetric flag buffers are created once; a trial costs shipping
+# the pickled function + building its model.  `hr.last_timing` has the per-trial bootstrap breakdown.
+PERSISTENT = os.environ.get("HVD_PERSISTENT", "1") == "1"
+hr = Runner(np=HVD_NUM_PROCESSES, driver_log_verbosity=os.environ.get("HVD_LOGS", "all"), persistent=PERSISTENT)
+trial_timings = []
+
+
 def objective_function(params):                                                              # reference :294-309
-    hr = Runner(np=HVD_NUM_PROCESSES, driver_log_verbosity="all")
+    t0 = time.time()
     loss, acc = hr.run(train_and_evaluate_hvd, learning_rate=params["learning_rate"], dropout=params["dropout"],
                        batch_size=params["batch_size"], checkpoint_dir=checkpoint_dir)
+    trial_timings.append({"trial_s": time.time() - t0, **hr.last_timing})
     return {"loss": loss, "status": STATUS_OK}                                               # minimise val_loss
 
 
@@ -79,6 +88,11 @@ with tracking.start_run(run_name="hyperopt_horovod_tuning") as parent_run:      
     # default Trials => trials run one after another on the driver, so each may launch a distributed job (:342-344)
     best_hyperparam = fmin(fn=objective_function, space=search_space, algo=tpe.suggest, max_evals=MAX_EVALS)
     tracking.log_params({"best_" + k: v for k, v in best_hyperparam.items()})
+hr.close()
+import json
+print("HPO_TIMING " + json.dumps({"np": HVD_NUM_PROCESSES, "trials": len(trial_timings), "persistent_ranks": PERSISTENT,
+                                  "wall_s": sum(t["trial_s"] for t in trial_timings), "per_trial": trial_timings,
+                                  "arch": ARCH, "epochs": EPOCHS}))
 print("best:", best_hyperparam, "->", space_eval(search_space, best_hyperparam))
 print("checkpoints:", session.fs.ls(checkpoint_dir))                                        # reference :380
 

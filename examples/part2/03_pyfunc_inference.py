@@ -10,7 +10,7 @@ import numpy as np
 import pandas as pd
 from b200ddl import optim, pyfunc, tracking
 from b200ddl.loader import make_converter
-from b200ddl.models import CLASSES, build_model, decode_image
+from b200ddl.models import CLASSES, build_model, decode_batch, decode_image
 from b200ddl.train import EarlyStopping, Trainer
 
 BATCH_SIZE = 16 if SMALL else 128     # reference :64
@@ -38,7 +38,9 @@ class FlowerPyFunc(pyfunc.PythonModel):                                    # ref
         return decode_image(img_bytes, (self.img_height, self.img_width))
 
     def predict(self, context, model_input: pd.Series) -> np.ndarray:
-        arr = np.stack([self.preprocess(b) for b in model_input])
+        # whole-column decode: JPEG/PNG rows on a thread pool; raw fixed-size payloads as one zero-copy view of the
+        # column buffer (per-row `self.preprocess` above is what it does row by row)
+        arr = decode_batch(model_input, (self.img_height, self.img_width))
         logits = self.model.predict(arr, batch_size=BATCH_SIZE)
         return np.take(CLASSES, np.argmax(logits, axis=1))
 
@@ -94,3 +96,19 @@ pred_df.display(10)
 pdf = pred_df.toPandas()
 print(f"scored {len(pdf)} rows with {classify_udf.stats['workers']} worker(s): "
       f"{classify_udf.stats['rows_per_sec']:.0f} rows/s, accuracy {(pdf.label == pdf.prediction).mean():.3f}")
+
+# -- the same UDF at scale (BASELINE.json config 4): WORKSHOP_INFER_IMAGES=1000000 scores a lazily generated table
+#    whose fragments are produced and read inside the per-GPU workers; only predictions return to the driver
+N_INFER = int(os.environ.get("WORKSHOP_INFER_IMAGES", "0"))
+if N_INFER > 0:
+    from b200ddl.data import synthetic_scan
+    big = synthetic_scan(N_INFER, size=(IMG_HEIGHT, IMG_WIDTH), num_classes=len(CLASSES))
+    scored = big.withColumn("prediction", classify_udf("content")).select("path", "label", "prediction")
+    st = dict(classify_udf.stats)
+    head = scored.limit(5).toPandas()
+    print(head.to_string(index=False))
+    print("INFERENCE_STATS " + json.dumps({"rows": st["rows"], "workers": st["workers"], "fragments": st["fragments"],
+                                           "seconds": st["seconds"], "images_per_sec": st["rows_per_sec"],
+                                           "per_worker": st["per_worker"], "api": "pyfunc.spark_udf over data.synthetic_scan",
+                                           "image": f"{IMG_HEIGHT}x{IMG_WIDTH}x3 uint8", "arch": ARCH, "batch": BATCH_SIZE}))
+classify_udf.close()

@@ -157,3 +157,49 @@ def test_hyperopt_stopping_arguments():
     assert 4 <= len(t) < 120 and all(tr["result"].get("status") == STATUS_OK for tr in t.trials)
     with pytest.warns(UserWarning):
         fmin(lambda p: p["x"], space, algo=rand.suggest, max_evals=2, rstate=4, max_queue_len=4)
+
+
+def _slot_objective(p):
+    """Module-level objective for the process executor: reports which worker process / slot evaluated it."""
+    import os
+    import time
+
+    from b200ddl import tracking
+
+    time.sleep(0.15)
+    tracking.log_metric("inner_metric", p["x"])
+    return {"loss": (p["x"] - 0.3) ** 2, "status": hpo.STATUS_OK, "pid": os.getpid(),
+            "slot": os.environ.get("B200DDL_TRIAL_SLOT"), "tid": hpo.current_trial()["tid"]}
+
+
+def test_parallel_trials_process_executor(tmp_path):
+    """`ParallelTrials(executor='process')`: trials run in persistent worker processes (one per slot), the objective
+    travels by value, per-trial tracking lands in the trial's nested run, and a failing objective is recorded."""
+    import os
+
+    from b200ddl import tracking
+
+    tracking.set_tracking_uri(str(tmp_path / "mlruns"))
+    tracking.set_experiment("proc_hpo")
+    trials = hpo.ParallelTrials(parallelism=3, executor="process")
+    with tracking.start_run(run_name="parent") as parent:
+        best = hpo.fmin(_slot_objective, {"x": hpo.hp.uniform("x", 0, 1)}, algo=hpo.rand.suggest, max_evals=9, trials=trials,
+                        rstate=np.random.default_rng(0))
+    assert 0 <= best["x"] <= 1 and len(trials) == 9
+    pids = {t["result"]["pid"] for t in trials.trials}
+    assert os.getpid() not in pids and 1 <= len(pids) <= 3            # evaluated in worker processes, reused across trials
+    assert {t["result"]["slot"] for t in trials.trials} <= {"0", "1", "2"}
+    assert sorted(t["result"]["tid"] for t in trials.trials) == list(range(9))
+    kids = tracking.search_runs(filter_string=f"tags.mlflow.parentRunId = '{parent.info.run_id}'")
+    assert len(kids) == 9 and kids["metrics.inner_metric"].notna().all()  # logged from inside the worker into the child run
+
+    def flaky(p):
+        if p["x"] > 0.5:
+            raise ValueError("bad region")
+        return p["x"]
+
+    t2 = hpo.ParallelTrials(parallelism=2, executor="process")
+    hpo.fmin(flaky, {"x": hpo.hp.uniform("x", 0, 1)}, algo=hpo.rand.suggest, max_evals=8, trials=t2,
+             rstate=np.random.default_rng(1))
+    states = [t["result"]["status"] for t in t2.trials]
+    assert hpo.STATUS_FAIL in states and hpo.STATUS_OK in states

@@ -194,3 +194,44 @@ def test_workers_get_their_share_of_the_cores(monkeypatch):
     assert env_val == str(share) and torch_threads == share
     monkeypatch.setenv("OMP_NUM_THREADS", "3")           # an explicit user setting wins
     assert Runner(np=2, driver_log_verbosity="none", force_cpu=True).run(fn)[0] == "3"
+
+
+def test_persistent_rank_pool_reuses_processes_and_process_group():
+    """`Runner(persistent=True)`: the same rank processes (and their process group) serve several `run()` calls - what
+    back-to-back HPO trials over the distributed trainer use; a failing job stops the gang and the next call gets a new one."""
+    import time
+
+    def fn(offset):
+        import os
+
+        import torch
+        import b200ddl.parallel as hvd
+
+        hvd.init()
+        s = hvd.allreduce(torch.ones(2) * (hvd.rank() + offset), average=False)
+        return os.getpid(), float(s[0])
+
+    with Runner(np=2, driver_log_verbosity="none", force_cpu=True, persistent=True) as r:
+        pid0, v0 = r.run(fn, offset=1.0)
+        assert v0 == 3.0 and r.last_timing["pool_started"] is True
+        t0 = time.time()
+        pid1, v1 = r.run(fn, offset=2.0)
+        dt = time.time() - t0
+        assert pid1 == pid0 and v1 == 5.0 and r.last_timing["pool_started"] is False
+        assert dt < r.last_timing["pool_start_s"] + 2.0  # no spawn / import / rendezvous the second time
+
+        def bad():
+            import b200ddl.parallel as hvd
+
+            hvd.init()
+            if hvd.rank() == 1:
+                raise ValueError("second job exploded")
+            import time as _t
+
+            _t.sleep(30)
+
+        with pytest.raises(RunnerError) as ei:
+            r.run(bad)
+        assert "second job exploded" in str(ei.value)
+        pid2, v2 = r.run(fn, offset=1.0)   # a fresh gang
+        assert pid2 != pid0 and v2 == 3.0
