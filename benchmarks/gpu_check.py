@@ -347,6 +347,14 @@ def case_elementwise():
     e.preprocess_u8(xb, ob, 1 / 127.5, -1.0)
     ok &= report("preprocess_u8", rel_err(ob[..., :3], xb.float() / 127.5 - 1), 1e-2)
     ok &= report("preprocess_u8_pad", float(ob[..., 3:].float().abs().max()), 0.0)
+    # bilinear resize (half-pixel centres, no antialias - tf.image.resize / F.interpolate(align_corners=False))
+    for (H_, W_, OH, OW) in ((64, 48, 32, 32), (40, 40, 96, 96), (224, 224, 224, 224)):
+        xs = torch.randint(0, 256, (3, H_, W_, 3), device=DEV, dtype=torch.uint8, generator=g)
+        od = torch.empty(3, OH, OW, 3, device=DEV, dtype=torch.uint8)
+        e.resize_bilinear_u8(xs, od)
+        ref_r = torch.nn.functional.interpolate(xs.permute(0, 3, 1, 2).float(), size=(OH, OW), mode="bilinear",
+                                                align_corners=False).permute(0, 2, 3, 1)
+        ok &= report(f"resize_bilinear_u8/{H_}x{W_}->{OH}x{OW}", float((od.float() - ref_r).abs().max()), 1.0, "(max abs diff in uint8 steps)")
     # optimizers
     n = 4096 * 4
     p = torch.randn(n, device=DEV, generator=g); gr = torch.randn(n, device=DEV, generator=g)
@@ -863,7 +871,7 @@ def case_big_numerics():
 
 def case_umma_probe():
     """Row-shifted SWIZZLE_128B descriptors: which (shift, base_offset) combinations read the right rows?"""
-    ext = ops.ext("_b200_conv")
+    ext = ops.ext("_b200_probe")
     g = torch.Generator(device=DEV).manual_seed(21)
     T = torch.randn(160, 64, device=DEV, generator=g).to(torch.bfloat16)
     B = torch.randn(64, 64, device=DEV, generator=g).to(torch.bfloat16)
@@ -895,7 +903,7 @@ def case_umma_probe():
 
 def case_tma_probe():
     """TMA load pipeline alone (no MMA, no epilogue): time per box load for the shapes the 3x3 convs use or could use."""
-    ext = ops.ext("_b200_conv")
+    ext = ops.ext("_b200_probe")
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     x56 = torch.randn(256, 56, 56, 64, device=DEV).to(torch.bfloat16)
     x28 = torch.randn(512, 28, 28, 64, device=DEV).to(torch.bfloat16)

@@ -84,6 +84,14 @@ class SyntheticDataset(RingDataset):
 
 
 class _TableDataset(RingDataset):
+    """Rows of one shard of the parquet cache -> decoded uint8 batches in the pinned ring.
+
+    Sharding: shard s owns the contiguous global row range [n*s/k, n*(s+1)/k) and opens ONLY the row groups that
+    intersect it (no read amplification: k ranks together read the cache once, not k times).  `shuffle=True` permutes
+    the shard's row groups and the rows inside every group with `seed + epoch` (Petastorm shuffles row groups too).
+    Row groups stay Arrow arrays (no `to_pylist`); the short critical section only hands out (array, index) pairs, the
+    decode (PIL releases the GIL) runs outside it in `workers_count` threads."""
+
     def __init__(self, files, total_rows, batch_size, image_size, device, cur_shard, shard_count, num_epochs,
                  workers_count, shuffle, seed):
         super().__init__(batch_size, image_size, device, num_slots=max(4, workers_count + 2))
@@ -92,6 +100,9 @@ class _TableDataset(RingDataset):
         self.cur_shard, self.shard_count = cur_shard, shard_count
         self.num_epochs = num_epochs
         self.shuffle, self.seed = shuffle, seed
+        n, k = self.total_rows, shard_count
+        self.row_lo, self.row_hi = (n * cur_shard) // k, (n * (cur_shard + 1)) // k
+        self.row_groups_read = 0   # statistics: how many row groups this shard has opened
         self._stop = threading.Event()
         self._lock = threading.Lock()
         self._row_iter = self._rows()
@@ -101,33 +112,51 @@ class _TableDataset(RingDataset):
             t.start()
 
     def __len__(self) -> int:
-        """Full batches per epoch of THIS shard (global row i belongs to shard i % shard_count), so that
-        `fit(ds)` / `steps_per_epoch=len(ds)` work like they do for a Keras dataset."""
-        rows = (self.total_rows - self.cur_shard + self.shard_count - 1) // self.shard_count if self.total_rows > self.cur_shard else 0
-        return rows // self.batch_size
+        """Full batches per epoch of THIS shard, so that `fit(ds)` / `steps_per_epoch=len(ds)` work like they do for a
+        Keras dataset."""
+        return (self.row_hi - self.row_lo) // self.batch_size
 
-    def _rows(self):
-        """Infinite (or `num_epochs`) stream of (content, label) of THIS shard: global row i belongs to shard
-        i % shard_count (any shard_count works; the reference needed `repartition(2)`)."""
+    def _plan(self):
+        """[(file index, row group, first row inside the group, row count)] of this shard, in file order."""
         import pyarrow.parquet as pq
 
+        plan = []
+        for fi, (path, base) in enumerate(self.files):
+            md = pq.ParquetFile(path).metadata
+            g0 = base
+            for rg in range(md.num_row_groups):
+                nr = md.row_group(rg).num_rows
+                lo, hi = max(self.row_lo, g0), min(self.row_hi, g0 + nr)
+                if hi > lo:
+                    plan.append((fi, rg, lo - g0, hi - lo))
+                g0 += nr
+        return plan
+
+    def _rows(self):
+        """Infinite (or `num_epochs`) stream of (content array, label array, row index) of THIS shard."""
+        import pyarrow.parquet as pq
+
+        plan = self._plan()
+        handles = {}
         epoch = 0
-        while self.num_epochs is None or epoch < self.num_epochs:
-            gi = 0
-            order = list(range(len(self.files)))
-            if self.shuffle:
-                np.random.default_rng(self.seed + epoch).shuffle(order)
-            for fi in order:
-                pf = pq.ParquetFile(self.files[fi][0])
-                base = self.files[fi][1]
-                for rg in range(pf.num_row_groups):
-                    t = pf.read_row_group(rg, columns=["content", "label_idx"])
-                    contents = t.column("content").to_pylist()
-                    labels = t.column("label_idx").to_pylist()
-                    for j, (c, l) in enumerate(zip(contents, labels)):
-                        if (base + gi + j) % self.shard_count == self.cur_shard:
-                            yield c, l
-                    gi += len(contents)
+        while (self.num_epochs is None or epoch < self.num_epochs) and plan:
+            order = list(range(len(plan)))
+            rng = np.random.default_rng(self.seed + epoch) if self.shuffle else None
+            if rng is not None:
+                rng.shuffle(order)
+            for pi in order:
+                fi, rg, skip, count = plan[pi]
+                if fi not in handles:
+                    handles[fi] = pq.ParquetFile(self.files[fi][0])
+                t = handles[fi].read_row_group(rg, columns=["content", "label_idx"])
+                self.row_groups_read += 1
+                contents = t.column("content").combine_chunks()
+                labels = t.column("label_idx").to_numpy()
+                idx = np.arange(skip, skip + count)
+                if rng is not None:
+                    rng.shuffle(idx)
+                for j in idx:
+                    yield contents, labels, int(j)
             epoch += 1
 
     def _worker(self):
@@ -159,9 +188,9 @@ class _TableDataset(RingDataset):
             img, lab = self.ring.slot_tensors(slot)
             img = img.numpy().reshape(self.batch_size, self.h, self.w, 3)
             lab = lab.numpy()
-            for i, (c, l) in enumerate(batch):
-                img[i] = decode_image(c, (self.h, self.w))
-                lab[i] = l
+            for i, (contents, labels, j) in enumerate(batch):
+                img[i] = decode_image(contents[j].as_py(), (self.h, self.w))
+                lab[i] = labels[j]
             self.ring.commit(slot)
 
     def close(self) -> None:

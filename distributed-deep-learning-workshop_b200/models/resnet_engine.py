@@ -675,7 +675,22 @@ class ResNet50Engine:
 
     # ------------------------------------------------------------------------------------------------ utilities
     def set_input(self, x_u8: torch.Tensor, labels: Optional[torch.Tensor] = None) -> None:
-        self.x_u8.copy_(x_u8.view(self.x_u8.shape), non_blocking=True)
+        """Copy a batch into the static input buffers.  Images whose spatial size differs from the engine's are resized
+        ON THE GPU (bilinear, half-pixel centres like `tf.image.resize` - the reference's preprocess, P1/03:182-189):
+        the batch goes to a device staging buffer of its own size and `resize_bilinear_u8` writes the engine input."""
+        if x_u8.dim() == 4 and tuple(x_u8.shape[1:3]) != (self.image_size, self.image_size):
+            if x_u8.shape[0] != self.batch or x_u8.shape[3] != 3 or x_u8.dtype != torch.uint8:
+                raise ValueError(f"set_input: expected uint8 [{self.batch}, H, W, 3], got {tuple(x_u8.shape)} {x_u8.dtype}")
+            key = tuple(x_u8.shape)
+            stage = getattr(self, "_resize_stage", {}).get(key)
+            if stage is None:
+                if not hasattr(self, "_resize_stage"):
+                    self._resize_stage = {}
+                stage = self._resize_stage[key] = torch.empty(key, device=self.device, dtype=torch.uint8)
+            stage.copy_(x_u8, non_blocking=True)
+            self._e.resize_bilinear_u8(stage, self.x_u8)
+        else:
+            self.x_u8.copy_(x_u8.view(self.x_u8.shape), non_blocking=True)
         if labels is not None:
             self.labels.copy_(labels, non_blocking=True)
 

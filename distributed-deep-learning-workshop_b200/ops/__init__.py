@@ -3,6 +3,7 @@
 ``ops.ext(name)`` loads (building in-tree if needed) one of the extensions:
 
     _b200_conv    tcgen05/TMEM/TMA implicit-GEMM convolution forward / dgrad / wgrad
+    _b200_probe   hardware probes (UMMA descriptor addressing, TMA pipeline throughput); never on a hot path
     _b200_ops     BN / ReLU / pool / softmax-CE / preprocess kernels + fused optimizers
     _b200_comm    fused all-reduce kernels over NVLink symmetric memory
     _b200_loader  pinned-host ring buffer with side-stream H2D

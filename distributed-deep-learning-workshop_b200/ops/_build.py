@@ -32,7 +32,8 @@ CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC"]
 
 # name -> sources (relative to csrc/)
 EXTENSIONS: Dict[str, List[str]] = {
-    "_b200_conv": ["conv_igemm.cu", "conv_wgrad.cu", "stem.cu", "umma_probe.cu", "tma_probe.cu", "conv_bind.cpp"],
+    "_b200_conv": ["conv_igemm.cu", "conv_wgrad.cu", "stem.cu", "tmap.cpp", "conv_bind.cpp"],
+    "_b200_probe": ["umma_probe.cu", "tma_probe.cu", "tmap.cpp", "probe_bind.cpp"],   # hardware probes, not on any hot path
     "_b200_ops": ["elementwise.cu", "head_stem.cu", "optim.cu", "ops_bind.cpp"],
     "_b200_comm": ["allreduce.cu", "comm_bind.cpp"],
     "_b200_loader": ["ring_loader.cpp"],
@@ -41,6 +42,7 @@ EXTENSIONS: Dict[str, List[str]] = {
 # mark the others stale
 HEADERS: Dict[str, List[str]] = {
     "_b200_conv": ["ptx.cuh", "conv_igemm.cuh", "conv_params.h", "conv_api.h"],
+    "_b200_probe": ["ptx.cuh", "conv_params.h", "conv_api.h"],
     "_b200_ops": ["ops_api.h"],
     "_b200_comm": ["comm_api.h"],
     "_b200_loader": [],

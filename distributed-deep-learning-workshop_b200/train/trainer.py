@@ -354,7 +354,8 @@ class Trainer:
             self._compile_for_inference()
         arr = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x)
         n = arr.shape[0]
-        if hasattr(self.backend, "predict_stream") and arr.dtype == torch.uint8 and arr.dim() == 4:
+        if (hasattr(self.backend, "predict_stream") and arr.dtype == torch.uint8 and arr.dim() == 4
+                and tuple(arr.shape[1:]) == tuple(self.backend.engine.x_u8.shape[1:])):
             return self.backend.predict_stream(arr).numpy()
         fixed = getattr(self.backend, "batch", None)
         bs = fixed or batch_size

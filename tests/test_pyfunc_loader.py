@@ -180,3 +180,34 @@ def test_train_log_pyfunc_and_batch_inference(session):
     assert list(data.limit(2).withColumn("prediction", udf9("content")).to_pandas()["prediction"]) == list(df["prediction"][:2])
     assert udf9.stats["workers"] == 2
     assert len(data.limit(0).withColumn("prediction", udf9("content")).to_pandas()) == 0
+
+
+def test_row_group_sharding_reads_each_group_once_and_shuffle_changes_order(session):
+    """Shard s owns a contiguous row range and opens only the row groups that intersect it (8 ranks together read the
+    cache once, not 8 times); `shuffle=True` permutes row groups and rows with seed + epoch, deterministically."""
+    from b200ddl.loader import Converter
+
+    t = _tables(session, 96).select(["content", "label_idx"])
+    conv = Converter(t, session.cache_dir, rows_per_group=8)                   # 12 row groups
+    labels = t.to_pandas()["label_idx"].tolist()
+    seen, groups = [], 0
+    for shard in range(4):
+        with conv.make_dataset(batch_size=8, cur_shard=shard, shard_count=4, num_epochs=1, workers_count=1,
+                               image_size=(IMG, IMG), device="cpu") as ds:
+            got = [l for _, y in ds for l in y.tolist()]
+            assert got == labels[24 * shard:24 * (shard + 1)]                     # contiguous range, file order
+            seen += got
+            groups += ds.row_groups_read
+    assert seen == labels and groups == 12                                       # every row group opened exactly once
+
+    def epoch_labels(seed, epochs=1):
+        with conv.make_dataset(batch_size=8, num_epochs=epochs, workers_count=1, image_size=(IMG, IMG), device="cpu",
+                               shuffle=True, seed=seed) as ds:
+            return [l for _, y in ds for l in y.tolist()]
+
+    a, b, c = epoch_labels(1), epoch_labels(1), epoch_labels(2)
+    assert a == b and sorted(a) == sorted(labels)                                # same seed -> same order, a permutation
+    assert a != labels and c != a                                                # not the file order; seed changes it
+    two = epoch_labels(1, epochs=2)
+    assert two[:96] == a and two[96:] != a and sorted(two[96:]) == sorted(labels)  # epoch 2 is reshuffled
+    conv.delete()
