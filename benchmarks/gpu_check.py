@@ -800,13 +800,17 @@ def case_stem_bwd():
         torch.cuda.synchronize()
         ok &= report(f"stem_bwd_sum_dz/N{N}_Ho{Ho}", float((s_n - s_keep).abs().max() / (s_keep.abs().max() + 1e-6)), 1e-4)
         ok &= report(f"stem_bwd_sum_dzy/N{N}_Ho{Ho}", float((sy_n - sy_keep).abs().max() / (sy_keep.abs().max() + 1e-6)), 1e-4)
-        ok &= report(f"stem_bwd_dy/N{N}_Ho{Ho}", float((dy_n.float() - dy_o.float()).abs().max()), 0.0, "(bit-identical to the unfused path)")
+        # the scatter sums the <= 4 window contributions of a pixel in colour-class order, the unfused kernel in window
+        # order: fp32 sums may differ in the last bit, i.e. rarely one bf16 ulp after rounding
+        mism = float((dy_n != dy_o).float().mean())
+        ok &= report(f"stem_bwd_dy/N{N}_Ho{Ho}", rel_err(dy_n, dy_o), 8e-3, f"(vs the unfused path; differing elements {mism:.2e})")
+        ok &= report(f"stem_bwd_dy_mismatch_rate/N{N}_Ho{Ho}", mism, 2e-3)
         # one-gradient variant (g2 = None)
         e.maxpool_bwd(idx, g1, None, da0)
         e.bn_bwd_apply(da0, y0, scale, shift, cA, cB, cC, dy_o)
         e.stem_pool_bn_bwd(1, idx, g1, None, y0, scale, shift, cA, cB, cC, dy_n, s_n, sy_n)
         torch.cuda.synchronize()
-        ok &= report(f"stem_bwd_dy_single_grad/N{N}_Ho{Ho}", float((dy_n.float() - dy_o.float()).abs().max()), 0.0)
+        ok &= report(f"stem_bwd_dy_single_grad/N{N}_Ho{Ho}", rel_err(dy_n, dy_o), 8e-3)
         if N >= 256:
             flush = torch.empty(256 * 1024 * 1024, device=DEV, dtype=torch.uint8)
             def old():

@@ -4,9 +4,9 @@
 // (P1/02:175) and MaxPool backward need besides the GEMMs:
 //   * softmax_ce_head: bf16 logits + fp32 bias -> loss, accuracy, bf16 dlogits (padded columns zero) in one pass;
 //   * fc_bias_grad: column sums of dlogits;
-//   * stem_pool_bn_bwd: 3x3/2 max-pool backward (argmax gather) fused with the stem BatchNorm+ReLU backward - the
+//   * stem_pool_bn_bwd: 3x3/2 max-pool backward (argmax scatter) fused with the stem BatchNorm+ReLU backward - the
 //     112x112x64 pooled-gradient tensor is never written: pass 0 reduces sum(dz), sum(dz*y), pass 1 writes dy;
-//     both gather from a shared-memory tile of (g1 + g2, argmax) so the <= 4 windows per pixel hit smem, not L2;
+//     both rebuild the pooled gradient of a 16x16-pixel tile in shared memory (conflict-free colour-class scatter);
 //   * pack_stem_weight: fp32 [49, 64, 3] master -> bf16 [64, 192] GEMM operand.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -134,13 +134,21 @@ void pack_stem_weight(const float* w, void* out, cudaStream_t s) {
 //   dz        = da * [y*scale + shift > 0]
 //   PASS 0:   sum_dz += dz, sum_dzy += dz * y          (per channel; one flush of atomics per CTA)
 //   PASS 1:   dy = cA*dz + cB*y + cC
-// A CTA walks 8x8 pooled tiles (16x16 input pixels): the 9x9 windows it needs are staged in shared memory as
-// fp32 (g1 + g2) + the argmax byte, so the gather reads smem; y / dy move as coalesced 16-byte vectors.
+// v1 of this kernel GATHERED per input pixel (compare the saved argmax of up to four windows, per channel) and was
+// instruction-bound: ncu 327 M warp instructions per pass, DRAM 15 % (profiles/r2_ncu_stem_bwd_*_v1.txt) - slower than the
+// three-kernel path it replaced.  v2 SCATTERS: every window contributes its gradient to exactly ONE pixel (its argmax), so
+// a CTA builds the da tile of 16x16 pixels x 64 channels in shared memory (fp32, 64 KB) by read-modify-write:
+//   * a warp handles (window, 32-channel half); lane = channel, so the smem bank is the lane whatever pixel is hit;
+//   * windows are processed in four colour classes (row parity x column parity): windows of one class have disjoint 3x3
+//     footprints, so plain (non-atomic) updates are race-free inside a class; __syncthreads between classes
+//     (shared-memory fp32 atomicAdd is a CAS spin loop on sm_100a - ATOMS.CAST.SPIN - and would dominate);
+//   * then the pixel phase reads da from smem, y from global, and reduces / applies.
 constexpr int kPoolTile = 8;
 constexpr int kPoolWin = kPoolTile + 1;
+constexpr int kStemDaBytes = 16 * 16 * 64 * 4;
 
 template <int PASS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 stem_pool_bn_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ g1,
                         const __nv_bfloat16* __restrict__ g2, const __nv_bfloat16* __restrict__ y,
                         const float* __restrict__ scale, const float* __restrict__ shift,
@@ -148,13 +156,13 @@ stem_pool_bn_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __
                         __nv_bfloat16* __restrict__ dy, float* __restrict__ sum_dz, float* __restrict__ sum_dzy, int N,
                         int Ho, int Wo) {
   constexpr int C = 64;
-  __shared__ __align__(16) float gS[kPoolWin * kPoolWin][C];
-  __shared__ __align__(8) uint8_t iS[kPoolWin * kPoolWin][C];
+  extern __shared__ __align__(16) float da[];  // [256 pixels][64 channels]
   __shared__ float red[2][8][C];
   const int H = 2 * Ho, W = 2 * Wo;
   const int tiles_h = Ho / kPoolTile, tiles_w = Wo / kPoolTile;
   const int num_tiles = N * tiles_h * tiles_w;
   const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
   const int cv = t & 7;
   const int pl = t >> 3;  // 0..31: pixel lane; pixels p = pl + 32*i
   float sc[8], sh[8], A[8], B[8], Cc[8], t0[8], t1[8];
@@ -175,56 +183,39 @@ stem_pool_bn_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __
     const int ta = rest % tiles_h;
     const int n = rest / tiles_h;
     const int a0 = ta * kPoolTile, b0 = tb * kPoolTile;
-    __syncthreads();  // the previous tile's gather is done with gS / iS
-    for (int item = t; item < kPoolWin * kPoolWin * 8; item += 256) {
-      const int win = item >> 3, v8 = item & 7;
-      const int wi = win / kPoolWin, wj = win - wi * kPoolWin;
-      const int ho = a0 + wi, wo = b0 + wj;
-      float gv[8];
-      uint2 pk = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);  // position 255 never matches
-#pragma unroll
-      for (int k = 0; k < 8; ++k) gv[k] = 0.f;
-      if (ho < Ho && wo < Wo) {
-        const int64_t o = ((((int64_t)n * Ho + ho) * Wo + wo) * C) + v8 * 8;
-        unpack8h(*reinterpret_cast<const bf8*>(g1 + o), gv);
-        if (g2 != nullptr) {
-          float hv[8];
-          unpack8h(*reinterpret_cast<const bf8*>(g2 + o), hv);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) gv[k] += hv[k];
-        }
-        pk = *reinterpret_cast<const uint2*>(idx + o);
-      }
-      *reinterpret_cast<float4*>(&gS[win][v8 * 8]) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-      *reinterpret_cast<float4*>(&gS[win][v8 * 8 + 4]) = make_float4(gv[4], gv[5], gv[6], gv[7]);
-      *reinterpret_cast<uint2*>(&iS[win][v8 * 8]) = pk;
-    }
+    __syncthreads();  // the previous tile's pixel phase is done with da
+    for (int i = t; i < 16 * 16 * C / 4; i += 256) reinterpret_cast<float4*>(da)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
+#pragma unroll 1
+    for (int cls = 0; cls < 4; ++cls) {
+      const int ci = cls >> 1, cj = cls & 1;
+      const int nwj = (kPoolWin - 1 - cj) / 2 + 1;
+      const int items = ((kPoolWin - 1 - ci) / 2 + 1) * nwj * 2;
+#pragma unroll 2
+      for (int it = warp; it < items; it += 8) {
+        const int w = it >> 1;
+        const int wi = ci + 2 * (w / nwj), wj = cj + 2 * (w % nwj);
+        const int ho = a0 + wi, wo = b0 + wj;
+        if (ho >= Ho || wo >= Wo) continue;  // warp-uniform
+        const int ch = (it & 1) * 32 + lane;
+        const int64_t o = ((((int64_t)n * Ho + ho) * Wo + wo) * C) + ch;
+        const int a = idx[o];
+        float g = __bfloat162float(g1[o]);
+        if (g2 != nullptr) g += __bfloat162float(g2[o]);
+        const int r = (a * 11) >> 5;  // a / 3 for a in 0..8
+        const int row = 2 * wi - 1 + r, col = 2 * wj - 1 + (a - 3 * r);
+        if (static_cast<unsigned>(row) < 16u && static_cast<unsigned>(col) < 16u) da[(row * 16 + col) * C + ch] += g;
+      }
+      __syncthreads();
+    }
     const int pw = pl & 15;
 #pragma unroll 2
     for (int i = 0; i < 8; ++i) {
       const int ph = (pl >> 4) + 2 * i;
       const int h = 2 * a0 + ph, w = 2 * b0 + pw;
-      float acc[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-      // local windows containing local row ph: wi in [ph/2, (ph+1)/2], position r = ph - (2*wi - 1)
-      for (int wi = ph >> 1; wi <= ((ph + 1) >> 1); ++wi) {
-        const int r = ph - (2 * wi - 1);
-        for (int wj = pw >> 1; wj <= ((pw + 1) >> 1); ++wj) {
-          const uint32_t pos = r * 3 + (pw - (2 * wj - 1));
-          const int win = wi * kPoolWin + wj;
-          const uint2 pk = *reinterpret_cast<const uint2*>(&iS[win][cv * 8]);
-          const float4 ga = *reinterpret_cast<const float4*>(&gS[win][cv * 8]);
-          const float4 gb = *reinterpret_cast<const float4*>(&gS[win][cv * 8 + 4]);
-          const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint32_t a = ((k < 4 ? pk.x : pk.y) >> (8 * (k & 3))) & 0xFFu;
-            acc[k] += (a == pos) ? gv[k] : 0.f;
-          }
-        }
-      }
+      const float4 d0 = *reinterpret_cast<const float4*>(&da[(ph * 16 + pw) * C + cv * 8]);
+      const float4 d1 = *reinterpret_cast<const float4*>(&da[(ph * 16 + pw) * C + cv * 8 + 4]);
+      const float acc[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
       const int64_t off = ((((int64_t)n * H + h) * W + w) * C) + cv * 8;
       float yy[8];
       unpack8h(*reinterpret_cast<const bf8*>(y + off), yy);
@@ -258,7 +249,6 @@ stem_pool_bn_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __
       t1[k] += __shfl_xor_sync(0xffffffffu, t1[k], 8);
       t1[k] += __shfl_xor_sync(0xffffffffu, t1[k], 16);
     }
-    const int warp = t >> 5, lane = t & 31;
     __syncthreads();
     if (lane < 8) {
 #pragma unroll
@@ -282,17 +272,23 @@ stem_pool_bn_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __
 void stem_pool_bn_bwd(int pass, const void* idx, const void* g1, const void* g2, const void* y, const float* scale,
                       const float* shift, const float* cA, const float* cB, const float* cC, void* dy, float* sum_dz,
                       float* sum_dzy, int N, int Ho, int Wo, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(stem_pool_bn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemDaBytes);
+    cudaFuncSetAttribute(stem_pool_bn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemDaBytes);
+    attr_set = true;
+  }
   const int tiles = N * (Ho / kPoolTile) * (Wo / kPoolTile);
-  int grid = 148 * 4;
+  int grid = 148 * 3;
   if (grid > tiles) grid = tiles;
   if (pass == 0)
-    stem_pool_bn_bwd_kernel<0><<<grid, 256, 0, s>>>((const uint8_t*)idx, (const __nv_bfloat16*)g1,
-                                                    (const __nv_bfloat16*)g2, (const __nv_bfloat16*)y, scale, shift,
-                                                    cA, cB, cC, (__nv_bfloat16*)dy, sum_dz, sum_dzy, N, Ho, Wo);
+    stem_pool_bn_bwd_kernel<0><<<grid, 256, kStemDaBytes, s>>>((const uint8_t*)idx, (const __nv_bfloat16*)g1,
+                                                               (const __nv_bfloat16*)g2, (const __nv_bfloat16*)y, scale,
+                                                               shift, cA, cB, cC, (__nv_bfloat16*)dy, sum_dz, sum_dzy, N, Ho, Wo);
   else
-    stem_pool_bn_bwd_kernel<1><<<grid, 256, 0, s>>>((const uint8_t*)idx, (const __nv_bfloat16*)g1,
-                                                    (const __nv_bfloat16*)g2, (const __nv_bfloat16*)y, scale, shift,
-                                                    cA, cB, cC, (__nv_bfloat16*)dy, sum_dz, sum_dzy, N, Ho, Wo);
+    stem_pool_bn_bwd_kernel<1><<<grid, 256, kStemDaBytes, s>>>((const uint8_t*)idx, (const __nv_bfloat16*)g1,
+                                                               (const __nv_bfloat16*)g2, (const __nv_bfloat16*)y, scale,
+                                                               shift, cA, cB, cC, (__nv_bfloat16*)dy, sum_dz, sum_dzy, N, Ho, Wo);
 }
 
 }  // namespace b200

@@ -77,7 +77,10 @@ def _synthetic_read(f: Fragment, columns, pinned_alloc) -> pa.Table:
 
     h, w, n_classes, pool, seed = f.spec
     imgs, labels = _synthetic_pool(f.spec)
-    idx = (np.arange(f.start, f.start + f.rows, dtype=np.int64) * 2654435761 % pool).astype(np.int64)
+    # row r of the table is pool image r % pool: a fragment is a handful of LONG contiguous runs of the pool, so filling
+    # it is a few large memcpys (measured: np.take of scattered 150 KB rows reaches only ~2-4 GB/s per process, which
+    # capped a scoring worker at ~27 k images/s - below what its GPU consumes)
+    idx = (np.arange(f.start, f.start + f.rows, dtype=np.int64) % pool)
     want = list(columns) if columns else ["path", "length", "content", "label", "label_idx"]
     cols = {}
     row_bytes = h * w * 3
@@ -87,7 +90,7 @@ def _synthetic_read(f: Fragment, columns, pinned_alloc) -> pa.Table:
         # Arrow binary column's data buffer without a copy - and later the source of the H2D copy
         buf = pinned_alloc(nbytes) if pinned_alloc is not None else np.empty(nbytes, dtype=np.uint8)
         view = buf[:nbytes].reshape(f.rows, row_bytes)
-        _parallel_take(imgs, idx, view)
+        _copy_runs(imgs, int(f.start % pool), view)
         offsets = (np.arange(f.rows + 1, dtype=np.int64) * row_bytes)
         if nbytes < 2 ** 31:
             arr = pa.Array.from_buffers(pa.binary(), f.rows, [None, pa.py_buffer(offsets.astype(np.int32)), pa.py_buffer(view)])
@@ -105,6 +108,32 @@ def _synthetic_read(f: Fragment, columns, pinned_alloc) -> pa.Table:
     if "length" in want:
         cols["length"] = pa.array(np.full(f.rows, row_bytes, dtype=np.int64))
     return pa.table({k: cols[k] for k in want if k in cols})
+
+
+def _copy_runs(pool_imgs: np.ndarray, first: int, out: np.ndarray) -> None:
+    """out[r] = pool_imgs[(first + r) % P] as contiguous block copies (numpy releases the GIL for them), a few in parallel."""
+    import concurrent.futures as cf
+
+    P, n = pool_imgs.shape[0], out.shape[0]
+    runs, r, src = [], 0, first
+    chunk = max(1, min(P, 64))  # <= 64 images (~10 MB at 224x224x3) per copy keeps several threads busy
+    while r < n:
+        k = min(chunk, P - src, n - r)
+        runs.append((r, src, k))
+        r += k
+        src = (src + k) % P
+    threads = int(os.environ.get("B200DDL_GEN_THREADS", "6"))
+
+    def do(run):
+        r0, s0, k = run
+        np.copyto(out[r0:r0 + k], pool_imgs[s0:s0 + k])
+
+    if threads > 1 and len(runs) > 1:
+        with cf.ThreadPoolExecutor(threads) as ex:
+            list(ex.map(do, runs))
+    else:
+        for run in runs:
+            do(run)
 
 
 def _parallel_take(src: np.ndarray, idx: np.ndarray, out: np.ndarray, threads: int = 4) -> None:

@@ -385,24 +385,23 @@ def _trial_worker(slot: int, conn) -> None:
 
 
 class _TrialProcessPool:
+    """`n` trial workers started as `python -m b200ddl.hpo._trial_worker` (utils/procpool.py explains why not mp.spawn)."""
+
     def __init__(self, n: int, fn: Callable):
-        import multiprocessing as mp
         import queue
 
         import cloudpickle
 
-        ctx = mp.get_context("spawn")
+        from ..utils.procpool import start_worker
+
         blob = cloudpickle.dumps(fn)
         self.procs, self.conns = [], []
         self.idle: "queue.Queue[int]" = queue.Queue()
         for i in range(n):
-            a, b = ctx.Pipe()
-            p = ctx.Process(target=_trial_worker, args=(i, b), daemon=True)
-            p.start()
-            b.close()
-            a.send(("fn", blob))
+            p, c = start_worker("b200ddl.hpo._trial_worker", i)
+            c.send(("fn", blob))
             self.procs.append(p)
-            self.conns.append(a)
+            self.conns.append(c)
             self.idle.put(i)
 
     def call(self, params, trial: dict):
@@ -418,7 +417,7 @@ class _TrialProcessPool:
             try:
                 msg = self.conns[i].recv()
             except EOFError:
-                raise RuntimeError(f"trial worker {i} died (exit code {self.procs[i].exitcode})") from None
+                raise RuntimeError(f"trial worker {i} died (exit code {self.procs[i].poll()})") from None
             if msg[0] == "ok":
                 return cloudpickle.loads(msg[1])
             raise RuntimeError(f"objective failed in trial worker {i}: {msg[1]}\n{msg[2]}")
@@ -433,8 +432,9 @@ class _TrialProcessPool:
             except Exception:
                 pass
         for p in self.procs:
-            p.join(timeout=10)
-            if p.is_alive():
+            try:
+                p.wait(timeout=10)
+            except Exception:
                 p.kill()
 
 

@@ -298,8 +298,9 @@ class ResNet50Engine:
         max_act = max(max_act, N * H0 * H0 * 64)
         if training:
             self._scr = {k: torch.zeros(max_act, **bf) for k in ("dy", "dyB", "da", "dds", "dzA", "dzB")}
+            # the downsample branch runs between bn1's backward and conv1's (whose dy sits in "dy"): always its own buffer
             self._dy_key = {"conv3": "dy", "conv2": "dyB" if self.overlap_wgrad else "dy", "conv1": "dy",
-                            "downsample.0": "dyB" if self.overlap_wgrad else "dy"}
+                            "downsample.0": "dyB"}
             self._dy_reader: Dict[str, torch.cuda.Event] = {}
             if self.overlap_wgrad:
                 self._wg_stream = torch.cuda.Stream(device=dev)

@@ -185,114 +185,138 @@ class _FragmentScorer:
                 yield pos, out
 
 
-def _pool_worker(rank: int, model_uri: str, tracking_uri: str, column: str, tasks, results) -> None:
-    """Persistent scoring process: pinned to GPU `rank`, model loaded ONCE, fragments pulled from a shared queue."""
+def _pool_worker(rank: int, conn) -> None:
+    """Persistent scoring process: pinned to GPU `rank`, model loaded ONCE; the driver keeps two fragments in flight per
+    worker so fragment k+1 is read while fragment k is scored."""
+    scorer = None
     try:
         from .. import tracking
 
+        _, model_uri, tracking_uri, column = conn.recv()
         tracking.set_tracking_uri(tracking_uri)
         scorer = _FragmentScorer(model_uri, column, rank)
-        results.put(("ready", rank, None))
+        conn.send(("ready", rank, None))
 
         def pull():
             while True:
-                item = tasks.get()
-                if item is None or item[0] == "end":
+                item = conn.recv()
+                if item is None:
+                    raise SystemExit(0)
+                if item[0] == "end":
                     return
                 yield item[1], item[2]
 
         while True:
-            # a job = a stream of ('frag', pos, fragment) items terminated by ('end',); None shuts the worker down
-            first = tasks.get()
-            if first is None:
-                return
-            if first[0] == "end":
-                results.put(("done", rank, {"read_s": scorer.read_s, "predict_s": scorer.predict_s}))
-                continue
-
-            def chain(first_item):
-                yield first_item[1], first_item[2]
-                yield from pull()
-
-            for pos, out in scorer.score(chain(first)):
-                results.put(("res", pos, out))
-            results.put(("done", rank, {"read_s": scorer.read_s, "predict_s": scorer.predict_s}))
+            # a job = a stream of ('frag', pos, fragment) messages terminated by ('end',); None shuts the worker down
+            for pos, out in scorer.score(pull()):
+                conn.send(("res", pos, out))
+            conn.send(("done", rank, {"read_s": scorer.read_s, "predict_s": scorer.predict_s}))
+    except (EOFError, SystemExit):
+        return
     except BaseException as ex:  # surface the failure instead of leaving the driver waiting
         import traceback
 
-        results.put(("error", rank, f"{type(ex).__name__}: {ex}\n{traceback.format_exc()}"))
+        try:
+            conn.send(("error", rank, f"{type(ex).__name__}: {ex}\n{traceback.format_exc()}"))
+        except Exception:
+            pass
 
 
 class _WorkerPool:
-    """One spawned process per GPU, alive for the life of the UDF (like a Spark executor's python worker)."""
+    """One scoring process per GPU (`python -m b200ddl.pyfunc._score_worker`), alive for the life of the UDF - like a
+    Spark executor's python worker.  Fragments are dispatched dynamically: every worker always has `depth` fragments
+    outstanding, a new one is sent as soon as a result comes back (load balancing without a shared queue)."""
 
-    def __init__(self, model_uri: str, column: str, workers: int):
-        import multiprocessing as mp
-
+    def __init__(self, model_uri: str, column: str, workers: int, depth: int = 2):
         from .. import tracking
+        from ..utils.procpool import start_worker
 
-        ctx = mp.get_context("spawn")
-        self.tasks = ctx.Queue()
-        self.results = ctx.Queue()
         self.column = column
-        self.procs = [ctx.Process(target=_pool_worker, args=(i, model_uri, tracking.get_tracking_uri(), column, self.tasks,
-                                                              self.results), daemon=True) for i in range(workers)]
-        for p in self.procs:
-            p.start()
-        ready = 0
-        while ready < workers:
-            kind, who, payload = self._get()
-            if kind == "ready":
-                ready += 1
+        self.depth = depth
+        self.procs, self.conns = [], []
+        for i in range(workers):
+            p, c = start_worker("b200ddl.pyfunc._score_worker", i)
+            c.send(("init", model_uri, tracking.get_tracking_uri(), column))
+            self.procs.append(p)
+            self.conns.append(c)
+        for i, c in enumerate(self.conns):
+            self._expect(i, "ready")
 
-    def _get(self, timeout: float = 1800.0):
-        import queue
-
+    def _recv(self, i: int, timeout: float = 1800.0):
+        c = self.conns[i]
         waited = 0.0
-        while True:
-            try:
-                item = self.results.get(timeout=2.0)
-            except queue.Empty:
-                waited += 2.0
-                dead = [p for p in self.procs if not p.is_alive()]
-                if dead and self.results.empty():
-                    raise RuntimeError(f"a scoring worker died (exit code {dead[0].exitcode})")
-                if waited > timeout:
-                    raise TimeoutError("scoring workers did not answer")
-                continue
-            if item[0] == "error":
-                raise RuntimeError(f"scoring worker {item[1]} failed:\n{item[2]}")
-            return item
+        while not c.poll(2.0):
+            waited += 2.0
+            if self.procs[i].poll() is not None and not c.poll(0):
+                raise RuntimeError(f"scoring worker {i} died (exit code {self.procs[i].poll()})")
+            if waited > timeout:
+                raise TimeoutError(f"scoring worker {i} did not answer")
+        try:
+            msg = c.recv()
+        except EOFError:
+            raise RuntimeError(f"scoring worker {i} died (exit code {self.procs[i].poll()})") from None
+        if msg[0] == "error":
+            raise RuntimeError(f"scoring worker {msg[1]} failed:\n{msg[2]}")
+        return msg
+
+    def _expect(self, i: int, kind: str):
+        msg = self._recv(i)
+        if msg[0] != kind:
+            raise RuntimeError(f"scoring worker {i}: expected {kind!r}, got {msg[0]!r}")
+        return msg
 
     def run(self, frags) -> Tuple[Dict[int, np.ndarray], List[dict]]:
-        n = len(self.procs)
-        for pos, f in enumerate(frags):
-            self.tasks.put(("frag", pos, f))
-        for _ in range(n):
-            self.tasks.put(("end",))
+        from multiprocessing.connection import wait
+
+        n = len(self.conns)
+        todo = list(enumerate(frags))[::-1]
         out: Dict[int, np.ndarray] = {}
         stats: List[dict] = []
+        ended = [False] * n
+
+        def feed(i: int) -> None:
+            if todo:
+                pos, f = todo.pop()
+                self.conns[i].send(("frag", pos, f))
+            elif not ended[i]:
+                self.conns[i].send(("end",))
+                ended[i] = True
+
+        for _ in range(self.depth):
+            for i in range(n):
+                feed(i)
         done = 0
         while done < n:
-            kind, a, b = self._get()
-            if kind == "res":
-                out[a] = b
-            elif kind == "done":
-                done += 1
-                stats.append({"worker": a, **b})
+            ready = wait(self.conns, timeout=5.0)
+            if not ready:
+                for i, p in enumerate(self.procs):
+                    if p.poll() is not None:
+                        raise RuntimeError(f"scoring worker {i} died (exit code {p.poll()})")
+                continue
+            for c in ready:
+                i = self.conns.index(c)
+                msg = self._recv(i)
+                if msg[0] == "res":
+                    out[msg[1]] = msg[2]
+                    feed(i)
+                elif msg[0] == "done":
+                    done += 1
+                    stats.append({"worker": msg[1], **msg[2]})
         return out, stats
 
     def close(self) -> None:
-        for _ in self.procs:
+        for c in self.conns:
             try:
-                self.tasks.put(None)
+                c.send(None)
+                c.close()
             except Exception:
                 pass
         for p in self.procs:
-            p.join(timeout=10)
-            if p.is_alive():
+            try:
+                p.wait(timeout=10)
+            except Exception:
                 p.kill()
-        self.procs = []
+        self.procs, self.conns = [], []
 
 
 class ShardUDFExpr:

@@ -63,7 +63,8 @@ search_space = {"optimizer": hp.choice("optimizer", ["Adadelta", "Adam"]),   # r
 
 tracking.set_experiment(f"/Users/{user}/distributed_dl_workshop")          # reference :221
 with tracking.start_run(run_name="hyperopt_tuning") as parent_run:
-    trials = ParallelTrials(parallelism=4)                                 # SparkTrials(parallelism=4), :226
+    # SparkTrials(parallelism=4), :226 - on a GPU box every slot is a worker PROCESS pinned to GPU slot % device_count
+    trials = ParallelTrials(parallelism=4, executor=os.environ.get("HPO_EXECUTOR", "auto"))
     best_hyperparam = fmin(fn=objective_function, space=search_space, algo=tpe.suggest, trials=trials,
                            max_evals=NUM_EVALS)
     tracking.log_params({"best_" + k: v for k, v in best_hyperparam.items()})

@@ -30,7 +30,9 @@ class FlowerPyFunc(pyfunc.PythonModel):                                    # ref
         with open(context.artifacts["img_params_dict_path"]) as f:
             d = json.load(f)
         self.img_height, self.img_width = d["img_height"], d["img_width"]
-        self.model = tracking.keras.load_model(context.artifacts["keras_model_path"])
+        # the serving batch may differ from the training batch (static-shape engine): WORKSHOP_INFER_BATCH, default = training's
+        self.model = tracking.keras.load_model(context.artifacts["keras_model_path"],
+                                               batch_size=int(os.environ.get("WORKSHOP_INFER_BATCH", "0")) or None)
 
     def preprocess(self, img_bytes):
         # ONE preprocessing for training and serving (the reference resizes with PIL and skips normalisation here,
