@@ -71,7 +71,6 @@ struct ConvPlan {
     p.taps = taps;
     p.kblocks = (int)(cin / 64);
     p.cout = (int)cout;
-    p.n_blocks = (int)(cout / raw.block_n);
     for (int t = 0; t < taps; ++t) {
       TORCH_CHECK(tap_map[t] >= 0 && tap_map[t] < (int64_t)views.size());
       p.tap_map[t] = (int8_t)tap_map[t];
@@ -111,6 +110,27 @@ struct ConvPlan {
       }
       raw.tmD = map_nhwc(out, 64, (int)bw, (int)bh, (int)bn);
     }
+    // Tile width: the widest N tile re-reads the A operand least, but a persistent grid of one CTA per SM pays for whole
+    // waves - e.g. 3x3 512->512 @7^2 at batch 256 is 98 M-tiles x 2 N-blocks = 196 tiles of 128x256 on 148 SMs = 2 waves at
+    // 66 % fill (ncu: tensor pipe 80 % busy, 59 us vs cuDNN 47), while 392 tiles of 128x128 fill 3 waves at 88 %.  The cost
+    // model is waves x tile width (the MMA time of a tile is proportional to its width); a narrower tile is taken only when
+    // it wins by >= 10 %.  B200DDL_BLOCK_N=256|128|64 forces a width (A/B measurements).
+    {
+      const int cap_ = max_ctas > 0 ? (int)max_ctas : sm_count();
+      auto cost = [&](int bn) {
+        const int64_t tiles = (int64_t)p.m_tiles * (cout / bn);
+        return ((tiles + cap_ - 1) / cap_) * bn;
+      };
+      int best = raw.block_n;
+      for (int bn = raw.block_n / 2; bn >= 64; bn /= 2)
+        if (cout % bn == 0 && cost(bn) * 10 <= cost(best) * 9) best = bn;
+      if (const char* f = std::getenv("B200DDL_BLOCK_N")) {
+        const int v = std::atoi(f);
+        if ((v == 256 || v == 128 || v == 64) && cout % v == 0) best = v;
+      }
+      raw.block_n = best;
+    }
+    p.n_blocks = (int)(cout / raw.block_n);
     raw.tmB = map_2d(weight.data_ptr(), taps * cout, cin, cin, 64, raw.block_n);
     p.num_tiles = p.m_tiles * p.n_blocks;
     raw.stats = stat_sum.has_value() ? (bwd_y.has_value() ? (relu_mask.has_value() ? 3 : 2) : 1) : 0;

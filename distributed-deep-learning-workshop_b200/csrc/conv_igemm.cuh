@@ -48,7 +48,8 @@ constexpr int kHaloRows = 224;  // largest halo box: bw * (bh + 2) pixels (56 x 
 
 template <int BLOCK_N, int kStats = 0, bool kResB = false, bool kHalo = false>
 struct ConvSmem {
-  static constexpr int kYBytes = kStats >= 2 ? 2 * kBlockM * 128 : 0;  // two 128x64 bf16 tiles of y
+  static constexpr int kYBufs = 4;  // pre-BN tiles are prefetched TWO output chunks ahead (see the epilogue)
+  static constexpr int kYBytes = kStats >= 2 ? kYBufs * kBlockM * 128 : 0;  // 128x64 bf16 tiles of y
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kASlot = kHalo ? kHaloRows * 128 : kABytes;     // bytes of A per pipeline stage
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -58,12 +59,13 @@ struct ConvSmem {
   static constexpr int kBarBytes = 256;
   static constexpr int kStatBytes = 2 * BLOCK_N * 4;
   static constexpr int kFixed = kResBytes + kStagingBytes + kYBytes + kBarBytes + kStatBytes;
-  static constexpr int kStages = kResB ? ((232448 - kFixed) / kStageBytes > 8 ? 8 : (232448 - kFixed) / kStageBytes)
-                                       : ((BLOCK_N == 256) ? (kStats >= 2 ? 3 : 4) : (BLOCK_N == 128 ? 5 : 6));
+  static constexpr int kFit = (232448 - kFixed) / kStageBytes;   // stages that fit beside the fixed buffers
+  static constexpr int kCap = kResB ? 8 : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 5 : 6));
+  static constexpr int kStages = kFit > kCap ? kCap : kFit;
   static constexpr int kTotal = kStages * kStageBytes + kFixed;
   static_assert(!kResB || BLOCK_N == 64, "resident filter: BLOCK_N == 64 only");
   static_assert(!kHalo || kResB, "halo mode builds on the resident filter");
-  static_assert(kStages >= 3 && 2 * kStages + 7 <= kBarBytes / 8, "pipeline depth / barrier area");
+  static_assert(kStages >= 2 && 2 * kStages + 9 <= kBarBytes / 8, "pipeline depth / barrier area");
   static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
 };
 
@@ -88,9 +90,9 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
   uint64_t* empty_bar = bars + kStages;          // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;      // [2]
   uint64_t* tempty_bar = bars + 2 * kStages + 2; // [2]
-  uint64_t* y_bar = bars + 2 * kStages + 4;      // [2] (kStats == 2)
-  uint64_t* bres_bar = bars + 2 * kStages + 6;   // resident filter loaded (kResB)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 7);
+  uint64_t* y_bar = bars + 2 * kStages + 4;      // [4] (kStats >= 2)
+  uint64_t* bres_bar = bars + 2 * kStages + 8;   // resident filter loaded (kResB)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 9);
   float* sStat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::kBarBytes);  // [2][BLOCK_N]
 
   // Provably warp-uniform (the compiler cannot see that threadIdx.x >> 5 is): together with elect.sync for the
@@ -109,8 +111,8 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
-      mbar_init(&y_bar[i], 1);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&y_bar[i], 1);
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
@@ -327,6 +329,34 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     int chunk_ctr = 0;
+    // kStats >= 2: the pre-BN tile of CTA-local output chunk g (tile g / kChunks of this CTA, 64-column chunk g % kChunks)
+    // is loaded into Y buffer g & 3 TWO chunks before it is needed.  Issuing it at the start of its own chunk (v1) put a
+    // full DRAM round trip on the epilogue <-> statistics hand-off chain of every chunk: ncu on the block-gradient kernel
+    // showed 44 % of the warp samples parked at named barriers and the kernel at 4.5 of 6.5 TB/s (profiles/ncu/).
+    // Buffer (g + 2) & 3 was last used by chunk g - 2, which the statistics warps have finished when the epilogue passes
+    // the "staging buffer g & 1 is free" barrier of chunk g.
+    auto issue_y = [&](int g) {
+      constexpr int kChunksE = BLOCK_N / 64;
+      const int lt = g / kChunksE, c = g - lt * kChunksE;
+      const int tl = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
+      if (tl >= p.num_tiles) return;
+      const int mt = tl / p.n_blocks, nbb = tl - mt * p.n_blocks;
+      const int b = g & 3;
+      mbar_arrive_expect_tx(&y_bar[b], static_cast<uint32_t>(p.valid_rows) * 128u);
+      if (p.mode == 0) {
+        tma_load_2d(sY + b * (kBlockM * 128), &tmY, &y_bar[b], nbb * BLOCK_N + c * 64, mt * kBlockM);
+      } else {
+        const int tw = mt % p.tiles_w;
+        const int rest = mt / p.tiles_w;
+        const int th = rest % p.tiles_h;
+        tma_load_4d(sY + b * (kBlockM * 128), &tmY, &y_bar[b], nbb * BLOCK_N + c * 64, tw * p.bw, th * p.bh,
+                    (rest / p.tiles_h) * p.bn);
+      }
+    };
+    if (kStats >= 2 && etid == 0) {
+      issue_y(0);
+      issue_y(1);
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_blocks;
       const int nb = tile - m_tile * p.n_blocks;
@@ -344,8 +374,8 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
       // accumulator wait, so the global-load latency hides behind the TMEM wait and the previous half's packing.
       const __nv_bfloat16* arow = nullptr;
       const uint8_t* mrow = nullptr;
-      uint4 gq[2][4];
-      uint32_t mq[2] = {0u, 0u};
+      uint4 gq[3][4];               // queue: [0] = current half, [1] = next, [2] = the one after (rotated by moves)
+      uint32_t mq[3] = {0u, 0u, 0u};
       if (kStats == 3) {
         const int64_t grow = static_cast<int64_t>(m_tile) * kBlockM + row;
         if (grow < p.m_rows) {
@@ -363,12 +393,17 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gq[0][j] = gq[1][j] = make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0; j < 4; ++j) gq[0][j] = gq[1][j] = gq[2][j] = make_uint4(0u, 0u, 0u, 0u);
         if (arow != nullptr) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) gq[0][j] = __ldg(reinterpret_cast<const uint4*>(arow) + j);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gq[1][j] = __ldg(reinterpret_cast<const uint4*>(arow + 32) + j);
         }
-        if (mrow != nullptr) mq[0] = __ldg(reinterpret_cast<const uint32_t*>(mrow));
+        if (mrow != nullptr) {
+          mq[0] = __ldg(reinterpret_cast<const uint32_t*>(mrow));
+          mq[1] = __ldg(reinterpret_cast<const uint32_t*>(mrow + 4));
+        }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -382,27 +417,19 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
           named_bar_sync(4 + (chunk_ctr & 1), 256);  // ... and the statistics warps are done reading it
         else
           named_bar_sync(1, 128);
-        if (kStats >= 2 && etid == 0) {
-          // pre-BN tensor tile for the fused BatchNorm-backward reduction (same pixels / channels as the output tile)
-          const int b = chunk_ctr & 1;
-          mbar_arrive_expect_tx(&y_bar[b], static_cast<uint32_t>(p.valid_rows) * 128u);
-          if (p.mode == 0)
-            tma_load_2d(sY + b * (kBlockM * 128), &tmY, &y_bar[b], nb * BLOCK_N + c64 * 64, m_tile * kBlockM);
-          else
-            tma_load_4d(sY + b * (kBlockM * 128), &tmY, &y_bar[b], nb * BLOCK_N + c64 * 64, w0, h0, n0);
-        }
+        if (kStats >= 2 && etid == 0) issue_y(chunk_ctr + 2);  // pre-BN tile two chunks ahead (see issue_y)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t r[32];
           if (kStats == 3) {
-            // prefetch the next half (h ^ 1 of this chunk or h = 0 of the next chunk) into the other slot
-            const int nxt = c64 * 64 + h * 32 + 32;
+            // prefetch the half after next (two 32-column halves = 128 B per thread stay in flight)
+            const int nxt = c64 * 64 + h * 32 + 64;
             if (nxt < BLOCK_N) {
               if (arow != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) gq[h ^ 1][j] = __ldg(reinterpret_cast<const uint4*>(arow + nxt) + j);
+                for (int j = 0; j < 4; ++j) gq[2][j] = __ldg(reinterpret_cast<const uint4*>(arow + nxt) + j);
               }
-              if (mrow != nullptr) mq[h ^ 1] = __ldg(reinterpret_cast<const uint32_t*>(mrow + (nxt >> 3)));
+              if (mrow != nullptr) mq[2] = __ldg(reinterpret_cast<const uint32_t*>(mrow + (nxt >> 3)));
             }
           }
           tmem_ld_32x32b_x32(taddr + c64 * 64 + h * 32, r);
@@ -411,15 +438,23 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
             // dz = (main-path gradient + skip gradient) * [block output > 0]
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t gw[4] = {gq[h][j].x, gq[h][j].y, gq[h][j].z, gq[h][j].w};
+              const uint32_t gw[4] = {gq[0][j].x, gq[0][j].y, gq[0][j].z, gq[0][j].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float lo = __uint_as_float(r[8 * j + 2 * e]) + __uint_as_float(gw[e] << 16);
                 const float hi = __uint_as_float(r[8 * j + 2 * e + 1]) + __uint_as_float(gw[e] & 0xFFFF0000u);
-                r[8 * j + 2 * e] = ((mq[h] >> (8 * j + 2 * e)) & 1u) ? __float_as_uint(lo) : 0u;
-                r[8 * j + 2 * e + 1] = ((mq[h] >> (8 * j + 2 * e + 1)) & 1u) ? __float_as_uint(hi) : 0u;
+                r[8 * j + 2 * e] = ((mq[0] >> (8 * j + 2 * e)) & 1u) ? __float_as_uint(lo) : 0u;
+                r[8 * j + 2 * e + 1] = ((mq[0] >> (8 * j + 2 * e + 1)) & 1u) ? __float_as_uint(hi) : 0u;
               }
             }
+            // rotate the queue
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              gq[0][j] = gq[1][j];
+              gq[1][j] = gq[2][j];
+            }
+            mq[0] = mq[1];
+            mq[1] = mq[2];
           }
           if (c64 == BLOCK_N / 64 - 1 && h == 1) {
             // all TMEM reads of this accumulator are done: hand it back to the MMA warp
@@ -499,8 +534,8 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
           }
         } else if (kStats == 3) {
           // the staged tile already is dz (merged + masked by the epilogue): accumulate sum(dz) and sum(dz * y)
-          const uint8_t* ybuf = sY + b * (kBlockM * 128);
-          mbar_wait(&y_bar[b], (chunk_ctr >> 1) & 1);
+          const uint8_t* ybuf = sY + (chunk_ctr & 3) * (kBlockM * 128);
+          mbar_wait(&y_bar[chunk_ctr & 3], (chunk_ctr >> 2) & 1);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + xoff[i & 7] + i * 128);
@@ -517,8 +552,8 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
           const int col = nb * BLOCK_N + c64 * 64 + cp * 2;
           const float sc0 = p.bn_scale[col], sc1 = p.bn_scale[col + 1];
           const float sh0 = p.bn_shift[col], sh1 = p.bn_shift[col + 1];
-          const uint8_t* ybuf = sY + b * (kBlockM * 128);
-          mbar_wait(&y_bar[b], (chunk_ctr >> 1) & 1);
+          const uint8_t* ybuf = sY + (chunk_ctr & 3) * (kBlockM * 128);
+          mbar_wait(&y_bar[chunk_ctr & 3], (chunk_ctr >> 2) & 1);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + xoff[i & 7] + i * 128);

@@ -785,7 +785,9 @@ void preprocess_u8(const uint8_t* x, void* out, int64_t npix, int cpad, float mu
   preprocess_u8_kernel<<<grid_for(npix, 256), 256, 0, s>>>(x, (__nv_bfloat16*)out, npix, cpad, mul, add);
 }
 
-// Bilinear resize (half-pixel centres, like tf.image.resize) of one uint8 HWC image batch to [N, OH, OW, 3] uint8.
+// Bilinear resize (half-pixel centres, like tf.image.resize) of one uint8 image batch to [N, OH, OW, 3] uint8 (HWC).
+// PLANAR: the input is [N, 3, H, W] (what nvJPEG / torchvision.io.decode_jpeg produce), otherwise [N, H, W, 3].
+template <bool PLANAR>
 __global__ void resize_bilinear_u8_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ out, int N, int H,
                                           int W, int OH, int OW) {
   const int64_t total = (int64_t)N * OH * OW;
@@ -803,15 +805,25 @@ __global__ void resize_bilinear_u8_kernel(const uint8_t* __restrict__ x, uint8_t
     const uint8_t* b = x + (int64_t)n * H * W * 3;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float v00 = b[((int64_t)y0 * W + x0) * 3 + c], v01 = b[((int64_t)y0 * W + x1) * 3 + c];
-      const float v10 = b[((int64_t)y1 * W + x0) * 3 + c], v11 = b[((int64_t)y1 * W + x1) * 3 + c];
+      float v00, v01, v10, v11;
+      if (PLANAR) {
+        const uint8_t* pc = b + (int64_t)c * H * W;
+        v00 = pc[(int64_t)y0 * W + x0]; v01 = pc[(int64_t)y0 * W + x1];
+        v10 = pc[(int64_t)y1 * W + x0]; v11 = pc[(int64_t)y1 * W + x1];
+      } else {
+        v00 = b[((int64_t)y0 * W + x0) * 3 + c]; v01 = b[((int64_t)y0 * W + x1) * 3 + c];
+        v10 = b[((int64_t)y1 * W + x0) * 3 + c]; v11 = b[((int64_t)y1 * W + x1) * 3 + c];
+      }
       const float v = (v00 * (1 - wx) + v01 * wx) * (1 - wy) + (v10 * (1 - wx) + v11 * wx) * wy;
       out[i * 3 + c] = (uint8_t)fminf(fmaxf(v + 0.5f, 0.f), 255.f);
     }
   }
 }
-void resize_bilinear_u8(const uint8_t* x, uint8_t* out, int N, int H, int W, int OH, int OW, cudaStream_t s) {
-  resize_bilinear_u8_kernel<<<grid_for((int64_t)N * OH * OW, 256), 256, 0, s>>>(x, out, N, H, W, OH, OW);
+void resize_bilinear_u8(const uint8_t* x, uint8_t* out, int N, int H, int W, int OH, int OW, bool planar, cudaStream_t s) {
+  if (planar)
+    resize_bilinear_u8_kernel<true><<<grid_for((int64_t)N * OH * OW, 256), 256, 0, s>>>(x, out, N, H, W, OH, OW);
+  else
+    resize_bilinear_u8_kernel<false><<<grid_for((int64_t)N * OH * OW, 256), 256, 0, s>>>(x, out, N, H, W, OH, OW);
 }
 
 // ------------------------------------------------------------------------------------------------ weight layouts

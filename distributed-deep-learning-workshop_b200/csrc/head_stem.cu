@@ -191,20 +191,38 @@ stem_pool_bn_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __
       const int ci = cls >> 1, cj = cls & 1;
       const int nwj = (kPoolWin - 1 - cj) / 2 + 1;
       const int items = ((kPoolWin - 1 - ci) / 2 + 1) * nwj * 2;
-#pragma unroll 2
-      for (int it = warp; it < items; it += 8) {
-        const int w = it >> 1;
-        const int wi = ci + 2 * (w / nwj), wj = cj + 2 * (w % nwj);
-        const int ho = a0 + wi, wo = b0 + wj;
-        if (ho >= Ho || wo >= Wo) continue;  // warp-uniform
-        const int ch = (it & 1) * 32 + lane;
-        const int64_t o = ((((int64_t)n * Ho + ho) * Wo + wo) * C) + ch;
-        const int a = idx[o];
-        float g = __bfloat162float(g1[o]);
-        if (g2 != nullptr) g += __bfloat162float(g2[o]);
-        const int r = (a * 11) >> 5;  // a / 3 for a in 0..8
-        const int row = 2 * wi - 1 + r, col = 2 * wj - 1 + (a - 3 * r);
-        if (static_cast<unsigned>(row) < 16u && static_cast<unsigned>(col) < 16u) da[(row * 16 + col) * C + ch] += g;
+      // A warp owns at most kMaxIt = 7 (window, half) items of a class (<= 25 windows x 2 halves over 8 warps): ALL their
+      // global loads are issued before the first read-modify-write, so ~7 x 5 bytes per lane are in flight instead of one
+      // item's (v2a: ncu 58 % long-scoreboard stalls in this loop, 16 % DRAM throughput).
+      constexpr int kMaxIt = 7;
+      int a_[kMaxIt];   // bits 0-7 argmax position, 8-15 wi, 16-23 wj, bit 30 = item present
+      float g_[kMaxIt];
+      const int ch = (warp & 1) * 32 + lane;  // it = warp + 8q: the channel half of all of a warp's items is warp & 1
+#pragma unroll
+      for (int q = 0; q < kMaxIt; ++q) {
+        const int it = warp + 8 * q;
+        a_[q] = 0;
+        g_[q] = 0.f;
+        if (it < items) {
+          const int w = it >> 1;
+          const int wi = ci + 2 * (w / nwj), wj = cj + 2 * (w % nwj);
+          const int ho = a0 + wi, wo = b0 + wj;
+          if (ho < Ho && wo < Wo) {  // warp-uniform
+            const int64_t o = ((((int64_t)n * Ho + ho) * Wo + wo) * C) + ch;
+            a_[q] = static_cast<int>(idx[o]) | (wi << 8) | (wj << 16) | (1 << 30);
+            g_[q] = __bfloat162float(g1[o]);
+            if (g2 != nullptr) g_[q] += __bfloat162float(g2[o]);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kMaxIt; ++q) {
+        if (a_[q] != 0) {
+          const int a = a_[q] & 0xFF, wi = (a_[q] >> 8) & 0xFF, wj = (a_[q] >> 16) & 0xFF;
+          const int r = (a * 11) >> 5;  // a / 3 for a in 0..8
+          const int row = 2 * wi - 1 + r, col = 2 * wj - 1 + (a - 3 * r);
+          if (static_cast<unsigned>(row) < 16u && static_cast<unsigned>(col) < 16u) da[(row * 16 + col) * C + ch] += g_[q];
+        }
       }
       __syncthreads();
     }

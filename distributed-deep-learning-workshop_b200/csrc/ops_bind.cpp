@@ -280,11 +280,15 @@ void preprocess_u8(Tensor x, Tensor out, double mul, double add) {
   b200::preprocess_u8(x.data_ptr<uint8_t>(), out.data_ptr(), x.numel() / 3, (int)out.size(-1), (float)mul, (float)add, cur());
   after();
 }
-void resize_bilinear_u8(Tensor x, Tensor out) {
+// x: uint8 [N, H, W, 3] (planar = false) or [N, 3, H, W] (planar = true, the nvJPEG layout);  out: uint8 [N, OH, OW, 3]
+void resize_bilinear_u8(Tensor x, Tensor out, bool planar) {
   chk(x, at::kByte, "x");
   chk(out, at::kByte, "out");
-  b200::resize_bilinear_u8(x.data_ptr<uint8_t>(), out.data_ptr<uint8_t>(), (int)x.size(0), (int)x.size(1),
-                           (int)x.size(2), (int)out.size(1), (int)out.size(2), cur());
+  TORCH_CHECK(x.dim() == 4 && out.dim() == 4 && out.size(3) == 3 && x.size(0) == out.size(0));
+  TORCH_CHECK(planar ? x.size(1) == 3 : x.size(3) == 3, "resize_bilinear_u8: 3-channel images");
+  const int H = (int)(planar ? x.size(2) : x.size(1)), W = (int)(planar ? x.size(3) : x.size(2));
+  b200::resize_bilinear_u8(x.data_ptr<uint8_t>(), out.data_ptr<uint8_t>(), (int)x.size(0), H, W, (int)out.size(1),
+                           (int)out.size(2), planar, cur());
   after();
 }
 void weight_prep(Tensor w, OptT wf, OptT wd, int64_t taps, int64_t cout, int64_t cin) {
@@ -365,7 +369,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("cC") = c10::nullopt, py::arg("dy") = c10::nullopt, py::arg("sum_dz"), py::arg("sum_dzy"));
   m.def("zero_", &zero_);
   m.def("preprocess_u8", &preprocess_u8);
-  m.def("resize_bilinear_u8", &resize_bilinear_u8);
+  m.def("resize_bilinear_u8", &resize_bilinear_u8, py::arg("x"), py::arg("out"), py::arg("planar") = false);
   m.def("weight_prep", &weight_prep);
   m.def("weight_prep_batched", &weight_prep_batched);
   m.def("sgd_step", &sgd_step);
