@@ -104,8 +104,11 @@ def run_baseline_child(args, rank: int, world: int):
     arm has finished; the child samples its own clocks during its timed region.  Returns rank 0's parsed JSON line.
     First attempt captures the step in a CUDA graph; if that child fails, one retry without the graph."""
     script = os.path.join(ROOT, "baseline", "torch_resnet50.py")
-    env = dict(os.environ)
+    # torchrun's variables must not leak into the children: with TORCHELASTIC_USE_AGENT_STORE=True, init_process_group
+    # would look for the AGENT's TCPStore on our new port (nobody serves one there) and wait for its timeout
+    env = {k: v for k, v in os.environ.items() if not k.startswith(("TORCHELASTIC_", "TORCH_NCCL_ASYNC", "GROUP_", "ROLE_"))}
     env["RANK"], env["WORLD_SIZE"] = str(rank), str(world)
+    env["LOCAL_WORLD_SIZE"] = str(world)
     env["LOCAL_RANK"] = os.environ.get("LOCAL_RANK", str(rank))
     env.setdefault("MASTER_ADDR", "127.0.0.1")
     base_port = int(os.environ.get("MASTER_PORT", "29500"))
@@ -192,7 +195,7 @@ def main():
     ap.add_argument("--wgrad-smem", type=int, default=0)
     ap.add_argument("--fused-update", action="store_true", help="all-reduce + SGD + weight multicast in one kernel")
     ap.add_argument("--no-baseline", action="store_true", help="skip the same-lease torch+cuDNN+NCCL baseline child")
-    ap.add_argument("--baseline-timeout", type=int, default=420)
+    ap.add_argument("--baseline-timeout", type=int, default=300)
     ap.add_argument("--no-block-grad", action="store_true", help="A/B: block-gradient merge as separate reduce passes")
     ap.add_argument("--stem-bwd-fuse", action="store_true", help="A/B (opt-in): max-pool backward fused with the stem-BN backward")
     args = ap.parse_args()
@@ -300,10 +303,18 @@ def main():
     cfg_flags = {"fuse_block_grad": bool(engine.fuse_block_grad), "fuse_stem_bwd": bool(engine.fuse_stem_bwd)}
     # ---------------------------------------------------------------- same-lease baseline (torch + cuDNN + NCCL)
     baseline = None
+    algo_used = getattr(opt, "algo", "none") if world > 1 else "none"
+    fused_used = bool(getattr(opt, "fused_update", False))
+    # release the CUDA graph (it may hold captured NCCL work with --algo nccl), the engine and the symmetric buffers BEFORE
+    # the process group goes away, then the group itself
+    del trainer, step, engine, opt, base_opt
+    import gc
+
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    dist.shutdown()
     if not args.no_baseline:
-        dist.shutdown()  # our process group / symmetric memory are released before the children start theirs
-        del trainer, step, engine
-        torch.cuda.empty_cache()
         baseline = run_baseline_child(args, rank, world)
     if rank == 0:
         vs = None
@@ -323,8 +334,8 @@ def main():
             "impl": "b200ddl",
             "config": {"model": "resnet50", "global_batch": global_batch, "per_gpu_batch": args.batch,
                        "image": "224x224x3", "classes": args.classes, "parallelism": f"dp{world}",
-                       "optimizer": args.optimizer, "allreduce": getattr(opt, "algo", "none") if world > 1 else "none",
-                       "fused_allreduce_sgd": bool(getattr(opt, "fused_update", False)),
+                       "optimizer": args.optimizer, "allreduce": algo_used,
+                       "fused_allreduce_sgd": fused_used,
                        "cuda_graph": not args.no_graph, "overlap_wgrad": not args.no_overlap_wgrad, **cfg_flags,
                        "l2": "activations per step are several GB (>> 126 MB L2); no explicit flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),

@@ -51,6 +51,8 @@ def main():
     ap.add_argument("--medium", action="store_true", help="1 KB, 64 KB, 1 MB, 16 MB, 128 MB, 1 GB")
     ap.add_argument("--max-mb", type=float, default=1024.0)
     ap.add_argument("--out", default="gpurun_out")
+    ap.add_argument("--f32-only", action="store_true", help="sweep the fp32 payload only (the gradient dtype)")
+    ap.add_argument("--skip-extras", action="store_true", help="no broadcast / CTA sweep / DistributedOptimizer sections")
     args = ap.parse_args()
     hvd.init()
     rank, world = hvd.rank(), hvd.size()
@@ -70,7 +72,7 @@ def main():
     ok_all = True
     rows = []
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    for dtype, name, esz in ((torch.float32, "f32", 4), (torch.bfloat16, "bf16", 2)):
+    for dtype, name, esz in (((torch.float32, "f32", 4),) if args.f32_only else ((torch.float32, "f32", 4), (torch.bfloat16, "bf16", 2))):
         view = buf.tensor.view(dtype)
         for nbytes in sizes:
             n = nbytes // esz

@@ -873,6 +873,167 @@ def case_big_numerics():
     return ok
 
 
+
+def case_fused_infer():
+    """Inference epilogue (conv_igemm kStats = 4): y = act(conv * scale + shift [+ residual]) vs fp32, on flat / box / halo /
+    strided plans; then the inference-built ResNet-50 engine (no BatchNorm passes) vs the training-built engine's eval path."""
+    ok = True
+    g = torch.Generator(device=DEV).manual_seed(41)
+    for name, N, H, W, cin, cout, R, stride, pad in CONV_SHAPES + [("bench_s1_1x1_64_256_b256", 256, 56, 56, 64, 256, 1, 1, 0)]:
+        try:
+            x, w, Ho, Wo = make_conv_case(N, H, W, cin, cout, R, stride, pad)
+            w16 = w.to(torch.bfloat16)
+            wk = w16.reshape(R * R * cout, cin).contiguous()
+            scale = torch.rand(cout, device=DEV, generator=g) + 0.5
+            shift = torch.randn(cout, device=DEV, generator=g) * 0.5
+            ref = C.conv_reference(x, w16, R, R, stride, pad) * scale + shift
+            flat = (R == 1 and stride == 1)
+            for act in ("relu", "relu6", "none"):
+                res = torch.randn(N, Ho, Wo, cout, device=DEV, generator=g).to(torch.bfloat16) if (flat and act != "relu6") else None
+                y = torch.full((N, Ho, Wo, cout), 9.0, device=DEV, dtype=torch.bfloat16)
+                op = C.ConvForward(x, wk, y, R, R, stride, pad, epilogue=(scale, shift, act, res))
+                op.run()
+                torch.cuda.synchronize()
+                r = ref + (res.float() if res is not None else 0.0)
+                r = torch.relu(r) if act == "relu" else (r.clamp(0, 6) if act == "relu6" else r)
+                ok &= report(f"fused_infer_conv/{name}/{act}{'+res' if res is not None else ''}", rel_err(y, r), 1.5e-2,
+                             f"box={op.box} bn={op.plan.block_n} halo={op.plan.halo}")
+        except Exception:
+            ok = False
+            print(f"CHECK fused_infer_conv/{name} EXCEPTION FAIL\n{traceback.format_exc()}", flush=True)
+    # engine level: same weights / running statistics, inference build (fused epilogues) vs training build (eval mode)
+    from b200ddl.models.resnet_engine import EngineEvalStep, ResNet50Engine
+    N, K = 32, 10
+    ref_eng = ResNet50Engine(batch=N, num_classes=K, zero_init_residual=False, seed=3)
+    ref_eng.bind_grad_buffer()
+    ref_eng.build(training=True)
+    for n_ in ref_eng.bn_names:   # non-trivial running statistics
+        ref_eng.running_mean[n_].copy_(torch.randn(ref_eng.bn_channels[n_], device=DEV, generator=g) * 0.1)
+        ref_eng.running_var[n_].copy_(torch.rand(ref_eng.bn_channels[n_], device=DEV, generator=g) + 0.5)
+    sd = ref_eng.state_dict()
+    inf = ResNet50Engine(batch=N, num_classes=K, zero_init_residual=False, seed=99)
+    inf.load_state_dict(sd)
+    inf.build(training=False)
+    xs = torch.randint(0, 256, (N, 224, 224, 3), device=DEV, dtype=torch.uint8, generator=g)
+    ys = torch.randint(0, K, (N,), device=DEV, generator=g)
+    ref_eng.set_input(xs, ys); inf.set_input(xs, ys)
+    ref_eng.forward(training=False)
+    ev = EngineEvalStep(inf)
+    ev.run(); ev.run()
+    torch.cuda.synchronize()
+    print(f"INFO fused inference engine: infer_fused={inf._infer_fused} launches={len(inf._fwd)} conv plans", flush=True)
+    ok &= report("fused_infer_engine/logits", rel_err(inf.logits, ref_eng.logits), 3e-2)
+    ok &= report("fused_infer_engine/argmax_agree", 1.0 - float((inf.logits.argmax(1) == ref_eng.logits.argmax(1)).float().mean()), 0.1)
+    # throughput of the two eval paths at the serving batch
+    for label, build_training in (("bn_passes", True), ("fused_epilogues", False)):
+        e2 = ResNet50Engine(batch=256, num_classes=1000, seed=5)
+        if build_training:
+            e2.bind_grad_buffer()
+        e2.build(training=build_training)
+        st = EngineEvalStep(e2)
+        t = time_fn(st.run, iters=10, warmup=3)
+        print(f"TIME eval_forward/{label} batch 256: {t*1e3:.0f} us = {256 / t:.0f} images/s", flush=True)
+        del e2, st
+        torch.cuda.empty_cache()
+    return ok
+
+
+
+def case_mobilenet():
+    """The reference's own model on native kernels: depthwise / stem kernels vs torch, then the whole frozen-base
+    MobileNetV2 engine (tcgen05 pointwise convs with folded-BN epilogues) vs the torch.nn module with the same weights."""
+    ok = True
+    e = ops.ext("_b200_ops")
+    g = torch.Generator(device=DEV).manual_seed(51)
+    # depthwise 3x3 + affine + relu6
+    for (N, H, C_, stride) in ((2, 14, 64, 1), (3, 28, 192, 2), (2, 7, 960, 1)):
+        x = torch.randn(N, H, H, C_, device=DEV, generator=g).to(torch.bfloat16)
+        w = torch.randn(9, C_, device=DEV, generator=g) * 0.3
+        sc = torch.rand(C_, device=DEV, generator=g) + 0.5
+        sh = torch.randn(C_, device=DEV, generator=g) * 0.5
+        Ho = (H - 1) // stride + 1
+        out = torch.empty(N, Ho, Ho, C_, device=DEV, dtype=torch.bfloat16)
+        e.dwconv3x3(x, w, sc, sh, out, stride)
+        wt = w.t().reshape(C_, 1, 3, 3)
+        ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt, stride=stride, padding=1, groups=C_)
+        ref = (ref * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).clamp(0, 6).permute(0, 2, 3, 1)
+        ok &= report(f"dwconv3x3/N{N}_H{H}_C{C_}_s{stride}", rel_err(out, ref), 1e-2)
+    # stem 3x3/2 from uint8
+    xs = torch.randint(0, 256, (3, 64, 64, 3), device=DEV, dtype=torch.uint8, generator=g)
+    wst = torch.randn(32, 3, 3, 3, device=DEV, generator=g) * 0.2
+    sc = torch.rand(32, device=DEV, generator=g) + 0.5
+    sh = torch.randn(32, device=DEV, generator=g) * 0.5
+    out = torch.zeros(3, 32, 32, 64, device=DEV, dtype=torch.bfloat16)
+    e.mbv2_stem(xs, wst.permute(2, 3, 1, 0).reshape(27, 32).contiguous(), sc, sh, out, 1.0 / 127.5, -1.0)
+    xin = (xs.float() / 127.5 - 1.0).to(torch.bfloat16).float().permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(xin, wst, stride=2, padding=1)
+    ref = (ref * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).clamp(0, 6).permute(0, 2, 3, 1)
+    ok &= report("mbv2_stem", rel_err(out[..., :32], ref), 1e-2)
+    ok &= report("mbv2_stem_padding_untouched", float(out[..., 32:].float().abs().max()), 0.0)
+    # whole model vs the torch module (fp32) with identical weights
+    from b200ddl.models import build_model
+    from b200ddl.models.mobilenet_engine import MobileNetV2Engine
+    N, K = 16, 5
+    eng = build_model(224, 224, 3, K, dropout=0.0, arch="mobilenetv2", batch_size=N, seed=3)
+    assert isinstance(eng, MobileNetV2Engine), type(eng)
+    ref = build_model(224, 224, 3, K, dropout=0.0, arch="mobilenetv2_torch", seed=3).to(DEV)
+    # non-trivial BatchNorm statistics / affine so the folded epilogues are really exercised
+    with torch.no_grad():
+        for m in ref.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.num_features, device=DEV, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, device=DEV, generator=g) * 0.5 + 0.75)
+                m.weight.copy_(torch.rand(m.num_features, device=DEV, generator=g) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(m.num_features, device=DEV, generator=g) * 0.1)
+    eng.load_state_dict(ref.state_dict())
+    eng.bind_grad_buffer()
+    eng.build(training=True)
+    x = torch.randint(0, 256, (N, 224, 224, 3), device=DEV, dtype=torch.uint8, generator=g)
+    y = torch.randint(0, K, (N,), device=DEV, generator=g)
+    eng.set_input(x, y)
+    eng.forward(training=True)
+    eng.backward()
+    torch.cuda.synchronize()
+    ref.train()
+    logits = ref((x.permute(0, 3, 1, 2).float() / 127.5 - 1.0))
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    feat_ref = ref.base((x.permute(0, 3, 1, 2).float() / 127.5 - 1.0)).mean(dim=(2, 3))
+    ok &= report("mobilenet_engine/features", rel_err(eng.pooled, feat_ref), 6e-2, f"launches per forward ~{len(eng._plan) + 4}")
+    ok &= report("mobilenet_engine/logits", rel_err(eng.logits, logits), 6e-2)
+    le, _ = eng.loss_and_acc()
+    ok &= report("mobilenet_engine/loss", abs(le - loss.item()) / abs(loss.item()), 3e-2, f"engine={le:.4f} torch={loss.item():.4f}")
+    gw = eng.g("fc.weight")[:K]
+    cos = torch.nn.functional.cosine_similarity(gw.flatten(), ref.fc.weight.grad.flatten(), dim=0).item()
+    ok &= report("mobilenet_engine/fc_wgrad_cos", 1 - cos, 2e-2)
+    ok &= report("mobilenet_engine/fc_bgrad", rel_err(eng.g("fc.bias"), ref.fc.bias.grad), 3e-2)
+    ok &= report("mobilenet_engine/param_counts", float(eng.trainable_parameters() != 6405) + float(eng.num_parameters() != 2230277), 0.0)
+    # through the public API: Trainer.fit on the engine (graph step), loss goes down on a fixed batch; throughput
+    from b200ddl import optim
+    from b200ddl.train import Trainer
+    eng2 = build_model(224, 224, 3, K, dropout=0.0, arch="mobilenetv2", batch_size=64, seed=4)
+    tr = Trainer(eng2).compile(optimizer=optim.Adam(0.01), loss="sparse_categorical_crossentropy", metrics=["accuracy"])
+    xb = torch.randint(0, 256, (64, 224, 224, 3), device=DEV, dtype=torch.uint8, generator=g)
+    yb = torch.randint(0, K, (64,), device=DEV, generator=g)
+    hist = tr.fit([(xb, yb)] * 30, steps_per_epoch=30, epochs=2, verbose=0)
+    ok &= report("mobilenet_engine/fit_loss_decreases", float(hist.history["loss"][-1] >= hist.history["loss"][0]), 0.0,
+                 f"{hist.history['loss'][0]:.3f} -> {hist.history['loss'][-1]:.3f}")
+    step = tr.backend.step
+    t = time_fn(step.run, iters=10, warmup=3)
+    print(f"TIME mobilenet_engine train step batch 64: {t*1e3:.0f} us = {64 / t:.0f} images/s", flush=True)
+    import time as _t
+    refm = build_model(224, 224, 3, K, dropout=0.0, arch="mobilenetv2_torch", seed=4).to(DEV)
+    tr2 = Trainer(refm, device=DEV).compile(optimizer=optim.Adam(0.01))
+    for _ in range(3):
+        tr2.backend.train_batch(xb, yb)
+    torch.cuda.synchronize(); t0 = _t.perf_counter()
+    for _ in range(10):
+        tr2.backend.train_batch(xb, yb)
+    torch.cuda.synchronize(); dt = (_t.perf_counter() - t0) / 10
+    print(f"TIME mobilenet torch.nn module (eager, fp32) train step batch 64: {dt*1e6:.0f} us = {64 / dt:.0f} images/s", flush=True)
+    return ok
+
+
 def case_umma_probe():
     """Row-shifted SWIZZLE_128B descriptors: which (shift, base_offset) combinations read the right rows?"""
     ext = ops.ext("_b200_probe")
@@ -964,6 +1125,8 @@ CASES = {
     "head": case_head,
     "stem_bwd": case_stem_bwd,
     "big_numerics": case_big_numerics,
+    "fused_infer": case_fused_infer,
+    "mobilenet": case_mobilenet,
     "engine_unfused_block_grad": lambda: case_engine(quick=True, fuse_block_grad=False),
     "umma_probe": case_umma_probe,
 }

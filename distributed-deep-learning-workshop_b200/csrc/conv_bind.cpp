@@ -51,7 +51,8 @@ struct ConvPlan {
            std::vector<int64_t> tap_dw, std::vector<int64_t> tap_dh, int64_t bw, int64_t bh, int64_t bn,
            c10::optional<at::Tensor> stat_sum, c10::optional<at::Tensor> stat_sqsum, int64_t max_ctas,
            c10::optional<at::Tensor> bwd_y, c10::optional<at::Tensor> bn_scale, c10::optional<at::Tensor> bn_shift,
-           c10::optional<at::Tensor> add_src, c10::optional<at::Tensor> relu_mask) {
+           c10::optional<at::Tensor> add_src, c10::optional<at::Tensor> relu_mask, c10::optional<at::Tensor> ep_scale,
+           c10::optional<at::Tensor> ep_shift, int64_t ep_act) {
     TORCH_CHECK(!views.empty() && views.size() <= 4, "1..4 input views");
     for (auto& v : views) check_nhwc_view(v, "input view");
     check_nhwc_view(out, "out");
@@ -133,7 +134,7 @@ struct ConvPlan {
     p.n_blocks = (int)(cout / raw.block_n);
     raw.tmB = map_2d(weight.data_ptr(), taps * cout, cin, cin, 64, raw.block_n);
     p.num_tiles = p.m_tiles * p.n_blocks;
-    raw.stats = stat_sum.has_value() ? (bwd_y.has_value() ? (relu_mask.has_value() ? 3 : 2) : 1) : 0;
+    raw.stats = stat_sum.has_value() ? (bwd_y.has_value() ? (relu_mask.has_value() ? 3 : 2) : 1) : (ep_scale.has_value() ? 4 : 0);
     p.m_rows = N * Ho * Wo;
     // Resident filter: one N-block of 64 channels whose taps * kblocks filter tiles (8 KB each) fit in 72 KB.
     // B200DDL_NO_RESIDENT_FILTER=1 switches it off (A/B measurements).
@@ -202,6 +203,26 @@ struct ConvPlan {
       keep.push_back(*add_src);
       keep.push_back(*relu_mask);
     }
+    if (raw.stats == 4) {
+      // inference epilogue: out = act(acc * scale[c] + shift[c] [+ residual]); the residual needs a flat (dense 1x1) plan
+      TORCH_CHECK(ep_shift.has_value() && ep_scale->is_cuda() && ep_scale->scalar_type() == at::kFloat &&
+                      ep_shift->scalar_type() == at::kFloat && ep_scale->numel() >= cout && ep_shift->numel() >= cout &&
+                      ep_scale->is_contiguous() && ep_shift->is_contiguous(), "epilogue scale/shift: fp32 CUDA vectors of Cout");
+      TORCH_CHECK(ep_act >= 0 && ep_act <= 2, "epilogue activation: 0 none, 1 relu, 2 relu6");
+      p.ep_scale = ep_scale->data_ptr<float>();
+      p.ep_shift = ep_shift->data_ptr<float>();
+      p.ep_act = (int)ep_act;
+      keep.push_back(*ep_scale);
+      keep.push_back(*ep_shift);
+      if (add_src.has_value()) {
+        TORCH_CHECK(p.mode == 0, "an epilogue residual needs a flat (dense 1x1) plan");
+        check_nhwc_view(*add_src, "add_src");
+        TORCH_CHECK(add_src->is_contiguous() && add_src->sizes() == out.sizes(), "the residual must have the output's dense shape");
+        p.add_mode = 0;
+        p.add_src = reinterpret_cast<const __nv_bfloat16*>(add_src->data_ptr());
+        keep.push_back(*add_src);
+      }
+    }
     if (raw.stats == 2) {
       // fused BatchNorm-backward reduction: y has exactly the output's shape / layout
       TORCH_CHECK(bn_scale.has_value() && bn_shift.has_value(), "bwd stats need the forward BN scale/shift");
@@ -217,7 +238,7 @@ struct ConvPlan {
       keep.push_back(*bn_scale);
       keep.push_back(*bn_shift);
     }
-    if (raw.stats) {
+    if (raw.stats >= 1 && raw.stats <= 3) {
       TORCH_CHECK(stat_sqsum.has_value());
       TORCH_CHECK(stat_sum->is_cuda() && stat_sum->scalar_type() == at::kFloat && stat_sum->numel() >= cout);
       TORCH_CHECK(stat_sqsum->is_cuda() && stat_sqsum->scalar_type() == at::kFloat && stat_sqsum->numel() >= cout);
@@ -418,12 +439,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def(py::init<std::vector<at::Tensor>, at::Tensor, at::Tensor, std::vector<int64_t>, std::vector<int64_t>,
                     std::vector<int64_t>, int64_t, int64_t, int64_t, c10::optional<at::Tensor>,
                     c10::optional<at::Tensor>, int64_t, c10::optional<at::Tensor>, c10::optional<at::Tensor>,
-                    c10::optional<at::Tensor>, c10::optional<at::Tensor>, c10::optional<at::Tensor>>(),
+                    c10::optional<at::Tensor>, c10::optional<at::Tensor>, c10::optional<at::Tensor>, c10::optional<at::Tensor>,
+                    c10::optional<at::Tensor>, int64_t>(),
            py::arg("views"), py::arg("weight"), py::arg("out"), py::arg("tap_map"), py::arg("tap_dw"),
            py::arg("tap_dh"), py::arg("bw"), py::arg("bh"), py::arg("bn"), py::arg("stat_sum") = c10::nullopt,
            py::arg("stat_sqsum") = c10::nullopt, py::arg("max_ctas") = 0, py::arg("bwd_y") = c10::nullopt,
            py::arg("bn_scale") = c10::nullopt, py::arg("bn_shift") = c10::nullopt, py::arg("add_src") = c10::nullopt,
-           py::arg("relu_mask") = c10::nullopt)
+           py::arg("relu_mask") = c10::nullopt, py::arg("ep_scale") = c10::nullopt, py::arg("ep_shift") = c10::nullopt,
+           py::arg("ep_act") = 0)
       .def("run", &b200::ConvPlan::run)
       .def_readonly("launches", &b200::ConvPlan::launches)
       .def_property_readonly("grid", &b200::ConvPlan::grid)

@@ -20,7 +20,7 @@ static void launch_t(const ConvPlanRaw& pl, cudaStream_t s) {
   }
   TmapArray4 a;
   for (int i = 0; i < 4; ++i) a.m[i] = pl.tmA[i];
-  kern<<<pl.grid, ST ? 384 : 256, L::kTotal, s>>>(a, pl.tmB, pl.tmD, pl.tmY, pl.p);
+  kern<<<pl.grid, (ST >= 1 && ST <= 3) ? 384 : 256, L::kTotal, s>>>(a, pl.tmB, pl.tmD, pl.tmY, pl.p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("conv_igemm launch: ") + cudaGetErrorString(e));
 }
@@ -42,7 +42,8 @@ void conv_plan_launch(const ConvPlanRaw& pl, cudaStream_t s) {
     if (pl.block_n == 256) launch_t<256, 3>(pl, s);
     else if (pl.block_n == 128) launch_t<128, 3>(pl, s);
     else launch_t<64, 3>(pl, s);
-  } else launch_n<0>(pl, s);
+  } else if (pl.stats == 4) launch_n<4>(pl, s);
+  else launch_n<0>(pl, s);
 }
 
 }  // namespace b200

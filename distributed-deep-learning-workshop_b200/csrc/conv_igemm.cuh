@@ -34,6 +34,8 @@ namespace b200 {
 // happens in the epilogue - dz = (acc + skip_gradient) * relu_bitmask is what gets stored, and the statistics warps
 // accumulate sum(dz), sum(dz*y3) for that block's final BatchNorm.  The separate reduce pass (4 tensor reads + 1 write of
 // the widest activation of the block) and the store / re-read of the main-path gradient disappear.
+// kStats = 4 (inference): per-channel affine (folded BatchNorm: y*scale + shift) + optional residual add (flat mode) +
+// ReLU / ReLU6 applied in the epilogue - the convolution writes the block's activation directly, no BatchNorm pass at all.
 // The (up to four) parity views of the A operand as ONE kernel parameter: the per-tap choice is an index.
 struct TmapArray4 {
   CUtensorMap m[4];
@@ -48,8 +50,11 @@ constexpr int kHaloRows = 224;  // largest halo box: bw * (bh + 2) pixels (56 x 
 
 template <int BLOCK_N, int kStats = 0, bool kResB = false, bool kHalo = false>
 struct ConvSmem {
-  static constexpr int kYBufs = 4;  // pre-BN tiles are prefetched TWO output chunks ahead (see the epilogue)
-  static constexpr int kYBytes = kStats >= 2 ? kYBufs * kBlockM * 128 : 0;  // 128x64 bf16 tiles of y
+  // Two pre-BN tile buffers, loaded at the start of their own chunk.  (Four buffers prefetched two chunks ahead were tried:
+  // the statistics warps already run a chunk behind the epilogue, so the load latency was hidden, and the extra 32 KB cost
+  // a pipeline stage - the block-gradient kernel went from 302 to 353 us.  profiles/README.md, r2 negative results.)
+  static constexpr int kYBufs = 2;
+  static constexpr int kYBytes = (kStats == 2 || kStats == 3) ? kYBufs * kBlockM * 128 : 0;  // 128x64 bf16 tiles of y
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kASlot = kHalo ? kHaloRows * 128 : kABytes;     // bytes of A per pipeline stage
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -70,12 +75,20 @@ struct ConvSmem {
 };
 
 template <int BLOCK_N, int kStats, bool kResB = false, bool kHalo = false>
-__global__ void __launch_bounds__(kStats ? 384 : 256, 1)
+__global__ void __launch_bounds__((kStats >= 1 && kStats <= 3) ? 384 : 256, 1)
 conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY,
                   const __grid_constant__ ConvParams p) {
   using L = ConvSmem<BLOCK_N, kStats, kResB, kHalo>;
   constexpr int kStages = L::kStages;
+  constexpr bool kStatWarps = kStats >= 1 && kStats <= 3;  // warps 8-11 exist and consume the staged tiles
+  constexpr bool kHasY = kStats == 2 || kStats == 3;       // a pre-BN tile accompanies every output chunk
+  constexpr bool kAffine = kStats == 4;                    // epilogue: acc*scale + shift (+ residual) -> activation
+  constexpr bool kRowAdd = kStats == 3 || kStats == 4;     // per-row global loads of an additive tensor in the epilogue
+#ifndef B200DDL_ADD_AHEAD
+#define B200DDL_ADD_AHEAD 1
+#endif
+  constexpr int kAddAhead = B200DDL_ADD_AHEAD;             // 32-column halves the additive rows are prefetched ahead (1 or 2)
   constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -116,10 +129,10 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
-  if (kStats) {
+  if (kStatWarps) {
     for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) sStat[i] = 0.f;
   }
-  if (kStats >= 2) {
+  if (kHasY) {
     // rows past the pixel box are never written by TMA: keep them finite (0 * NaN would poison the sums)
     for (int i = threadIdx.x; i < L::kYBytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(sY)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
@@ -329,19 +342,16 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     int chunk_ctr = 0;
-    // kStats >= 2: the pre-BN tile of CTA-local output chunk g (tile g / kChunks of this CTA, 64-column chunk g % kChunks)
-    // is loaded into Y buffer g & 3 TWO chunks before it is needed.  Issuing it at the start of its own chunk (v1) put a
-    // full DRAM round trip on the epilogue <-> statistics hand-off chain of every chunk: ncu on the block-gradient kernel
-    // showed 44 % of the warp samples parked at named barriers and the kernel at 4.5 of 6.5 TB/s (profiles/ncu/).
-    // Buffer (g + 2) & 3 was last used by chunk g - 2, which the statistics warps have finished when the epilogue passes
-    // the "staging buffer g & 1 is free" barrier of chunk g.
+    // kStats 2 / 3: the pre-BN tile of CTA-local output chunk g (tile g / kChunks of this CTA, 64-column chunk g % kChunks)
+    // goes to Y buffer g & 1; it is issued at the start of chunk g, after the barrier that says the statistics warps are
+    // done with chunk g - 2 (which used the same buffer).
     auto issue_y = [&](int g) {
       constexpr int kChunksE = BLOCK_N / 64;
       const int lt = g / kChunksE, c = g - lt * kChunksE;
       const int tl = static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x);
       if (tl >= p.num_tiles) return;
       const int mt = tl / p.n_blocks, nbb = tl - mt * p.n_blocks;
-      const int b = g & 3;
+      const int b = g & 1;
       mbar_arrive_expect_tx(&y_bar[b], static_cast<uint32_t>(p.valid_rows) * 128u);
       if (p.mode == 0) {
         tma_load_2d(sY + b * (kBlockM * 128), &tmY, &y_bar[b], nbb * BLOCK_N + c * 64, mt * kBlockM);
@@ -353,10 +363,6 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
                     (rest / p.tiles_h) * p.bn);
       }
     };
-    if (kStats >= 2 && etid == 0) {
-      issue_y(0);
-      issue_y(1);
-    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_blocks;
       const int nb = tile - m_tile * p.n_blocks;
@@ -376,10 +382,22 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
       const uint8_t* mrow = nullptr;
       uint4 gq[3][4];               // queue: [0] = current half, [1] = next, [2] = the one after (rotated by moves)
       uint32_t mq[3] = {0u, 0u, 0u};
-      if (kStats == 3) {
+      if (kAffine) {
+        // per-channel scale / shift of this tile's N-block -> shared memory (read back as float4 broadcasts); every thread
+        // passed the previous tile's last staging barrier after its last read, and the first chunk barrier below publishes
+        for (int i = etid; i < BLOCK_N; i += 128) {
+          sStat[i] = p.ep_scale[nb * BLOCK_N + i];
+          sStat[BLOCK_N + i] = p.ep_shift[nb * BLOCK_N + i];
+        }
+      }
+      if (kRowAdd) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gq[0][j] = gq[1][j] = gq[2][j] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (kRowAdd && (kStats == 3 || (p.add_src != nullptr && p.mode == 0))) {
         const int64_t grow = static_cast<int64_t>(m_tile) * kBlockM + row;
         if (grow < p.m_rows) {
-          mrow = p.relu_mask + grow * (p.cout >> 3) + ((nb * BLOCK_N) >> 3);
+          if (kStats == 3) mrow = p.relu_mask + grow * (p.cout >> 3) + ((nb * BLOCK_N) >> 3);
           if (p.add_mode == 0) {
             arow = p.add_src + grow * p.cout + nb * BLOCK_N;
           } else {
@@ -392,17 +410,17 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
               arow = p.add_src + ((nq * (p.add_h >> 1) + (hq >> 1)) * (p.add_w >> 1) + (wq >> 1)) * p.cout + nb * BLOCK_N;
           }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) gq[0][j] = gq[1][j] = gq[2][j] = make_uint4(0u, 0u, 0u, 0u);
         if (arow != nullptr) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) gq[0][j] = __ldg(reinterpret_cast<const uint4*>(arow) + j);
+          if (kAddAhead == 2) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) gq[1][j] = __ldg(reinterpret_cast<const uint4*>(arow + 32) + j);
+            for (int j = 0; j < 4; ++j) gq[1][j] = __ldg(reinterpret_cast<const uint4*>(arow + 32) + j);
+          }
         }
         if (mrow != nullptr) {
           mq[0] = __ldg(reinterpret_cast<const uint32_t*>(mrow));
-          mq[1] = __ldg(reinterpret_cast<const uint32_t*>(mrow + 4));
+          if (kAddAhead == 2) mq[1] = __ldg(reinterpret_cast<const uint32_t*>(mrow + 4));
         }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -413,27 +431,57 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
       for (int c64 = 0; c64 < BLOCK_N / 64; ++c64, ++chunk_ctr) {
         uint8_t* sbuf = sStage + (chunk_ctr & 1) * (kBlockM * 128);
         if (etid == 0) tma_store_wait_read<1>();  // the store that used this buffer two chunks ago is done
-        if (kStats)
+        if (kStatWarps)
           named_bar_sync(4 + (chunk_ctr & 1), 256);  // ... and the statistics warps are done reading it
         else
           named_bar_sync(1, 128);
-        if (kStats >= 2 && etid == 0) issue_y(chunk_ctr + 2);  // pre-BN tile two chunks ahead (see issue_y)
+        if (kHasY && etid == 0) issue_y(chunk_ctr);  // pre-BN tile of this chunk (see issue_y)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t r[32];
-          if (kStats == 3) {
-            // prefetch the half after next (two 32-column halves = 128 B per thread stay in flight)
-            const int nxt = c64 * 64 + h * 32 + 64;
+          if (kRowAdd) {
+            // prefetch kAddAhead halves ahead into the queue slot that reaches [0] exactly when that half is processed
+            const int nxt = c64 * 64 + h * 32 + 32 * kAddAhead;
             if (nxt < BLOCK_N) {
               if (arow != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) gq[2][j] = __ldg(reinterpret_cast<const uint4*>(arow + nxt) + j);
+                for (int j = 0; j < 4; ++j) gq[kAddAhead][j] = __ldg(reinterpret_cast<const uint4*>(arow + nxt) + j);
               }
-              if (mrow != nullptr) mq[2] = __ldg(reinterpret_cast<const uint32_t*>(mrow + (nxt >> 3)));
+              if (mrow != nullptr) mq[kAddAhead] = __ldg(reinterpret_cast<const uint32_t*>(mrow + (nxt >> 3)));
             }
           }
           tmem_ld_32x32b_x32(taddr + c64 * 64 + h * 32, r);
           tmem_ld_wait();
+          if (kAffine) {
+            // out = act(acc * scale[c] + shift[c] [+ residual])
+            const float4* sc4 = reinterpret_cast<const float4*>(sStat + c64 * 64 + h * 32);
+            const float4* sh4 = reinterpret_cast<const float4*>(sStat + BLOCK_N + c64 * 64 + h * 32);
+            const int act = p.ep_act;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t gw[4] = {gq[0][j].x, gq[0][j].y, gq[0][j].z, gq[0][j].w};
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float4 sc = sc4[2 * j + e], sh = sh4[2 * j + e];
+                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int col = 8 * j + 4 * e + q;
+                  const uint32_t gword = gw[(4 * e + q) >> 1];
+                  const float res = __uint_as_float(((4 * e + q) & 1) ? (gword & 0xFFFF0000u) : (gword << 16));
+                  float f = fmaf(__uint_as_float(r[col]), scv[q], shv[q]) + res;
+                  if (act >= 1) f = fmaxf(f, 0.f);
+                  if (act == 2) f = fminf(f, 6.f);
+                  r[col] = __float_as_uint(f);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              gq[0][j] = gq[1][j];
+              gq[1][j] = gq[2][j];
+            }
+          }
           if (kStats == 3) {
             // dz = (main-path gradient + skip gradient) * [block output > 0]
 #pragma unroll
@@ -470,14 +518,14 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
             v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
             v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
             v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-            if (kStats && row >= p.valid_rows) v = make_uint4(0u, 0u, 0u, 0u);  // rows past the pixel box: no statistics
+            if (kStatWarps && row >= p.valid_rows) v = make_uint4(0u, 0u, 0u, 0u);  // rows past the pixel box: no statistics
             const int chunk = (h * 4 + j) ^ (row & 7);
             *reinterpret_cast<uint4*>(sbuf + row * 128 + chunk * 16) = v;
           }
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
-        if (kStats) named_bar_arrive(6 + (chunk_ctr & 1), 256);  // staged tile is complete: wake the statistics warps
+        if (kStatWarps) named_bar_arrive(6 + (chunk_ctr & 1), 256);  // staged tile is complete: wake the statistics warps
         if (etid == 0) {
           const int ccol = nb * BLOCK_N + c64 * 64;
           if (p.mode == 0)
@@ -493,7 +541,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
       }
     }
     if (etid == 0) tma_store_wait_all<0>();
-  } else if (kStats && warp >= 8) {
+  } else if (kStatWarps && warp >= 8) {
     // ------------------------------------------------------------------ BatchNorm statistics warps (128 threads)
     // Column sums / sums of squares of the bf16 tile the epilogue just staged (exactly the values BatchNorm will
     // read), concurrent with the epilogue's next chunk.  Thread = (column pair cp, 32-row group rg): one
@@ -534,8 +582,8 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
           }
         } else if (kStats == 3) {
           // the staged tile already is dz (merged + masked by the epilogue): accumulate sum(dz) and sum(dz * y)
-          const uint8_t* ybuf = sY + (chunk_ctr & 3) * (kBlockM * 128);
-          mbar_wait(&y_bar[chunk_ctr & 3], (chunk_ctr >> 2) & 1);
+          const uint8_t* ybuf = sY + (chunk_ctr & 1) * (kBlockM * 128);
+          mbar_wait(&y_bar[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + xoff[i & 7] + i * 128);
@@ -552,8 +600,8 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
           const int col = nb * BLOCK_N + c64 * 64 + cp * 2;
           const float sc0 = p.bn_scale[col], sc1 = p.bn_scale[col + 1];
           const float sh0 = p.bn_shift[col], sh1 = p.bn_shift[col + 1];
-          const uint8_t* ybuf = sY + (chunk_ctr & 3) * (kBlockM * 128);
-          mbar_wait(&y_bar[chunk_ctr & 3], (chunk_ctr >> 2) & 1);
+          const uint8_t* ybuf = sY + (chunk_ctr & 1) * (kBlockM * 128);
+          mbar_wait(&y_bar[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + xoff[i & 7] + i * 128);

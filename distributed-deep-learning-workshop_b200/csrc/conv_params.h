@@ -40,6 +40,10 @@ struct ConvParams {
   int add_mode;
   int add_h, add_w;              // add_mode 1: spatial extent of the OUTPUT grid (rows decode to (n, h, w))
   int64_t m_rows;                // number of real rows (pixels) of the flat problem
+  // kStats == 4 (inference epilogue): out = act(acc * ep_scale[c] + ep_shift[c] [+ add_src]);  act: 0 none, 1 ReLU, 2 ReLU6
+  const float* ep_scale;
+  const float* ep_shift;
+  int ep_act;
 };
 
 // Weight-gradient GEMM:  dW[tap][co][ci] += sum_px dY[px, co] * X_tap[px, ci]

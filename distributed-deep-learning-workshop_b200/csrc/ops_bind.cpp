@@ -273,6 +273,37 @@ void zero_(Tensor t) {
   TORCH_CHECK(t.is_cuda() && t.is_contiguous());
   C10_CUDA_CHECK(cudaMemsetAsync(t.data_ptr(), 0, t.numel() * t.element_size(), cur()));
 }
+// MobileNetV2 stem: uint8 [N,H,W,3] -> bf16 [N,H/2,W/2,ldc] (32 real channels), relu6(conv3x3/2(x*mul+add) * scale + shift)
+void mbv2_stem(Tensor x, Tensor w, Tensor scale, Tensor shift, Tensor out, double mul, double add) {
+  chk(x, at::kByte, "x");
+  chk(w, at::kFloat, "w");
+  chk(scale, at::kFloat, "scale");
+  chk(shift, at::kFloat, "shift");
+  chk(out, at::kBFloat16, "out");
+  TORCH_CHECK(x.dim() == 4 && x.size(3) == 3 && x.size(1) % 2 == 0 && x.size(2) % 2 == 0, "stem input: uint8 [N, H, W, 3], even H / W");
+  TORCH_CHECK(w.numel() == 27 * 32 && scale.numel() >= 32 && shift.numel() >= 32);
+  TORCH_CHECK(out.dim() == 4 && out.size(0) == x.size(0) && out.size(1) == x.size(1) / 2 && out.size(2) == x.size(2) / 2 &&
+              out.size(3) >= 32 && out.size(3) % 8 == 0);
+  b200::mbv2_stem(x.data_ptr<uint8_t>(), w.data_ptr<float>(), scale.data_ptr<float>(), shift.data_ptr<float>(), out.data_ptr(),
+                  (int)x.size(0), (int)x.size(1), (int)x.size(2), (int)out.size(3), (float)mul, (float)add, cur());
+  after();
+}
+// depthwise 3x3 (pad 1, stride 1 / 2) + folded BatchNorm + ReLU6;  x bf16 [N,H,W,C], w fp32 [9, C], out bf16 [N,Ho,Wo,C]
+void dwconv3x3(Tensor x, Tensor w, Tensor scale, Tensor shift, Tensor out, int64_t stride) {
+  chk(x, at::kBFloat16, "x");
+  chk(w, at::kFloat, "w");
+  chk(scale, at::kFloat, "scale");
+  chk(shift, at::kFloat, "shift");
+  chk(out, at::kBFloat16, "out");
+  TORCH_CHECK(stride == 1 || stride == 2);
+  const int C = (int)x.size(3), H = (int)x.size(1), W = (int)x.size(2);
+  TORCH_CHECK(x.dim() == 4 && C % 8 == 0 && w.numel() == 9 * C && scale.numel() == C && shift.numel() == C);
+  TORCH_CHECK(out.dim() == 4 && out.size(0) == x.size(0) && out.size(3) == C && out.size(1) == (H - 1) / stride + 1 &&
+              out.size(2) == (W - 1) / stride + 1, "dwconv3x3 output shape");
+  b200::dwconv3x3(x.data_ptr(), w.data_ptr<float>(), scale.data_ptr<float>(), shift.data_ptr<float>(), out.data_ptr(),
+                  (int)x.size(0), H, W, C, (int)stride, cur());
+  after();
+}
 void preprocess_u8(Tensor x, Tensor out, double mul, double add) {
   chk(x, at::kByte, "x");
   chk(out, at::kBFloat16, "out");
@@ -368,6 +399,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("scale"), py::arg("shift"), py::arg("cA") = c10::nullopt, py::arg("cB") = c10::nullopt,
         py::arg("cC") = c10::nullopt, py::arg("dy") = c10::nullopt, py::arg("sum_dz"), py::arg("sum_dzy"));
   m.def("zero_", &zero_);
+  m.def("mbv2_stem", &mbv2_stem);
+  m.def("dwconv3x3", &dwconv3x3);
   m.def("preprocess_u8", &preprocess_u8);
   m.def("resize_bilinear_u8", &resize_bilinear_u8, py::arg("x"), py::arg("out"), py::arg("planar") = false);
   m.def("weight_prep", &weight_prep);

@@ -198,6 +198,91 @@ class _TableDataset(RingDataset):
         super().close()
 
 
+class _GpuDecodeDataset:
+    """`make_dataset(decode='gpu')`: JPEG payloads are decoded ON THE GPU (nvJPEG through `torchvision.io.decode_jpeg`, a
+    library call - the reference's tf.io.decode_jpeg, P1/03:182-189) and resized by OUR bilinear kernel
+    (csrc/elementwise.cu resize_bilinear_u8, planar input -> HWC output) straight into the uint8 device batch; only the
+    compressed bytes cross PCIe.  Rows that are not JPEG (PNG, raw tensors) take the CPU decoder.  Same sharding / shuffle /
+    epoch semantics as the pinned-ring dataset (it reuses its row planner); yields (images uint8 [B,H,W,3], labels int64 [B])."""
+
+    def __init__(self, files, total_rows, batch_size, image_size, device, cur_shard, shard_count, num_epochs, shuffle, seed):
+        import types
+
+        from .. import ops
+
+        self.batch_size = batch_size
+        self.h, self.w = image_size
+        self.device = torch.device("cuda", _device_index(device))
+        self._e = ops.ext("_b200_ops")
+        # borrow the row planner of the ring dataset without starting its decode threads
+        self._src = types.SimpleNamespace(files=files, total_rows=int(total_rows), cur_shard=cur_shard, shard_count=shard_count,
+                                          num_epochs=num_epochs, shuffle=shuffle, seed=seed, row_groups_read=0,
+                                          batch_size=batch_size)
+        n, k = int(total_rows), shard_count
+        self._src.row_lo, self._src.row_hi = (n * cur_shard) // k, (n * (cur_shard + 1)) // k
+        self._src._plan = lambda: _TableDataset._plan(self._src)
+        self._rows = _TableDataset._rows(self._src)
+        self._out = [torch.empty(batch_size, self.h, self.w, 3, device=self.device, dtype=torch.uint8) for _ in range(2)]
+        self._lab = [torch.empty(batch_size, device=self.device, dtype=torch.int64) for _ in range(2)]
+        self._k = 0
+        self.compressed_bytes = 0
+        self.gpu_decoded = 0
+        self.cpu_decoded = 0
+
+    def __len__(self) -> int:
+        return (self._src.row_hi - self._src.row_lo) // self.batch_size
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def close(self) -> None:
+        self._rows = iter(())
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        import warnings
+
+        import torchvision
+
+        batch = []
+        try:
+            for _ in range(self.batch_size):
+                batch.append(next(self._rows))
+        except StopIteration:
+            pass
+        if len(batch) < self.batch_size:
+            raise StopIteration
+        out, lab = self._out[self._k & 1], self._lab[self._k & 1]
+        self._k += 1
+        jpeg_idx, jpeg_data, labels = [], [], []
+        for i, (contents, lbls, j) in enumerate(batch):
+            buf = contents[j].as_buffer()
+            labels.append(int(lbls[j]))
+            head = bytes(buf[:3])
+            if head == b"\xff\xd8\xff":
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")  # read-only buffer: decode_jpeg does not write to it
+                    jpeg_data.append(torch.frombuffer(buf, dtype=torch.uint8))
+                jpeg_idx.append(i)
+                self.compressed_bytes += buf.size
+            else:
+                out[i].copy_(torch.from_numpy(np.ascontiguousarray(decode_image(contents[j].as_py(), (self.h, self.w)))),
+                             non_blocking=False)
+                self.cpu_decoded += 1
+        if jpeg_data:
+            imgs = torchvision.io.decode_jpeg(jpeg_data, device=self.device, mode=torchvision.io.ImageReadMode.RGB)
+            for i, img in zip(jpeg_idx, imgs):
+                self._e.resize_bilinear_u8(img.unsqueeze(0), out[i:i + 1], True)  # [1,3,h,w] planar -> [1,H,W,3]
+            self.gpu_decoded += len(jpeg_data)
+        lab.copy_(torch.tensor(labels, dtype=torch.int64), non_blocking=False)
+        return out, lab
+
+
 class Converter:
     """Materialised, shardable copy of a table (Petastorm `SparkDatasetConverter`)."""
 
@@ -220,12 +305,18 @@ class Converter:
 
     def make_dataset(self, batch_size: int = 32, cur_shard: Optional[int] = None, shard_count: Optional[int] = None,
                      num_epochs: Optional[int] = None, workers_count: int = 4, image_size=(IMG_HEIGHT, IMG_WIDTH),
-                     device=None, shuffle: bool = False, seed: int = 0) -> _TableDataset:
+                     device=None, shuffle: bool = False, seed: int = 0, decode: str = "cpu"):
+        """``decode='cpu'``: PIL decode + resize in `workers_count` threads into the pinned ring (default);
+        ``decode='gpu'``: nvJPEG decode + our resize kernel on the device (`_GpuDecodeDataset`)."""
         if (cur_shard is None) != (shard_count is None):
             raise ValueError("cur_shard and shard_count must be given together")
         cs, sc = (0, 1) if cur_shard is None else (int(cur_shard), int(shard_count))
         if not (0 <= cs < sc):
             raise ValueError("need 0 <= cur_shard < shard_count")
+        if decode == "gpu":
+            return _GpuDecodeDataset(self.files, self._n, batch_size, image_size, device, cs, sc, num_epochs, shuffle, seed)
+        if decode != "cpu":
+            raise ValueError("decode must be 'cpu' or 'gpu'")
         return _TableDataset(self.files, self._n, batch_size, image_size, device, cs, sc, num_epochs, workers_count,
                              shuffle, seed)
 

@@ -5,7 +5,9 @@
     build_model()                                                       (P2/03:125)
 
 `arch='resnet50'` (TARGET, default on a B200): the hand-scheduled sm_100a engine, fully trainable, bf16.
-`arch='mobilenetv2'` (REF parity): frozen MobileNetV2 base + GAP + Dropout + Dense head, torch.nn.
+`arch='mobilenetv2'` (REF parity): frozen MobileNetV2 base + GAP + Dropout + Dense head - on a GPU the native
+`MobileNetV2Engine` (depthwise / stem kernels + tcgen05 pointwise convs with folded-BN epilogues), on CPU (or with
+`arch='mobilenetv2_torch'`, or `freeze_base=False`) the torch.nn module.
 `arch='resnet50_torch'`: torchvision-architecture ResNet-50 as a plain nn.Module (CPU plumbing runs).
 """
 from __future__ import annotations
@@ -33,7 +35,14 @@ def build_model(img_height: int = IMG_HEIGHT, img_width: int = IMG_WIDTH, img_ch
 
         return ResNet50Engine(batch=batch_size, num_classes=num_classes, device=device, image_size=img_height,
                               dropout=dropout, seed=seed, **engine_kwargs)
-    if arch == "mobilenetv2":
+    if arch == "mobilenetv2" and freeze_base and torch.cuda.is_available() and img_height == img_width and img_height % 32 == 0 \
+            and (device is None or torch.device(device).type == "cuda"):
+        # the reference's own model on native kernels (frozen base = inference-mode layers; trainable Dense head)
+        from .mobilenet_engine import MobileNetV2Engine
+
+        return MobileNetV2Engine(batch=batch_size, num_classes=num_classes, device=device, image_size=img_height,
+                                 dropout=dropout, seed=seed)
+    if arch in ("mobilenetv2", "mobilenetv2_torch"):
         from .mobilenet import FrozenBaseClassifier, MobileNetV2Base
 
         g = torch.random.fork_rng(devices=[])

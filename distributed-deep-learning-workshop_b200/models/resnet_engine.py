@@ -110,6 +110,10 @@ class ResNet50Engine:
         self.fuse_stem_bwd = (os.environ.get("B200DDL_STEM_BWD_FUSE") == "1") if fuse_stem_bwd is None else bool(fuse_stem_bwd)
         self._fused_reduce = set()
         self._block_fused = set()   # bn3 names whose reduction (and dz) come out of a fused dgrad epilogue
+        # inference-only builds (build(training=False)): BatchNorm (running statistics) + ReLU + residual add run in the
+        # convolutions' epilogues (conv_igemm kStats = 4) - no BatchNorm pass at all.  B200DDL_NO_FUSED_INFER=1 disables.
+        self.fused_inference = os.environ.get("B200DDL_NO_FUSED_INFER") != "1"
+        self._infer_fused = False
         self.wgrad_smem_budget = wgrad_smem_budget
         self.aux_streams: List[torch.cuda.Stream] = []
         if image_size % 32:
@@ -230,6 +234,13 @@ class ResNet50Engine:
         if getattr(self, "_wd_total", 0) > 0:
             self._e.weight_prep_batched(self.params, self._wd16, self._wd_table, self._wd_tiles)
         self._refresh_stem_weight()
+        if self._infer_fused:
+            self._refresh_eval_affine()
+
+    def _refresh_eval_affine(self) -> None:
+        """scale / shift of every BatchNorm from its running statistics (inference epilogues read them)."""
+        for bn in self.bn_names:
+            self._bn_fwd(bn, 1.0, False)
 
     def _refresh_stem_weight(self) -> None:
         if self.native_stem:
@@ -250,7 +261,12 @@ class ResNet50Engine:
     def build(self, training: bool = True) -> "ResNet50Engine":
         """Allocate activations / scratch and encode every TMA descriptor (once; buffers are static)."""
         if self._built:
-            return self
+            if not (training and not self._training_built):
+                return self
+            # built for inference (fused epilogues, no backward buffers) and now asked to train: build again
+            self._built = False
+            self._fused_reduce.clear()
+            self._block_fused.clear()
         if self.grads is None and training:
             self.bind_grad_buffer()
         dev, N, e = self.device, self.batch, self._e
@@ -369,7 +385,36 @@ class ResNet50Engine:
 
         dz_keys = ["dzA", "dzB"]
         x_in = self.p0
-        for bi, b in enumerate(self.blocks):
+        self._infer_fused = (not training) and self.fused_inference
+        for bi, b in enumerate(self.blocks if self._infer_fused else []):
+            # inference: every convolution writes its block activation directly (folded BN + ReLU [+ residual] epilogue)
+            Hi, Ho, mid, cout = b.h_in, b.h_out, b.mid, b.mid * 4
+            A, n = self.act, b.name
+            A[n + ".a1"] = torch.zeros(N, Hi, Hi, mid, **bf)
+            A[n + ".a2"] = torch.zeros(N, Ho, Ho, mid, **bf)
+            A[n + ".out"] = torch.zeros(N, Ho, Ho, cout, **bf)
+
+            def w2d(full):
+                w = self.w16v(full + ".weight")
+                return w.view(w.shape[0] * w.shape[1], w.shape[2])
+
+            def aff(bn, act, res=None):
+                return (self.bnw[n + "." + bn]["scale"], self.bnw[n + "." + bn]["shift"], act, res)
+
+            self._fwd[n + ".conv1"] = C.ConvForward(x_in, w2d(n + ".conv1"), A[n + ".a1"], 1, 1, 1, 0, None, None, mc,
+                                                    epilogue=aff("bn1", "relu"))
+            self._fwd[n + ".conv2"] = C.ConvForward(A[n + ".a1"], w2d(n + ".conv2"), A[n + ".a2"], 3, 3, b.stride, 1, None,
+                                                    None, mc, epilogue=aff("bn2", "relu"))
+            res = x_in
+            if b.downsample:
+                A[n + ".yd"] = torch.zeros(N, Ho, Ho, cout, **bf)
+                self._fwd[n + ".downsample.0"] = C.ConvForward(x_in, w2d(n + ".downsample.0"), A[n + ".yd"], 1, 1, b.stride,
+                                                               0, None, None, mc, epilogue=aff("downsample.1", "none"))
+                res = A[n + ".yd"]
+            self._fwd[n + ".conv3"] = C.ConvForward(A[n + ".a2"], w2d(n + ".conv3"), A[n + ".out"], 1, 1, 1, 0, None, None,
+                                                    mc, epilogue=aff("bn3", "relu", res))
+            x_in = A[n + ".out"]
+        for bi, b in enumerate([] if self._infer_fused else self.blocks):
             Hi, Ho, mid, cout = b.h_in, b.h_out, b.mid, b.mid * 4
             A = self.act
             A[b.name + ".y1"] = torch.zeros(N, Hi, Hi, mid, **bf)
@@ -502,7 +547,15 @@ class ResNet50Engine:
         # BN + ReLU + 3x3/2 max-pool in one pass (the 112x112 activation is never written)
         e.bn_relu_maxpool_fwd(self.y0, w0["scale"], w0["shift"], self.p0, self.pool_idx)
         x_in = self.p0
-        for b in self.blocks:
+        if self._infer_fused and not training:
+            for b in self.blocks:
+                n = b.name
+                self._fwd[n + ".conv1"].run()
+                self._fwd[n + ".conv2"].run()
+                if b.downsample:
+                    self._fwd[n + ".downsample.0"].run()
+                self._fwd[n + ".conv3"].run()
+        for b in ([] if (self._infer_fused and not training) else self.blocks):
             n = b.name
             cnt_in = N * b.h_in * b.h_in
             cnt_out = N * b.h_out * b.h_out

@@ -34,7 +34,7 @@ CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC"]
 EXTENSIONS: Dict[str, List[str]] = {
     "_b200_conv": ["conv_igemm.cu", "conv_wgrad.cu", "stem.cu", "tmap.cpp", "conv_bind.cpp"],
     "_b200_probe": ["umma_probe.cu", "tma_probe.cu", "tmap.cpp", "probe_bind.cpp"],   # hardware probes, not on any hot path
-    "_b200_ops": ["elementwise.cu", "head_stem.cu", "optim.cu", "ops_bind.cpp"],
+    "_b200_ops": ["elementwise.cu", "head_stem.cu", "mobilenet.cu", "optim.cu", "ops_bind.cpp"],
     "_b200_comm": ["allreduce.cu", "comm_bind.cpp"],
     "_b200_loader": ["ring_loader.cpp"],
 }

@@ -127,7 +127,10 @@ class ConvForward:
 
     def __init__(self, x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, R: int, S: int, stride: int = 1,
                  pad: int = 0, stat_sum: Optional[torch.Tensor] = None, stat_sqsum: Optional[torch.Tensor] = None,
-                 max_ctas: int = 0):
+                 max_ctas: int = 0, epilogue=None):
+        """``epilogue=(scale, shift, act, residual)`` (inference): y = act(conv(x, w) * scale[c] + shift[c] [+ residual])
+        with act in {'none', 'relu', 'relu6'} computed in the GEMM epilogue (folded BatchNorm); the residual (a tensor of
+        y's shape) needs a dense 1x1 stride-1 convolution.  Mutually exclusive with the statistics outputs."""
         ext = _build.load("_b200_conv")
         taps = make_taps(x, R, S, stride, pad)
         N, Ho, Wo, _ = y.shape
@@ -138,8 +141,18 @@ class ConvForward:
             cout_, cin_ = w.shape[0] // (R * S), w.shape[1]
             bw, bh, bn = halo_box(Ho, Wo, cin_, cout_, R, S, stride, pad) or pick_box(N, Ho, Wo)
         self.box = (bw, bh, bn)
-        self.plan = ext.ConvPlan(taps.views, w, y, taps.tap_map, taps.tap_dw, taps.tap_dh, bw, bh, bn,
-                                 stat_sum, stat_sqsum, max_ctas)
+        if epilogue is not None:
+            if stat_sum is not None:
+                raise ValueError("epilogue and statistics outputs are mutually exclusive")
+            scale, shift, act, residual = epilogue
+            if residual is not None and not flat:
+                raise ValueError("an epilogue residual needs a dense 1x1 stride-1 convolution")
+            self.plan = ext.ConvPlan(taps.views, w, y, taps.tap_map, taps.tap_dw, taps.tap_dh, bw, bh, bn, None, None,
+                                     max_ctas, None, None, None, residual, None, scale, shift,
+                                     {"none": 0, "relu": 1, "relu6": 2}[act])
+        else:
+            self.plan = ext.ConvPlan(taps.views, w, y, taps.tap_map, taps.tap_dw, taps.tap_dh, bw, bh, bn,
+                                     stat_sum, stat_sqsum, max_ctas)
         _plans.add(self.plan)
 
     def run(self) -> None:

@@ -35,7 +35,7 @@ class DistributedOptimizer:
     """Wraps a fused flat optimizer; averages gradients over all ranks before every update."""
 
     def __init__(self, optimizer: FlatOptimizer, bucket_mb: float = 16.0, overlap: bool = True, algo: str = "auto",
-                 comm_blocks: int = 16, average: bool = True, fused_update: bool = False, tail_mb: float = 1.0,
+                 comm_blocks: int = 32, average: bool = True, fused_update: bool = False, tail_mb: float = 1.0,
                  nvls_min_mb: float = 32.0):
         self.opt = optimizer
         self.bucket_bytes = int(bucket_mb * 2 ** 20)
@@ -47,6 +47,8 @@ class DistributedOptimizer:
         self.nvls_min_bytes = int(nvls_min_mb * 2 ** 20)
         self.overlap = overlap
         self.algo = algo
+        # CTAs of a comm kernel (512 threads each).  16 MB bucket, 2 GPUs, two-shot P2P: 8 CTAs 121 us, 16: 67, 32: 43, 64: 40
+        # (profiles/r2_allreduce_w2.log) - 32 is where the curve flattens; they occupy SM slots only while a bucket is in flight
         self.comm_blocks = comm_blocks
         self.average = average
         # fused_update: reduce-scatter + SGD-momentum update of my 1/N slice + multicast of the new fp32/bf16 weights

@@ -10,9 +10,9 @@ import torch
 
 
 def _describe(model) -> dict:
-    if hasattr(model, "param_specs"):  # ResNet50Engine
-        return {"arch": "resnet50", "num_classes": model.num_classes, "image_size": model.image_size,
-                "dropout": model.dropout, "batch": model.batch}
+    if hasattr(model, "param_specs"):  # native engines (ResNet50Engine, MobileNetV2Engine)
+        return {"arch": getattr(model, "arch", "resnet50"), "num_classes": model.num_classes, "image_size": model.image_size,
+                "dropout": model.dropout, "batch": model.batch, "engine": True}
     from ..models.mobilenet import FrozenBaseClassifier
 
     if isinstance(model, FrozenBaseClassifier):
@@ -69,8 +69,12 @@ def load_model(model_uri: str, batch_size: Optional[int] = None, device=None):
         else:  # CPU box: same weights in the torchvision-architecture module
             model = build_model(num_classes=desc["num_classes"], arch="resnet50_torch")
             model.load_state_dict(sd, strict=False)
+    elif desc.get("engine") and torch.cuda.is_available():  # saved from the native MobileNetV2 engine
+        model = build_model(desc["image_size"], desc["image_size"], 3, desc["num_classes"], desc["dropout"],
+                            arch="mobilenetv2", batch_size=batch_size or desc["batch"], device=device)
+        model.load_state_dict(sd)
     else:
-        model = build_model(num_classes=desc["num_classes"], dropout=desc["dropout"], arch="mobilenetv2",
+        model = build_model(num_classes=desc["num_classes"], dropout=desc["dropout"], arch="mobilenetv2_torch",
                             freeze_base=desc.get("freeze_base", True))
         model.load_state_dict(sd)
     return Trainer(model, device=device)

@@ -33,13 +33,37 @@ class _EngineBackend:
 
         self.engine = engine
         self.optimizer = optimizer
-        self.step = EngineTrainStep(engine, optimizer, use_graph=use_graph)
-        self.eval_step = EngineEvalStep(engine, use_graph=use_graph)
+        self.use_graph = use_graph
+        # Both step objects are created on first use: a Trainer that only ever predicts (pyfunc serving, load_model) builds
+        # the engine for INFERENCE - BatchNorm folded into the convolution epilogues, no gradient / backward buffers - and
+        # only a later train_batch() rebuilds it for training.
+        self._step = None
+        self._eval_step = None
+        self.inference_only = False
         self.batch = engine.batch
         self._pending = deque()
         # one pinned result slot per IN-FLIGHT step: a slot goes back to the free list only after its value has been
         # read, so queueing many batches before popping (evaluate) can never overwrite an unread result
         self._free = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(4)]
+
+    @property
+    def step(self):
+        if self._step is None:
+            from ..models.resnet_engine import EngineTrainStep
+
+            self._step = EngineTrainStep(self.engine, self.optimizer, use_graph=self.use_graph)
+            self._eval_step = None  # the engine was (re)built for training: eval plans / graph must be re-captured
+        return self._step
+
+    @property
+    def eval_step(self):
+        if self._eval_step is None:
+            from ..models.resnet_engine import EngineEvalStep
+
+            if self._step is None and not self.inference_only:
+                _ = self.step  # training-capable trainer: evaluate on the training build (same buffers)
+            self._eval_step = EngineEvalStep(self.engine, use_graph=self.use_graph)
+        return self._eval_step
 
     def _enqueue_result(self) -> None:
         buf = self._free.pop() if self._free else torch.zeros(2, dtype=torch.float32).pin_memory()
@@ -63,13 +87,15 @@ class _EngineBackend:
         self._enqueue_result()
 
     def eval_batch(self, x, y) -> None:
+        step = self.eval_step  # (builds the engine on first use)
         self.engine.set_input(x, y)
-        self.eval_step.run()
+        step.run()
         self._enqueue_result()
 
     def predict_batch(self, x) -> torch.Tensor:
+        step = self.eval_step
         self.engine.set_input(x, None)
-        self.eval_step.run()
+        step.run()
         return self.engine.logits.clone()
 
     def predict_stream(self, arr: torch.Tensor) -> torch.Tensor:
@@ -78,6 +104,7 @@ class _EngineBackend:
         k runs; the logits of every batch go to one pinned result array with async copies; a single sync at the end.
         A pinned `arr` (what the pyfunc scoring workers provide) makes the H2D copies truly asynchronous."""
         e, B = self.engine, self.batch
+        step = self.eval_step  # builds the engine (for inference when this trainer never trained) before x_u8 is touched
         n = int(arr.shape[0])
         K = e.num_classes
         out = torch.empty((n, K), dtype=torch.float32).pin_memory() if n else torch.empty((0, K))
@@ -113,7 +140,7 @@ class _EngineBackend:
             done = torch.cuda.Event()
             done.record()
             self._stage_free[s] = done
-            self.eval_step.run()
+            step.run()
             out[k * B:k * B + m].copy_(e.logits[:m], non_blocking=True)
             ready = nxt
         cur.synchronize()
@@ -121,6 +148,8 @@ class _EngineBackend:
 
     def state_tensors(self) -> List[torch.Tensor]:
         e = self.engine
+        if not self.inference_only:
+            _ = self.step  # optimizer state exists (and weights may have moved to symmetric memory) only once attached
         opt = self.optimizer.opt if hasattr(self.optimizer, "opt") else self.optimizer
         return [e.params, e.running] + list(opt.state.values())
 
@@ -355,7 +384,7 @@ class Trainer:
         arr = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x)
         n = arr.shape[0]
         if (hasattr(self.backend, "predict_stream") and arr.dtype == torch.uint8 and arr.dim() == 4
-                and tuple(arr.shape[1:]) == tuple(self.backend.engine.x_u8.shape[1:])):
+                and tuple(arr.shape[1:]) == (self.backend.engine.image_size, self.backend.engine.image_size, 3)):
             return self.backend.predict_stream(arr).numpy()
         fixed = getattr(self.backend, "batch", None)
         bs = fixed or batch_size
@@ -373,6 +402,8 @@ class Trainer:
         from .. import optim
 
         self.compile(optim.SGD(0.0))
+        if hasattr(self.backend, "inference_only"):
+            self.backend.inference_only = True  # engine backend: build with the fused inference epilogues
 
     # ------------------------------------------------------------------------------------------------ state
     def broadcast_state(self, root: int = 0) -> None:
@@ -419,7 +450,10 @@ class Trainer:
     def summary(self) -> str:
         if _is_engine(self.model):
             n = self.model.num_parameters()
-            lines = [f"Model: {self.model.arch} (B200 engine)", f"Total params: {n:,}", f"Trainable params: {n:,}"]
+            tr = self.model.trainable_parameters() if hasattr(self.model, "trainable_parameters") else n
+            lines = [f"Model: {self.model.arch} (B200 engine)", f"Total params: {n:,}", f"Trainable params: {tr:,}"]
+            if tr != n:
+                lines.append(f"Non-trainable params: {n - tr:,}")
         else:
             tot = sum(p.numel() for p in self.model.parameters())
             tr = sum(p.numel() for p in self.model.parameters() if p.requires_grad)
