@@ -1034,6 +1034,73 @@ def case_mobilenet():
     return ok
 
 
+
+def case_tails():
+    """Last-CTA tails of the conv kernels: BatchNorm finalize after a forward GEMM with statistics, backward coefficients
+    after a dgrad GEMM with the fused reduction - vs the stand-alone bn_finalize / bn_bwd_coeffs kernels, run twice
+    (the ticket counter and the sums must be back at zero, as a CUDA-graph replay needs)."""
+    ok = True
+    e = ops.ext("_b200_ops")
+    g = torch.Generator(device=DEV).manual_seed(61)
+    for name, N, H, W, cin, cout, R, stride, pad in [s_ for s_ in CONV_SHAPES if s_[0] in ("1x1_64_256_56", "3x3_64_64_56", "3x3_256_256_14", "1x1_512_2048_7", "3x3s2_128_128_56")]:
+        x, w, Ho, Wo = make_conv_case(N, H, W, cin, cout, R, stride, pad)
+        wk = w.to(torch.bfloat16).reshape(R * R * cout, cin).contiguous()
+        y = torch.empty(N, Ho, Wo, cout, device=DEV, dtype=torch.bfloat16)
+        ssum = torch.zeros(cout, device=DEV); ssq = torch.zeros(cout, device=DEV)
+        gamma = torch.rand(cout, device=DEV, generator=g) + 0.5; beta = torch.randn(cout, device=DEV, generator=g)
+        rm = torch.zeros(cout, device=DEV); rv = torch.ones(cout, device=DEV)
+        outs = [torch.empty(cout, device=DEV) for _ in range(4)]
+        ctr = torch.zeros(1, device=DEV, dtype=torch.int32)
+        op = C.ConvForward(x, wk, y, R, R, stride, pad, ssum, ssq)
+        cnt = float(N * Ho * Wo)
+        op.plan.set_bn_finalize(ctr, gamma, beta, rm, rv, outs[0], outs[1], outs[2], outs[3], cnt, 0.1, 1e-5)
+        for rep in range(2):
+            op.run()
+        torch.cuda.synchronize()
+        # reference: statistics of the bf16 output, through the stand-alone kernel, applied twice to the running stats
+        s2 = torch.zeros(cout, device=DEV); q2 = torch.zeros(cout, device=DEV)
+        rm2 = torch.zeros(cout, device=DEV); rv2 = torch.ones(cout, device=DEV)
+        ref = [torch.empty(cout, device=DEV) for _ in range(4)]
+        for rep in range(2):
+            e.channel_stats(y, s2, q2)
+            e.bn_finalize(s2, q2, cnt, gamma, beta, rm2, rv2, 0.1, 1e-5, ref[0], ref[1], ref[2], ref[3], True)
+        torch.cuda.synchronize()
+        for nm, a_, b_ in (("mean", outs[0], ref[0]), ("invstd", outs[1], ref[1]), ("scale", outs[2], ref[2]), ("shift", outs[3], ref[3]),
+                           ("running_mean", rm, rm2), ("running_var", rv, rv2)):
+            ok &= report(f"tail_finalize_{nm}/{name}", float((a_ - b_).abs().max() / (b_.abs().max() + 1e-6)), 2e-3)
+        ok &= report(f"tail_finalize_sums_zeroed/{name}", float(ssum.abs().max() + ssq.abs().max() + ctr.abs().sum()), 0.0)
+        op.plan.enable_tail(False)   # eval mode: sums stay, nothing is finalized
+        before = outs[0].clone()
+        op.run(); torch.cuda.synchronize()
+        ok &= report(f"tail_disabled_keeps_sums/{name}", float(ssum.abs().max() == 0) + float((outs[0] - before).abs().max()), 0.0)
+        ssum.zero_(); ssq.zero_()
+        if stride == 1:
+            dy = torch.randn(N, Ho, Wo, cout, device=DEV, generator=g).to(torch.bfloat16)
+            yb = torch.randn(N, H, W, cin, device=DEV, generator=g).to(torch.bfloat16)
+            sc = torch.rand(cin, device=DEV, generator=g) + 0.5; sh = torch.randn(cin, device=DEV, generator=g) * 0.5
+            s_dz = torch.zeros(cin, device=DEV); s_dzy = torch.zeros(cin, device=DEV)
+            dx = torch.empty(N, H, W, cin, device=DEV, dtype=torch.bfloat16)
+            gam = torch.rand(cin, device=DEV, generator=g) + 0.5
+            mean = torch.randn(cin, device=DEV, generator=g) * 0.1; invstd = torch.rand(cin, device=DEV, generator=g) + 0.5
+            o = [torch.empty(cin, device=DEV) for _ in range(5)]
+            ctr2 = torch.zeros(1, device=DEV, dtype=torch.int32)
+            dg = C.ConvDgrad(dy, w, dx, R, R, stride, pad, bwd_stats=(yb, sc, sh, s_dz, s_dzy))
+            cnt2 = float(N * H * W)
+            dg.parts[0][0].set_bn_bwd_coeffs(ctr2, gam, mean, invstd, cnt2, o[0], o[1], o[2], o[3], o[4])
+            for rep in range(2):
+                dg.run()
+            torch.cuda.synchronize()
+            s3 = torch.zeros(cin, device=DEV); q3 = torch.zeros(cin, device=DEV)
+            e.bn_bwd_reduce(2, dx, None, None, yb, sc, sh, None, s3, q3)
+            r = [torch.empty(cin, device=DEV) for _ in range(5)]
+            e.bn_bwd_coeffs(s3, q3, gam, mean, invstd, cnt2, r[0], r[1], r[2], r[3], r[4])
+            torch.cuda.synchronize()
+            for nm, a_, b_ in zip(("dgamma", "dbeta", "cA", "cB", "cC"), o, r):
+                ok &= report(f"tail_bwd_{nm}/{name}", float((a_ - b_).abs().max() / (b_.abs().max() + 1e-6)), 3e-3)
+            ok &= report(f"tail_bwd_sums_zeroed/{name}", float(s_dz.abs().max() + s_dzy.abs().max() + ctr2.abs().sum()), 0.0)
+    return ok
+
+
 def case_umma_probe():
     """Row-shifted SWIZZLE_128B descriptors: which (shift, base_offset) combinations read the right rows?"""
     ext = ops.ext("_b200_probe")
@@ -1127,6 +1194,7 @@ CASES = {
     "big_numerics": case_big_numerics,
     "fused_infer": case_fused_infer,
     "mobilenet": case_mobilenet,
+    "tails": case_tails,
     "engine_unfused_block_grad": lambda: case_engine(quick=True, fuse_block_grad=False),
     "umma_probe": case_umma_probe,
 }

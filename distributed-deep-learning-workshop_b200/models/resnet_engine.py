@@ -114,6 +114,13 @@ class ResNet50Engine:
         # convolutions' epilogues (conv_igemm kStats = 4) - no BatchNorm pass at all.  B200DDL_NO_FUSED_INFER=1 disables.
         self.fused_inference = os.environ.get("B200DDL_NO_FUSED_INFER") != "1"
         self._infer_fused = False
+        # BatchNorm finalize / backward-coefficient computation in the LAST CTA of the GEMM that accumulated the sums
+        # (conv_igemm last-CTA tails) instead of ~100 tiny dependent launches per step; B200DDL_NO_TAILS=1 disables
+        self.fuse_tails = os.environ.get("B200DDL_NO_TAILS") != "1" and not self.fuse_bn_coeffs
+        self._fin_fwd = set()    # BatchNorms finalized by their producing conv's tail (training mode)
+        self._fin_bwd = set()    # BatchNorms whose backward coefficients come from a dgrad tail
+        self._tail_plans = []
+        self._tail_state = None
         self.wgrad_smem_budget = wgrad_smem_budget
         self.aux_streams: List[torch.cuda.Stream] = []
         if image_size % 32:
@@ -386,6 +393,25 @@ class ResNet50Engine:
         dz_keys = ["dzA", "dzB"]
         x_in = self.p0
         self._infer_fused = (not training) and self.fused_inference
+        self._fin_fwd.clear()
+        self._fin_bwd.clear()
+        self._tail_plans = []
+        self._tail_state = None
+        tail_counters = torch.zeros(256, device=dev, dtype=torch.int32)
+        n_tail = [0]
+
+        def next_counter():
+            n_tail[0] += 1
+            return tail_counters[n_tail[0] - 1:n_tail[0]]
+
+        def bwd_tail(plan, bn_name: str, count: int) -> None:
+            """dgrad plan that reduces sum(dz), sum(dz*y) of `bn_name`: its last CTA also emits dgamma / dbeta / A, B, C."""
+            if not (self.fuse_tails and training):
+                return
+            w_ = self.bnw[bn_name]
+            plan.set_bn_bwd_coeffs(next_counter(), self.p(bn_name + ".weight"), w_["mean"], w_["invstd"], float(count),
+                                   self.g(bn_name + ".weight"), self.g(bn_name + ".bias"), w_["cA"], w_["cB"], w_["cC"])
+            self._fin_bwd.add(bn_name)
         for bi, b in enumerate(self.blocks if self._infer_fused else []):
             # inference: every convolution writes its block activation directly (folded BN + ReLU [+ residual] epilogue)
             Hi, Ho, mid, cout = b.h_in, b.h_out, b.mid, b.mid * 4
@@ -438,6 +464,15 @@ class ResNet50Engine:
                 bw_ = self.bnw[b.name + "." + bnk]
                 y = A[b.name + "." + yk]
                 self._fwd[full] = C.ConvForward(xin, w2d, y, k, k, stride, pad, bw_["sum"], bw_["sqsum"], mc)
+                if training and self.fuse_tails:
+                    bname = b.name + "." + bnk
+                    cnt = N * y.shape[1] * y.shape[2]
+                    self._fwd[full].plan.set_bn_finalize(next_counter(), self.p(bname + ".weight"), self.p(bname + ".bias"),
+                                                         self.running_mean[bname], self.running_var[bname], bw_["mean"],
+                                                         bw_["invstd"], bw_["scale"], bw_["shift"], float(cnt),
+                                                         self.bn_momentum, self.bn_eps)
+                    self._fin_fwd.add(bname)
+                    self._tail_plans.append(self._fwd[full].plan)
                 if training:
                     dy = scr(self._dy_key[cname], y.shape)
                     gw = self.g(full + ".weight")
@@ -473,6 +508,12 @@ class ResNet50Engine:
                         self._fused_reduce.add(b.name + "." + pbn)
                     dgr = C.ConvDgrad(dy, self.p(full + ".weight"), dx, k, k, d_stride, pad, mc, wbufs=wd_views(full),
                                       bwd_stats=bwd_stats, block_grad=block_grad)
+                    if bwd_stats is not None:     # reduces bn1 (conv2's dgrad, count = conv1's output grid) or bn2 (conv3's)
+                        pbn = b.name + (".bn1" if cname == "conv2" else ".bn2")
+                        bwd_tail(dgr.parts[0][0], pbn, N * (Hi * Hi if cname == "conv2" else Ho * Ho))
+                    if block_grad is not None:    # reduces the previous block's bn3
+                        pb = self.blocks[bi - 1]
+                        bwd_tail(dgr.parts[0][0], pb.name + ".bn3", N * pb.h_out * pb.h_out)
                     self._dg[full] = dgr
                     self._dgrads.append(dgr)
             x_in = A[b.name + ".out"]
@@ -501,6 +542,8 @@ class ResNet50Engine:
     # ------------------------------------------------------------------------------------------------ forward
     def _bn_fwd(self, bn: str, count: float, training: bool) -> Dict[str, torch.Tensor]:
         w = self.bnw[bn]
+        if training and bn in self._fin_fwd:
+            return w  # finalized by the last CTA of the conv that produced the statistics
         self._e.bn_finalize(w["sum"], w["sqsum"], float(count), self.p(bn + ".weight"), self.p(bn + ".bias"),
                             self.running_mean[bn], self.running_var[bn], self.bn_momentum, self.bn_eps, w["mean"],
                             w["invstd"], w["scale"], w["shift"], training)
@@ -532,6 +575,12 @@ class ResNet50Engine:
         """x_u8 / labels (static inputs) -> logits, loss stats.  All launches go to the current stream."""
         e, N, A = self._e, self.batch, self.act
         w0 = self.bnw["bn1"]
+        if self._tail_plans and self._tail_state != training:
+            # eval-mode forwards of a training engine must not update running statistics: the conv tails are switched off
+            # (host-side kernel parameter, captured by value in the train / eval CUDA graphs) and bn_finalize runs instead
+            for pl in self._tail_plans:
+                pl.enable_tail(bool(training))
+            self._tail_state = training
         if training and self.fuse_bn_coeffs:
             e.zero_(self._bn_fwd_sums)  # nobody zeroes them after use on the fused path
         if self.native_stem:
@@ -613,8 +662,9 @@ class ResNet50Engine:
             e.bn_bwd_apply_fused(src, y, sc, sh, w["sum_dz"], w["sum_dzy"], self.p(bn + ".weight"), w["mean"],
                                  w["invstd"], float(count), self.g(bn + ".weight"), self.g(bn + ".bias"), dy)
         else:
-            e.bn_bwd_coeffs(w["sum_dz"], w["sum_dzy"], self.p(bn + ".weight"), w["mean"], w["invstd"], float(count),
-                            self.g(bn + ".weight"), self.g(bn + ".bias"), w["cA"], w["cB"], w["cC"])
+            if bn not in self._fin_bwd:  # otherwise the dgrad GEMM's last CTA already produced dgamma / dbeta / A, B, C
+                e.bn_bwd_coeffs(w["sum_dz"], w["sum_dzy"], self.p(bn + ".weight"), w["mean"], w["invstd"], float(count),
+                                self.g(bn + ".weight"), self.g(bn + ".bias"), w["cA"], w["cB"], w["cC"])
             e.bn_bwd_apply(src, y, sc, sh, w["cA"], w["cB"], w["cC"], dy)
         self._ready(bn + ".weight", bn + ".bias")
 

@@ -82,6 +82,11 @@ def test_reference_model_mobilenetv2_on_native_kernels(checks):
     assert checks.case_mobilenet()
 
 
+def test_last_cta_batchnorm_tails(checks):
+    """BatchNorm finalize / backward coefficients computed by the last CTA of the GEMM that accumulated the sums."""
+    assert checks.case_tails()
+
+
 def test_conv_numerics_at_benchmark_batch(checks):
     """forward (+statistics) / dgrad / wgrad vs fp32 at the batch-256 layer shapes the benchmark runs."""
     assert checks.case_big_numerics()
