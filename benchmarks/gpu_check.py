@@ -932,7 +932,7 @@ def case_fused_infer():
         e2.build(training=build_training)
         st = EngineEvalStep(e2)
         t = time_fn(st.run, iters=10, warmup=3)
-        print(f"TIME eval_forward/{label} batch 256: {t*1e3:.0f} us = {256 / t:.0f} images/s", flush=True)
+        print(f"TIME eval_forward/{label} batch 256: {t*1e3:.0f} us = {256 / t * 1e3:.0f} images/s", flush=True)
         del e2, st
         torch.cuda.empty_cache()
     return ok
@@ -1020,7 +1020,7 @@ def case_mobilenet():
                  f"{hist.history['loss'][0]:.3f} -> {hist.history['loss'][-1]:.3f}")
     step = tr.backend.step
     t = time_fn(step.run, iters=10, warmup=3)
-    print(f"TIME mobilenet_engine train step batch 64: {t*1e3:.0f} us = {64 / t:.0f} images/s", flush=True)
+    print(f"TIME mobilenet_engine train step batch 64: {t*1e3:.0f} us = {64 / t * 1e3:.0f} images/s", flush=True)
     import time as _t
     refm = build_model(224, 224, 3, K, dropout=0.0, arch="mobilenetv2_torch", seed=4).to(DEV)
     tr2 = Trainer(refm, device=DEV).compile(optimizer=optim.Adam(0.01))

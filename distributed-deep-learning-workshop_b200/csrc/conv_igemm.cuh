@@ -85,10 +85,6 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
   constexpr bool kHasY = kStats == 2 || kStats == 3;       // a pre-BN tile accompanies every output chunk
   constexpr bool kAffine = kStats == 4;                    // epilogue: acc*scale + shift (+ residual) -> activation
   constexpr bool kRowAdd = kStats == 3 || kStats == 4;     // per-row global loads of an additive tensor in the epilogue
-#ifndef B200DDL_ADD_AHEAD
-#define B200DDL_ADD_AHEAD 1
-#endif
-  constexpr int kAddAhead = B200DDL_ADD_AHEAD;             // 32-column halves the additive rows are prefetched ahead (1 or 2)
   constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -380,8 +376,12 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
       // accumulator wait, so the global-load latency hides behind the TMEM wait and the previous half's packing.
       const __nv_bfloat16* arow = nullptr;
       const uint8_t* mrow = nullptr;
-      uint4 gq[3][4];               // queue: [0] = current half, [1] = next, [2] = the one after (rotated by moves)
-      uint32_t mq[3] = {0u, 0u, 0u};
+      // Two STATICALLY indexed slots (slot = h, the 32-column half inside a 64-column chunk): half i is consumed from slot
+      // i & 1 while half i + 1 loads into the other one.  (A rotating queue - "gq[0] = gq[1]" - was tried for a deeper
+      // prefetch: the register move needs the value, so every rotation waited for the load that had just been issued and
+      // the kernel went from 302 to 353 us.  Prefetch slots must never be moved.)
+      uint4 gq[2][4];
+      uint32_t mq[2] = {0u, 0u};
       if (kAffine) {
         // per-channel scale / shift of this tile's N-block -> shared memory (read back as float4 broadcasts); every thread
         // passed the previous tile's last staging barrier after its last read, and the first chunk barrier below publishes
@@ -392,7 +392,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
       }
       if (kRowAdd) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gq[0][j] = gq[1][j] = gq[2][j] = make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0; j < 4; ++j) gq[0][j] = gq[1][j] = make_uint4(0u, 0u, 0u, 0u);
       }
       if (kRowAdd && (kStats == 3 || (p.add_src != nullptr && p.mode == 0))) {
         const int64_t grow = static_cast<int64_t>(m_tile) * kBlockM + row;
@@ -413,15 +413,8 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
         if (arow != nullptr) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) gq[0][j] = __ldg(reinterpret_cast<const uint4*>(arow) + j);
-          if (kAddAhead == 2) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) gq[1][j] = __ldg(reinterpret_cast<const uint4*>(arow + 32) + j);
-          }
         }
-        if (mrow != nullptr) {
-          mq[0] = __ldg(reinterpret_cast<const uint32_t*>(mrow));
-          if (kAddAhead == 2) mq[1] = __ldg(reinterpret_cast<const uint32_t*>(mrow + 4));
-        }
+        if (mrow != nullptr) mq[0] = __ldg(reinterpret_cast<const uint32_t*>(mrow));
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -440,14 +433,14 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
         for (int h = 0; h < 2; ++h) {
           uint32_t r[32];
           if (kRowAdd) {
-            // prefetch kAddAhead halves ahead into the queue slot that reaches [0] exactly when that half is processed
-            const int nxt = c64 * 64 + h * 32 + 32 * kAddAhead;
+            // prefetch the next half (h ^ 1 of this chunk, or h = 0 of the next chunk) into the other slot
+            const int nxt = c64 * 64 + h * 32 + 32;
             if (nxt < BLOCK_N) {
               if (arow != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) gq[kAddAhead][j] = __ldg(reinterpret_cast<const uint4*>(arow + nxt) + j);
+                for (int j = 0; j < 4; ++j) gq[h ^ 1][j] = __ldg(reinterpret_cast<const uint4*>(arow + nxt) + j);
               }
-              if (mrow != nullptr) mq[kAddAhead] = __ldg(reinterpret_cast<const uint32_t*>(mrow + (nxt >> 3)));
+              if (mrow != nullptr) mq[h ^ 1] = __ldg(reinterpret_cast<const uint32_t*>(mrow + (nxt >> 3)));
             }
           }
           tmem_ld_32x32b_x32(taddr + c64 * 64 + h * 32, r);
@@ -459,7 +452,7 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
             const int act = p.ep_act;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t gw[4] = {gq[0][j].x, gq[0][j].y, gq[0][j].z, gq[0][j].w};
+              const uint32_t gw[4] = {gq[h][j].x, gq[h][j].y, gq[h][j].z, gq[h][j].w};
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const float4 sc = sc4[2 * j + e], sh = sh4[2 * j + e];
@@ -476,33 +469,20 @@ conv_igemm_kernel(const __grid_constant__ TmapArray4 tmA, const __grid_constant_
                 }
               }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              gq[0][j] = gq[1][j];
-              gq[1][j] = gq[2][j];
-            }
           }
           if (kStats == 3) {
             // dz = (main-path gradient + skip gradient) * [block output > 0]
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t gw[4] = {gq[0][j].x, gq[0][j].y, gq[0][j].z, gq[0][j].w};
+              const uint32_t gw[4] = {gq[h][j].x, gq[h][j].y, gq[h][j].z, gq[h][j].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float lo = __uint_as_float(r[8 * j + 2 * e]) + __uint_as_float(gw[e] << 16);
                 const float hi = __uint_as_float(r[8 * j + 2 * e + 1]) + __uint_as_float(gw[e] & 0xFFFF0000u);
-                r[8 * j + 2 * e] = ((mq[0] >> (8 * j + 2 * e)) & 1u) ? __float_as_uint(lo) : 0u;
-                r[8 * j + 2 * e + 1] = ((mq[0] >> (8 * j + 2 * e + 1)) & 1u) ? __float_as_uint(hi) : 0u;
+                r[8 * j + 2 * e] = ((mq[h] >> (8 * j + 2 * e)) & 1u) ? __float_as_uint(lo) : 0u;
+                r[8 * j + 2 * e + 1] = ((mq[h] >> (8 * j + 2 * e + 1)) & 1u) ? __float_as_uint(hi) : 0u;
               }
             }
-            // rotate the queue
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              gq[0][j] = gq[1][j];
-              gq[1][j] = gq[2][j];
-            }
-            mq[0] = mq[1];
-            mq[1] = mq[2];
           }
           if (c64 == BLOCK_N / 64 - 1 && h == 1) {
             // all TMEM reads of this accumulator are done: hand it back to the MMA warp

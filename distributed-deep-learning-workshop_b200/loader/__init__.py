@@ -267,7 +267,7 @@ class _GpuDecodeDataset:
             if head == b"\xff\xd8\xff":
                 with warnings.catch_warnings():
                     warnings.simplefilter("ignore")  # read-only buffer: decode_jpeg does not write to it
-                    jpeg_data.append(torch.frombuffer(buf, dtype=torch.uint8))
+                    jpeg_data.append(torch.from_numpy(np.frombuffer(buf, dtype=np.uint8)))  # zero-copy view of the Arrow buffer
                 jpeg_idx.append(i)
                 self.compressed_bytes += buf.size
             else:
