@@ -12,7 +12,7 @@ for c in tails block_grad fused_infer engine; do
 done
 for r in 1 2; do
   timeout 200 python -u bench.py --steps 40 --warmup 5 --no-e2e --no-baseline > $O/ab6_default_$r.log 2>&1; echo "bench default $r rc=$?"
-  B200DDL_NO_TAILS=1 timeout 200 python -u bench.py --steps 40 --warmup 5 --no-e2e --no-baseline > $O/ab6_notails_$r.log 2>&1; echo "bench no-tails $r rc=$?"
+  B200DDL_TAILS=1 timeout 200 python -u bench.py --steps 40 --warmup 5 --no-e2e --no-baseline > $O/ab6_notails_$r.log 2>&1; echo "bench no-tails $r rc=$?"
 done
 python - <<'PY'
 import glob, json

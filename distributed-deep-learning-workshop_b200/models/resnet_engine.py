@@ -114,9 +114,12 @@ class ResNet50Engine:
         # convolutions' epilogues (conv_igemm kStats = 4) - no BatchNorm pass at all.  B200DDL_NO_FUSED_INFER=1 disables.
         self.fused_inference = os.environ.get("B200DDL_NO_FUSED_INFER") != "1"
         self._infer_fused = False
-        # BatchNorm finalize / backward-coefficient computation in the LAST CTA of the GEMM that accumulated the sums
-        # (conv_igemm last-CTA tails) instead of ~100 tiny dependent launches per step; B200DDL_NO_TAILS=1 disables
-        self.fuse_tails = os.environ.get("B200DDL_NO_TAILS") != "1" and not self.fuse_bn_coeffs
+        # OPT-IN (B200DDL_TAILS=1): BatchNorm finalize / backward-coefficient computation in the LAST CTA of the GEMM that
+        # accumulated the sums (conv_igemm last-CTA tails) instead of ~100 tiny dependent launches per step.  Numerically
+        # equivalent (gpu_check.py tails) but MEASURED SLOWER: 17.64 vs 17.11 ms per step, interleaved, both at 1965 MHz
+        # (profiles/r2_ab6_*.json): fence + ticket + a serial per-channel loop in ONE CTA at the end of every GEMM costs
+        # more than the ~4 us of a tiny dependent kernel that runs on all SMs.
+        self.fuse_tails = os.environ.get("B200DDL_TAILS") == "1" and not self.fuse_bn_coeffs
         self._fin_fwd = set()    # BatchNorms finalized by their producing conv's tail (training mode)
         self._fin_bwd = set()    # BatchNorms whose backward coefficients come from a dgrad tail
         self._tail_plans = []

@@ -87,6 +87,12 @@ def test_last_cta_batchnorm_tails(checks):
     assert checks.case_tails()
 
 
+def test_resnet50_engine_with_last_cta_tails_matches_torchvision(checks, monkeypatch):
+    """Opt-in path (B200DDL_TAILS=1): BatchNorm finalize / backward coefficients in the GEMMs' last CTAs."""
+    monkeypatch.setenv("B200DDL_TAILS", "1")
+    assert checks.case_engine(quick=True)
+
+
 def test_conv_numerics_at_benchmark_batch(checks):
     """forward (+statistics) / dgrad / wgrad vs fp32 at the batch-256 layer shapes the benchmark runs."""
     assert checks.case_big_numerics()
