@@ -8,6 +8,7 @@ W=${WORLD:-8}
 python -u benchmarks/preflight.py > $O/preflight.log 2>&1; echo "preflight rc=$?"; grep PREFLIGHT $O/preflight.log | head -2
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1"
 timeout 400 $TR --master-port 29641 bench.py --gpus $W --steps 30 --warmup 5 --no-baseline > $O/bench_w$W.log 2>&1; echo "bench w$W rc=$?"
+timeout 300 $TR --master-port 29651 bench.py --gpus $W --steps 30 --warmup 5 --no-baseline --no-e2e --algo p2p > $O/bench_w${W}_p2p.log 2>&1; echo "bench w$W p2p rc=$?"
 # comm-free control: W independent 1-GPU steps on the same box at the same time (what the clocks / power cap alone cost)
 for i in $(seq 0 $((W-1))); do
   CUDA_VISIBLE_DEVICES=$i timeout 300 python -u bench.py --steps 30 --warmup 5 --no-e2e --no-baseline > $O/control_w${W}_gpu$i.log 2>&1 &

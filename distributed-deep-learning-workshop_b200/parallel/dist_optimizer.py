@@ -36,7 +36,7 @@ class DistributedOptimizer:
 
     def __init__(self, optimizer: FlatOptimizer, bucket_mb: float = 16.0, overlap: bool = True, algo: str = "auto",
                  comm_blocks: int = 32, average: bool = True, fused_update: bool = False, tail_mb: float = 1.0,
-                 nvls_min_mb: float = 32.0):
+                 nvls_min_mb: Optional[float] = None, nvls_blocks: int = 16):
         self.opt = optimizer
         self.bucket_bytes = int(bucket_mb * 2 ** 20)
         # The LAST bucket to complete is the only all-reduce nothing can hide (backward has ended): keep it small.  The
@@ -44,7 +44,13 @@ class DistributedOptimizer:
         self.tail_bytes = int(tail_mb * 2 ** 20)
         # 'auto' picks the kernel PER BUCKET from the measured sweeps (profiles/): the P2P two-shot wins below ~32 MB
         # (8 GPUs, 16 MB: 92 vs 115 us), the in-switch NVLS reduction above
+        # measured crossover (profiles/r2_allreduce_w{2,4,8}.log, 16 MB bucket): 2 GPUs P2P 43 us vs NVLS 56; 4 GPUs NVLS 55 vs
+        # P2P 62-76 -> with 2 ranks P2P always, with more ranks NVLS from 1 MB up (the in-switch reduction needs few CTAs:
+        # 8-16 are as fast as 64, so NVLS buckets use `nvls_blocks`)
+        if nvls_min_mb is None:
+            nvls_min_mb = 1e9 if core.size() <= 2 else 1.0
         self.nvls_min_bytes = int(nvls_min_mb * 2 ** 20)
+        self.nvls_blocks = nvls_blocks
         self.overlap = overlap
         self.algo = algo
         # CTAs of a comm kernel (512 threads each).  16 MB bucket, 2 GPUs, two-shot P2P: 8 CTAs 121 us, 16: 67, 32: 43, 64: 40
@@ -207,7 +213,7 @@ class DistributedOptimizer:
                     if self.timeline is not None else contextlib.nullcontext())
             with torch.cuda.stream(cs), span:
                 if algo == "nvls":
-                    self._comm.twoshot_nvls(b.lo, n, "f32", scale, self.comm_blocks)
+                    self._comm.twoshot_nvls(b.lo, n, "f32", scale, self.nvls_blocks if self.algo == "auto-sym" else self.comm_blocks)
                 elif algo == "p2p":
                     self._comm.twoshot_p2p(b.lo, n, "f32", scale, self.comm_blocks)
                 else:
