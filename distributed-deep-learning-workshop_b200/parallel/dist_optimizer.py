@@ -36,7 +36,7 @@ class DistributedOptimizer:
 
     def __init__(self, optimizer: FlatOptimizer, bucket_mb: float = 16.0, overlap: bool = True, algo: str = "auto",
                  comm_blocks: int = 32, average: bool = True, fused_update: bool = False, tail_mb: float = 1.0,
-                 nvls_min_mb: Optional[float] = None, nvls_blocks: int = 16):
+                 nvls_min_mb: Optional[float] = None, nvls_blocks: Optional[int] = None):
         self.opt = optimizer
         self.bucket_bytes = int(bucket_mb * 2 ** 20)
         # The LAST bucket to complete is the only all-reduce nothing can hide (backward has ended): keep it small.  The
@@ -50,7 +50,9 @@ class DistributedOptimizer:
         if nvls_min_mb is None:
             nvls_min_mb = 1e9 if core.size() <= 2 else 1.0
         self.nvls_min_bytes = int(nvls_min_mb * 2 ** 20)
-        self.nvls_blocks = nvls_blocks
+        # 8 GPUs, 16 MB (profiles/r2_allreduce_sweep_w8.json): 8 CTAs 51.8 us, 16: 57.9, 32: 64.9 - each rank only reduces
+        # 1/world of the bucket, so the more ranks the fewer CTAs it takes to saturate the switch's reduction path
+        self.nvls_blocks = nvls_blocks if nvls_blocks is not None else (8 if core.size() >= 8 else 16)
         self.overlap = overlap
         self.algo = algo
         # CTAs of a comm kernel (512 threads each).  16 MB bucket, 2 GPUs, two-shot P2P: 8 CTAs 121 us, 16: 67, 32: 43, 64: 40

@@ -119,8 +119,9 @@ class _FragmentScorer:
     """Scores fragments with ONE loaded model; reads fragment k+1 on a helper thread while fragment k is on the GPU.
     Image payloads of generated fragments are written straight into pinned host buffers (two, alternating)."""
 
-    def __init__(self, model_uri: str, column: str, gpu: Optional[int]):
+    def __init__(self, model_uri: str, column: str, gpu: Optional[int], result_type: str = "string"):
         self.column = column
+        self.arrow_type = _RESULT_TYPES.get(result_type, pa.string())
         self.cuda = False
         if gpu is not None and gpu >= 0:
             try:
@@ -182,7 +183,23 @@ class _FragmentScorer:
                 t0 = time.perf_counter()
                 out = np.asarray(self.model.predict(_series_of(table.column(self.column))))
                 self.predict_s += time.perf_counter() - t0
-                yield pos, out
+                # the Arrow array is built HERE (in parallel across workers): the driver only concatenates buffers
+                yield pos, pa.array(out.tolist() if self.arrow_type == pa.string() else out, type=self.arrow_type)
+
+    def warm_up(self, fragment) -> float:
+        """Score a few rows of `fragment` once so that lazy model initialisation (engine build, CUDA-graph capture, cuDNN
+        autotune of a torch model, ...) happens at worker start-up, like a Spark executor loading its broadcast model,
+        and not inside the first timed fragment.  Returns the seconds it took."""
+        import time
+        from dataclasses import replace
+
+        t0 = time.perf_counter()
+        try:
+            small = replace(fragment, rows=min(fragment.rows, 8))
+            self.model.predict(_series_of(small.read([self.column]).column(self.column)))
+        except Exception:
+            pass  # warm-up is best effort; real errors surface on the first scored fragment
+        return time.perf_counter() - t0
 
 
 def _pool_worker(rank: int, conn) -> None:
@@ -192,10 +209,12 @@ def _pool_worker(rank: int, conn) -> None:
     try:
         from .. import tracking
 
-        _, model_uri, tracking_uri, column = conn.recv()
+        _, model_uri, tracking_uri, column, result_type, warm_frag = conn.recv()
         tracking.set_tracking_uri(tracking_uri)
-        scorer = _FragmentScorer(model_uri, column, rank)
-        conn.send(("ready", rank, None))
+        scorer = _FragmentScorer(model_uri, column, rank, result_type)
+        warm_s = scorer.warm_up(warm_frag) if warm_frag is not None else 0.0
+        scorer.read_s = scorer.predict_s = 0.0
+        conn.send(("ready", rank, warm_s))
 
         def pull():
             while True:
@@ -227,20 +246,25 @@ class _WorkerPool:
     Spark executor's python worker.  Fragments are dispatched dynamically: every worker always has `depth` fragments
     outstanding, a new one is sent as soon as a result comes back (load balancing without a shared queue)."""
 
-    def __init__(self, model_uri: str, column: str, workers: int, depth: int = 2):
+    def __init__(self, model_uri: str, column: str, workers: int, depth: int = 2, result_type: str = "string",
+                 warm_fragment=None):
+        import time
+
         from .. import tracking
         from ..utils.procpool import start_worker
 
         self.column = column
+        self.result_type = result_type
         self.depth = depth
         self.procs, self.conns = [], []
+        t0 = time.time()
         for i in range(workers):
             p, c = start_worker("b200ddl.pyfunc._score_worker", i)
-            c.send(("init", model_uri, tracking.get_tracking_uri(), column))
+            c.send(("init", model_uri, tracking.get_tracking_uri(), column, result_type, warm_fragment))
             self.procs.append(p)
             self.conns.append(c)
-        for i, c in enumerate(self.conns):
-            self._expect(i, "ready")
+        self.warm_s = [self._expect(i, "ready")[2] for i in range(len(self.conns))]
+        self.startup_s = time.time() - t0   # process start + model load + warm-up of all workers (one-off)
 
     def _recv(self, i: int, timeout: float = 1800.0):
         c = self.conns[i]
@@ -393,17 +417,25 @@ class ShardUDF:
         workers = min(self._workers(), max(1, len(frags)))
         per_worker: List[dict] = []
         try:
+            startup_s = 0.0
             if workers <= 1:
-                if self._local is None or self._local.column != column:
-                    self._local = _FragmentScorer(self.model_uri, column, 0)
+                if self._local is None or self._local.column != column or self._local.arrow_type != typ:
+                    self._local = _FragmentScorer(self.model_uri, column, 0, self.result_type)
+                    if frags:
+                        startup_s = self._local.warm_up(frags[0])
+                        self._local.read_s = self._local.predict_s = 0.0
+                t0 = time.time()
                 res = dict(self._local.score(enumerate(frags)))
                 per_worker = [{"worker": 0, "read_s": self._local.read_s, "predict_s": self._local.predict_s}]
             else:
-                if self._pool is None or self._pool.column != column or len(self._pool.procs) != workers:
+                if (self._pool is None or self._pool.column != column or len(self._pool.procs) != workers
+                        or self._pool.result_type != self.result_type):
                     if self._pool is not None:
                         self._pool.close()
-                    self._pool = _WorkerPool(self.model_uri, column, workers)
-                t0 = time.time()  # worker start-up (process spawn + model load) is a one-off, reported separately
+                    self._pool = _WorkerPool(self.model_uri, column, workers, result_type=self.result_type,
+                                             warm_fragment=frags[0] if frags else None)
+                    startup_s = self._pool.startup_s
+                t0 = time.time()  # worker start-up (process start + model load + warm-up) is a one-off, reported separately
                 res, per_worker = self._pool.run(frags)
         finally:
             for p in self._tmp:
@@ -412,11 +444,10 @@ class ShardUDF:
                 except OSError:
                     pass
             self._tmp = []
-        arrays = [pa.array(np.asarray(res[i]).tolist() if typ == pa.string() else np.asarray(res[i]), type=typ)
-                  for i in range(len(frags))]
+        arrays = [res[i] for i in range(len(frags))]   # Arrow arrays built by the workers: concatenation moves no elements
         dt = time.time() - t0
         self.stats = {"rows": n, "workers": workers, "fragments": len(frags), "seconds": dt,
-                      "rows_per_sec": n / max(dt, 1e-9), "per_worker": per_worker}
+                      "rows_per_sec": n / max(dt, 1e-9), "startup_seconds": startup_s, "per_worker": per_worker}
         return pa.chunked_array(arrays, type=typ)
 
     def close(self) -> None:
