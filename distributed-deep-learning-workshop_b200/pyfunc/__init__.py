@@ -137,6 +137,7 @@ class _FragmentScorer:
         self._slot = 0
         self.read_s = 0.0
         self.predict_s = 0.0
+        self.wall_s = 0.0   # first fragment received -> last result handed over, of the latest job
 
     def _alloc(self, nbytes: int):
         if not self.cuda:
@@ -164,6 +165,7 @@ class _FragmentScorer:
         import concurrent.futures as cf
         import time
 
+        t_job = time.perf_counter()
         with cf.ThreadPoolExecutor(1) as ex:
             nxt = None
             it = iter(frags_iter)
@@ -185,6 +187,7 @@ class _FragmentScorer:
                 self.predict_s += time.perf_counter() - t0
                 # the Arrow array is built HERE (in parallel across workers): the driver only concatenates buffers
                 yield pos, pa.array(out.tolist() if self.arrow_type == pa.string() else out, type=self.arrow_type)
+                self.wall_s = time.perf_counter() - t_job
 
     def warm_up(self, fragment) -> float:
         """Score a few rows of `fragment` once so that lazy model initialisation (engine build, CUDA-graph capture, cuDNN
@@ -195,8 +198,14 @@ class _FragmentScorer:
 
         t0 = time.perf_counter()
         try:
-            small = replace(fragment, rows=min(fragment.rows, 8))
-            self.model.predict(_series_of(small.read([self.column]).column(self.column)))
+            if self.cuda:
+                # full-size reads: both pinned host buffers get their final size now (cudaHostAlloc of ~0.6 GB is ~0.2 s)
+                for _ in range(2 if fragment.kind == "synthetic" else 1):   # only generated fragments use the pinned slots
+                    table = fragment.read([self.column], pinned_alloc=self._alloc)
+                table = table.slice(0, min(table.num_rows, 1024))
+            else:
+                table = replace(fragment, rows=min(fragment.rows, 8)).read([self.column])
+            self.model.predict(_series_of(table.column(self.column)))
         except Exception:
             pass  # warm-up is best effort; real errors surface on the first scored fragment
         return time.perf_counter() - t0
@@ -229,7 +238,8 @@ def _pool_worker(rank: int, conn) -> None:
             # a job = a stream of ('frag', pos, fragment) messages terminated by ('end',); None shuts the worker down
             for pos, out in scorer.score(pull()):
                 conn.send(("res", pos, out))
-            conn.send(("done", rank, {"read_s": scorer.read_s, "predict_s": scorer.predict_s}))
+            conn.send(("done", rank, {"read_s": scorer.read_s, "predict_s": scorer.predict_s,
+                                       "wall_s": scorer.wall_s}))
     except (EOFError, SystemExit):
         return
     except BaseException as ex:  # surface the failure instead of leaving the driver waiting

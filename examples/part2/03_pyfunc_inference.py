@@ -111,6 +111,8 @@ if N_INFER > 0:
     print(head.to_string(index=False))
     print("INFERENCE_STATS " + json.dumps({"rows": st["rows"], "workers": st["workers"], "fragments": st["fragments"],
                                            "seconds": st["seconds"], "images_per_sec": st["rows_per_sec"],
+                                           "startup_seconds": st.get("startup_seconds"),
+                                           "serving_batch": int(os.environ.get("WORKSHOP_INFER_BATCH", "0")) or BATCH_SIZE,
                                            "per_worker": st["per_worker"], "api": "pyfunc.spark_udf over data.synthetic_scan",
                                            "image": f"{IMG_HEIGHT}x{IMG_WIDTH}x3 uint8", "arch": ARCH, "batch": BATCH_SIZE}))
 classify_udf.close()
