@@ -165,16 +165,19 @@ class _FragmentScorer:
         import concurrent.futures as cf
         import time
 
-        t_job = time.perf_counter()
+        t_job = None
         with cf.ThreadPoolExecutor(1) as ex:
             nxt = None
             it = iter(frags_iter)
 
             def submit():
+                nonlocal t_job
                 try:
                     pos, frag = next(it)
                 except StopIteration:
                     return None
+                if t_job is None:
+                    t_job = time.perf_counter()   # the job starts when its first fragment arrives, not while idle between jobs
                 return pos, ex.submit(self._read, frag)
 
             nxt = submit()
@@ -211,6 +214,11 @@ class _FragmentScorer:
         return time.perf_counter() - t0
 
 
+def _frag_sig(f) -> tuple:
+    # what a warm-up prepares: the generator state + pinned slot size of generated fragments; file-backed ones only the model
+    return () if f is None else ((f.kind, f.rows, f.spec) if f.kind == "synthetic" else ("file",))
+
+
 def _pool_worker(rank: int, conn) -> None:
     """Persistent scoring process: pinned to GPU `rank`, model loaded ONCE; the driver keeps two fragments in flight per
     worker so fragment k+1 is read while fragment k is scored."""
@@ -232,6 +240,11 @@ def _pool_worker(rank: int, conn) -> None:
                     raise SystemExit(0)
                 if item[0] == "end":
                     return
+                if item[0] == "warm":   # a table of a different kind / fragment size than the one the pool was started on
+                    secs = scorer.warm_up(item[1])
+                    scorer.read_s = scorer.predict_s = 0.0
+                    conn.send(("ready", rank, secs))
+                    continue
                 yield item[1], item[2]
 
         while True:
@@ -275,6 +288,21 @@ class _WorkerPool:
             self.conns.append(c)
         self.warm_s = [self._expect(i, "ready")[2] for i in range(len(self.conns))]
         self.startup_s = time.time() - t0   # process start + model load + warm-up of all workers (one-off)
+        self.warm_sig = _frag_sig(warm_fragment)
+
+    def warm(self, fragment) -> float:
+        """Re-warm every worker for a table of a different kind / fragment size (pinned buffers, generator state): once
+        per new table shape, outside the scored region.  Returns the wall seconds."""
+        import time
+
+        if fragment is None or _frag_sig(fragment) == self.warm_sig:
+            return 0.0
+        t0 = time.time()
+        for c in self.conns:
+            c.send(("warm", fragment))
+        self.warm_s = [self._expect(i, "ready")[2] for i in range(len(self.conns))]
+        self.warm_sig = _frag_sig(fragment)
+        return time.time() - t0
 
     def _recv(self, i: int, timeout: float = 1800.0):
         c = self.conns[i]
@@ -377,6 +405,7 @@ class ShardUDF:
         self.num_workers = num_workers
         self.batch_rows = batch_rows
         self._local: Optional[_FragmentScorer] = None
+        self._local_sig = None
         self._pool: Optional[_WorkerPool] = None
         self._tmp: List[str] = []
         self.stats: Dict[str, Any] = {}
@@ -431,9 +460,11 @@ class ShardUDF:
             if workers <= 1:
                 if self._local is None or self._local.column != column or self._local.arrow_type != typ:
                     self._local = _FragmentScorer(self.model_uri, column, 0, self.result_type)
-                    if frags:
-                        startup_s = self._local.warm_up(frags[0])
-                        self._local.read_s = self._local.predict_s = 0.0
+                    self._local_sig = None
+                if frags and _frag_sig(frags[0]) != self._local_sig:
+                    startup_s = self._local.warm_up(frags[0])
+                    self._local.read_s = self._local.predict_s = 0.0
+                    self._local_sig = _frag_sig(frags[0])
                 t0 = time.time()
                 res = dict(self._local.score(enumerate(frags)))
                 per_worker = [{"worker": 0, "read_s": self._local.read_s, "predict_s": self._local.predict_s}]
@@ -445,6 +476,7 @@ class ShardUDF:
                     self._pool = _WorkerPool(self.model_uri, column, workers, result_type=self.result_type,
                                              warm_fragment=frags[0] if frags else None)
                     startup_s = self._pool.startup_s
+                startup_s += self._pool.warm(frags[0] if frags else None)
                 t0 = time.time()  # worker start-up (process start + model load + warm-up) is a one-off, reported separately
                 res, per_worker = self._pool.run(frags)
         finally:

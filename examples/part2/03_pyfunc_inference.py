@@ -104,15 +104,17 @@ print(f"scored {len(pdf)} rows with {classify_udf.stats['workers']} worker(s): "
 N_INFER = int(os.environ.get("WORKSHOP_INFER_IMAGES", "0"))
 if N_INFER > 0:
     from b200ddl.data import synthetic_scan
-    big = synthetic_scan(N_INFER, size=(IMG_HEIGHT, IMG_WIDTH), num_classes=len(CLASSES))
-    scored = big.withColumn("prediction", classify_udf("content")).select("path", "label", "prediction")
-    st = dict(classify_udf.stats)
-    head = scored.limit(5).toPandas()
-    print(head.to_string(index=False))
-    print("INFERENCE_STATS " + json.dumps({"rows": st["rows"], "workers": st["workers"], "fragments": st["fragments"],
-                                           "seconds": st["seconds"], "images_per_sec": st["rows_per_sec"],
-                                           "startup_seconds": st.get("startup_seconds"),
-                                           "serving_batch": int(os.environ.get("WORKSHOP_INFER_BATCH", "0")) or BATCH_SIZE,
-                                           "per_worker": st["per_worker"], "api": "pyfunc.spark_udf over data.synthetic_scan",
-                                           "image": f"{IMG_HEIGHT}x{IMG_WIDTH}x3 uint8", "arch": ARCH, "batch": BATCH_SIZE}))
+    # WORKSHOP_INFER_FRAG_ROWS: rows per generated fragment (a comma-separated list scores the table once per entry)
+    for frag_rows in [int(v) for v in os.environ.get("WORKSHOP_INFER_FRAG_ROWS", "4096").split(",")]:
+        big = synthetic_scan(N_INFER, size=(IMG_HEIGHT, IMG_WIDTH), num_classes=len(CLASSES), rows_per_fragment=frag_rows)
+        scored = big.withColumn("prediction", classify_udf("content")).select("path", "label", "prediction")
+        st = dict(classify_udf.stats)
+        head = scored.limit(5).toPandas()
+        print(head.to_string(index=False))
+        print("INFERENCE_STATS " + json.dumps({
+            "rows": st["rows"], "workers": st["workers"], "fragments": st["fragments"], "rows_per_fragment": frag_rows,
+            "seconds": st["seconds"], "images_per_sec": st["rows_per_sec"], "startup_seconds": st.get("startup_seconds"),
+            "serving_batch": int(os.environ.get("WORKSHOP_INFER_BATCH", "0")) or BATCH_SIZE,
+            "per_worker": st["per_worker"], "api": "pyfunc.spark_udf over data.synthetic_scan",
+            "image": f"{IMG_HEIGHT}x{IMG_WIDTH}x3 uint8", "arch": ARCH, "batch": BATCH_SIZE}))
 classify_udf.close()

@@ -211,3 +211,40 @@ def test_row_group_sharding_reads_each_group_once_and_shuffle_changes_order(sess
     two = epoch_labels(1, epochs=2)
     assert two[:96] == a and two[96:] != a and sorted(two[96:]) == sorted(labels)  # epoch 2 is reshuffled
     conv.delete()
+
+
+class MeanPixel(pyfunc.PythonModel):
+    def predict(self, context, model_input: pd.Series) -> np.ndarray:
+        from b200ddl.models import decode_batch
+        a = decode_batch(model_input, (IMG, IMG))
+        return a.reshape(len(a), -1).mean(1).astype(np.float64)
+
+
+def test_shard_udf_over_lazy_scan_pool_warmup_and_stats(session):
+    """BASELINE config 4's shape on CPU: a lazily generated table scored by a persistent worker pool.  Start-up (process
+    start, model load, warm-up) is reported apart from the scored seconds; a table with another fragment shape re-warms the
+    pool once; results are Arrow arrays built in the workers and come back in row order."""
+    from b200ddl.data import synthetic_scan
+
+    with tracking.start_run():
+        uri = pyfunc.log_model("mean_pixel", python_model=MeanPixel())
+    udf = pyfunc.shard_udf(uri, "double", num_workers=2)
+    try:
+        t1 = synthetic_scan(300, size=(IMG, IMG), rows_per_fragment=100)
+        p1 = t1.withColumn("p", udf("content")).select("p").toPandas()["p"].to_numpy()
+        s1 = dict(udf.stats)
+        assert s1["workers"] == 2 and s1["fragments"] == 3 and s1["rows"] == 300
+        assert s1["startup_seconds"] > 0                                # reported apart from `seconds`
+        ref = MeanPixel().predict(None, t1.select("content").toPandas()["content"])
+        assert np.allclose(p1, ref)
+        pool = udf._pool
+        t2 = synthetic_scan(800, size=(IMG, IMG), rows_per_fragment=200)
+        p2 = t2.withColumn("p", udf("content")).select("p").toPandas()["p"].to_numpy()
+        s2 = dict(udf.stats)
+        assert udf._pool is pool and s2["startup_seconds"] > 0          # same processes, re-warmed for the new fragment shape
+        p3 = t2.withColumn("p", udf("content")).select("p").toPandas()["p"].to_numpy()
+        s3 = dict(udf.stats)
+        assert s3["startup_seconds"] == 0.0 and np.array_equal(p2, p3)
+        assert all(w["wall_s"] >= w["predict_s"] * 0.5 for w in s3["per_worker"]) and len(s3["per_worker"]) == 2
+    finally:
+        udf.close()
