@@ -253,6 +253,7 @@ def _pool_worker(rank: int, conn) -> None:
                 conn.send(("res", pos, out))
             conn.send(("done", rank, {"read_s": scorer.read_s, "predict_s": scorer.predict_s,
                                        "wall_s": scorer.wall_s}))
+            scorer.read_s = scorer.predict_s = scorer.wall_s = 0.0   # stats are per job
     except (EOFError, SystemExit):
         return
     except BaseException as ex:  # surface the failure instead of leaving the driver waiting

@@ -105,7 +105,9 @@ N_INFER = int(os.environ.get("WORKSHOP_INFER_IMAGES", "0"))
 if N_INFER > 0:
     from b200ddl.data import synthetic_scan
     # WORKSHOP_INFER_FRAG_ROWS: rows per generated fragment (a comma-separated list scores the table once per entry)
-    for frag_rows in [int(v) for v in os.environ.get("WORKSHOP_INFER_FRAG_ROWS", "4096").split(",")]:
+    #    default: 8192-row fragments for big tables (fewer fragment boundaries: 391 k vs 358 k img/s on 8 GPUs), 4096 otherwise
+    default_rows = "8192" if N_INFER >= 500_000 else "4096"
+    for frag_rows in [int(v) for v in os.environ.get("WORKSHOP_INFER_FRAG_ROWS", default_rows).split(",")]:
         big = synthetic_scan(N_INFER, size=(IMG_HEIGHT, IMG_WIDTH), num_classes=len(CLASSES), rows_per_fragment=frag_rows)
         scored = big.withColumn("prediction", classify_udf("content")).select("path", "label", "prediction")
         st = dict(classify_udf.stats)
