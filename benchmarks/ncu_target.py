@@ -3,7 +3,7 @@
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 3 -c 1 -o gpurun_out/<name> \
         python benchmarks/ncu_target.py <what> <shape-name>
 
-what: fwd | fwd_stats | dgrad | wgrad | bn_reduce | bn_apply | bn_bwd_apply | block_grad | stem_bwd_reduce | stem_bwd_apply
+what: fwd | fwd_stats | fwd_infer | dgrad | wgrad | bn_reduce | bn_apply | bn_bwd_apply | block_grad | stem_bwd_reduce | stem_bwd_apply | dwconv
 shape-name: one of gpu_check.BIG_SHAPES (e.g. s4_3x3_512)
 """
 import os
@@ -77,6 +77,20 @@ elif what in ("stem_bwd_reduce", "stem_bwd_apply"):
                 e.stem_pool_bn_bwd(0, idx, g1, g2, y0, sc, sh, None, None, None, None, s0, s1)
             else:
                 e.stem_pool_bn_bwd(1, idx, g1, g2, y0, sc, sh, sc, sh, sh, dy0, s0, s1)
+    op = _Op()
+elif what == "fwd_infer":
+    # inference epilogue (kStats = 4): folded BatchNorm + ReLU + residual add in the GEMM epilogue (1x1 shapes take a residual)
+    sc = torch.rand(cout, device="cuda") + 0.5; sh = torch.randn(cout, device="cuda") * 0.1
+    res = torch.randn_like(y) if (R == 1 and stride == 1) else None
+    op = C.ConvForward(x, wk, y, R, R, stride, pad, None, None, epilogue=(sc, sh, "relu", res))
+elif what == "dwconv":
+    # MobileNetV2 depthwise 3x3 + folded BN + ReLU6 on the layer's INPUT shape (channels = cin)
+    wd = torch.randn(9, cin, device="cuda"); sc = torch.rand(cin, device="cuda") + 0.5; sh = torch.randn(cin, device="cuda") * 0.1
+    out = torch.empty(N, (H - 1) // stride + 1, (W - 1) // stride + 1, cin, device="cuda", dtype=torch.bfloat16)
+
+    class _Op:
+        def run(self):
+            e.dwconv3x3(x, wd, sc, sh, out, stride)
     op = _Op()
 else:
     raise SystemExit(f"unknown target {what}")
