@@ -175,6 +175,8 @@ class DistributedOptimizer:
     # -- hot path ------------------------------------------------------------------------------------------
     def begin_step(self) -> None:
         self.opt.begin_step()
+        if self.fused_update:
+            self._state_complete = False   # called once per step even when the step itself is a CUDA-graph replay
 
     def start_backward(self) -> None:
         for b in self.buckets:
@@ -263,9 +265,47 @@ class DistributedOptimizer:
         self.finish_backward()
         if not self.fused_update:
             self.opt.step()  # fused_update: the per-bucket kernels already updated and broadcast the weights
+        else:
+            self._state_complete = False   # momentum now differs per rank outside the owned slices
+
+    @property
+    def state_is_sharded(self) -> bool:
+        """True when this rank's optimizer state is only valid on its own slices (fused_update after a step and before
+        `consolidate_state()`): `Trainer.save` refuses to write such a state."""
+        return bool(self.fused_update and self.world > 1 and not getattr(self, "_state_complete", True))
 
     # -- utilities -----------------------------------------------------------------------------------------
+    @staticmethod
+    def owned_range(lo: int, hi: int, rank: int, world: int):
+        """Elements [a, b) of bucket [lo, hi) whose optimizer state rank `rank` owns under fused_update - the slicing of
+        csrc/allreduce.cu allreduce_sgd_nvls_kernel (float4 vectors split evenly, the last rank takes the short end)."""
+        nvec = (hi - lo) // 4
+        per = -(-nvec // world)
+        v0 = min(per * rank, nvec)
+        v1 = min(v0 + per, nvec)
+        return lo + 4 * v0, lo + 4 * v1
+
+    def consolidate_state(self) -> None:
+        """COLLECTIVE (every rank must call it).  With fused_update each rank holds the momentum of only its 1/N slice of
+        every bucket; this makes every rank's state tensors complete (sum of the owners' slices), so that a checkpoint
+        written by rank 0 can be resumed on any world size and `broadcast_parameters` does not overwrite live slices
+        with rank 0's stale ones.  No-op without fused_update."""
+        if not self.fused_update or self.world == 1:
+            self._state_complete = True
+            return
+        for name, v in self.opt.state.items():
+            if not torch.is_tensor(v) or v.numel() != self.grads.numel():
+                continue   # scalars (step counters) are replicated already
+            full = torch.zeros_like(v)
+            for b in self.buckets:
+                a, e = self.owned_range(b.lo, b.hi, self.rank, self.world)
+                if e > a:
+                    full[a:e] = v[a:e]
+            v.copy_(core.allreduce(full, average=False))
+        self._state_complete = True
+
     def broadcast_parameters(self, params: torch.Tensor, root: int = 0) -> None:
+        self.consolidate_state()
         core.broadcast(params, root)
         for v in self.opt.state.values():
             core.broadcast(v, root)

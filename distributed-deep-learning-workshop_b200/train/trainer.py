@@ -425,6 +425,12 @@ class Trainer:
         self.backend.load_state_dict(torch.load(path, map_location="cpu"))
 
     def save(self, path: str) -> None:
+        """Weights + optimizer state + step counter.  With `DistributedOptimizer(fused_update=True)` the momentum is sharded
+        over ranks: call `optimizer.consolidate_state()` on EVERY rank first (it is a collective; `save` usually runs on
+        rank 0 only and therefore cannot do it itself) - an unconsolidated state is refused, not silently truncated."""
+        if getattr(self.optimizer, "state_is_sharded", False):
+            raise RuntimeError("the optimizer state is sharded over ranks (fused_update): call "
+                               "optimizer.consolidate_state() on every rank before Trainer.save(), or use save_weights()")
         opt = self.optimizer.opt if hasattr(self.optimizer, "opt") else self.optimizer
         torch.save({"weights": self.backend.state_dict(), "optimizer": opt.state_dict() if opt is not None else None,
                     "arch": getattr(self.model, "arch", type(self.model).__name__)}, path)

@@ -77,3 +77,19 @@ def test_state_dict_round_trip():
 def test_unknown_optimizer_name():
     with pytest.raises(ValueError):
         optim.get("Nadam")
+
+
+def test_fused_update_owned_ranges_tile_every_bucket():
+    """`DistributedOptimizer.owned_range` (used by `consolidate_state`) must reproduce the slicing of the fused
+    all-reduce + SGD kernel: the ranks' ranges are disjoint, ordered, float4-aligned and cover the bucket's full vectors."""
+    from b200ddl.parallel.dist_optimizer import DistributedOptimizer as D
+
+    for lo, hi in [(0, 4096), (128, 128 + 250000), (64, 64 + 4 * 7), (0, 4 * 3)]:
+        for world in (2, 3, 4, 8):
+            rs = [D.owned_range(lo, hi, r, world) for r in range(world)]
+            assert rs[0][0] == lo and rs[-1][1] == lo + (hi - lo) // 4 * 4
+            for (a0, b0), (a1, b1) in zip(rs, rs[1:]):
+                assert b0 == a1 and a0 <= b0 and (a0 - lo) % 4 == 0
+            nvec = (hi - lo) // 4
+            per = -(-nvec // world)
+            assert all(b - a <= 4 * per for a, b in rs)
