@@ -946,18 +946,45 @@ def case_mobilenet():
     e = ops.ext("_b200_ops")
     g = torch.Generator(device=DEV).manual_seed(51)
     # depthwise 3x3 + affine + relu6
-    for (N, H, C_, stride) in ((2, 14, 64, 1), (3, 28, 192, 2), (2, 7, 960, 1)):
+    for (N, H, C_, stride) in ((2, 14, 64, 1), (3, 28, 192, 2), (2, 7, 960, 1), (2, 7, 64, 2), (1, 13, 32, 1), (2, 112, 96, 2),
+                               (1, 9, 16, 2)):
         x = torch.randn(N, H, H, C_, device=DEV, generator=g).to(torch.bfloat16)
         w = torch.randn(9, C_, device=DEV, generator=g) * 0.3
         sc = torch.rand(C_, device=DEV, generator=g) + 0.5
         sh = torch.randn(C_, device=DEV, generator=g) * 0.5
         Ho = (H - 1) // stride + 1
         out = torch.empty(N, Ho, Ho, C_, device=DEV, dtype=torch.bfloat16)
-        e.dwconv3x3(x, w, sc, sh, out, stride)
+        e.dwconv3x3(x, w, sc, sh, out, stride)          # register-tiled kernel (default, 4 output pixels per thread)
+        out1 = torch.empty_like(out)
+        e.dwconv3x3(x, w, sc, sh, out1, stride, 1)      # one-pixel kernel
         wt = w.t().reshape(C_, 1, 3, 3)
         ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt, stride=stride, padding=1, groups=C_)
         ref = (ref * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).clamp(0, 6).permute(0, 2, 3, 1)
         ok &= report(f"dwconv3x3/N{N}_H{H}_C{C_}_s{stride}", rel_err(out, ref), 1e-2)
+        ok &= report(f"dwconv3x3 tiled == one-pixel/N{N}_H{H}_C{C_}_s{stride}", 0.0 if torch.equal(out, out1) else 1.0, 0.5)
+    # MobileNetV2's depthwise layers at batch 64: tiled vs one-pixel kernel
+    tot = [0.0, 0.0]
+    l2 = torch.empty(256 << 20, device=DEV, dtype=torch.uint8)   # written between timed launches: inputs never come from L2
+
+    def time_op(fn):
+        return time_fn(fn, iters=10, warmup=3, flush=l2) * 1e3
+
+    for (H, C_, stride) in ((112, 32, 1), (112, 96, 2), (56, 144, 1), (56, 144, 2), (28, 192, 1), (28, 192, 2), (14, 384, 1),
+                            (14, 576, 1), (14, 576, 2), (7, 960, 1)):
+        Cp = (C_ + 63) // 64 * 64
+        x = torch.randn(64, H, H, Cp, device=DEV, generator=g).to(torch.bfloat16)
+        w = torch.randn(9, Cp, device=DEV, generator=g) * 0.3
+        sc = torch.rand(Cp, device=DEV, generator=g) + 0.5
+        sh = torch.randn(Cp, device=DEV, generator=g) * 0.5
+        Ho = (H - 1) // stride + 1
+        out = torch.empty(64, Ho, Ho, Cp, device=DEV, dtype=torch.bfloat16)
+        t4 = time_op(lambda: e.dwconv3x3(x, w, sc, sh, out, stride, 4))
+        t1 = time_op(lambda: e.dwconv3x3(x, w, sc, sh, out, stride, 1))
+        gb = (x.numel() + out.numel()) * 2 / 1e9
+        tot[0] += t4
+        tot[1] += t1
+        print(f"TIME dwconv3x3 b64 {H}x{H}x{Cp} s{stride}: tiled {t4:.1f} us ({gb / t4 * 1e6:.0f} GB/s)  one-pixel {t1:.1f} us", flush=True)
+    print(f"TIME dwconv3x3 sum over the 10 shapes: tiled {tot[0]:.0f} us, one-pixel {tot[1]:.0f} us", flush=True)
     # stem 3x3/2 from uint8
     xs = torch.randint(0, 256, (3, 64, 64, 3), device=DEV, dtype=torch.uint8, generator=g)
     wst = torch.randn(32, 3, 3, 3, device=DEV, generator=g) * 0.2

@@ -6,6 +6,7 @@ For each decode mode it reports (one JSON line per mode, prefix LOADER_JPEG):
   train_img_s         `Trainer.fit` over the dataset, wall clock with a device sync on both sides (what the user gets)
   loader_wait_ms      time fit() spent waiting for a READY slot (pinned-ring datasets)
 modes: 'cpu'  PIL decode (+draft-mode downscale) + resize on `--workers` threads into the pinned ring, side-stream H2D
+       'procs' the same decode in `--procs` worker PROCESSES (loader/_decode_worker.py) driven by `--proc-threads` filler threads
        'gpu'  nvJPEG (library) decode on the device + our bilinear resize kernel; only compressed bytes cross PCIe
        'ring' the synthetic raw-tensor ring (upper bound of the host path; what bench.py's e2e arm uses)
 
@@ -44,7 +45,9 @@ def main():
     ap.add_argument("--workers", type=int, default=32)
     ap.add_argument("--arch", default="resnet50")
     ap.add_argument("--device", default="cuda")
-    ap.add_argument("--modes", default="ring,cpu,gpu")
+    ap.add_argument("--procs", type=int, default=96, help="decode processes of the 'procs' mode")
+    ap.add_argument("--proc-threads", type=int, default=8, help="filler threads driving the decode processes")
+    ap.add_argument("--modes", default="ring,cpu,procs,gpu")
     args = ap.parse_args()
     dev = torch.device(args.device)
     sw, sh = (int(v) for v in args.stored.split("x"))
@@ -71,8 +74,11 @@ def main():
         if mode == "ring":
             return SyntheticDataset(args.batch, num_classes=len(CLASSES), device=dev, threads=6, pool_images=2048, seed=3,
                                     image_size=(args.size, args.size)) if dev.type == "cuda" else None
+        if mode == "procs":
+            return conv.make_dataset(batch_size=args.batch, num_epochs=None, workers_count=args.proc_threads,
+                                     image_size=(args.size, args.size), device=dev, decode="cpu", decode_processes=args.procs)
         return conv.make_dataset(batch_size=args.batch, num_epochs=None, workers_count=args.workers,
-                                 image_size=(args.size, args.size), device=dev, decode=mode)
+                                 image_size=(args.size, args.size), device=dev, decode=mode, decode_processes=0)
 
     for mode in args.modes.split(","):
         if mode == "gpu" and dev.type != "cuda":
@@ -99,7 +105,8 @@ def main():
             _sync(dev)
             dt = time.perf_counter() - t0
             rec = {"mode": mode, "images": args.images, "stored": args.stored, "jpeg_kb": round(jpeg_bytes / 1024, 1),
-                   "batch": args.batch, "steps": args.steps, "workers": args.workers if mode == "cpu" else None,
+                   "batch": args.batch, "steps": args.steps, "workers": args.workers if mode == "cpu" else (args.proc_threads if mode == "procs" else None),
+                   "decode_processes": getattr(ds, "decode_processes", None),
                    "loader_only_img_s": round(loader_only, 1), "train_img_s": round(args.batch * args.steps / dt, 1),
                    "train_ms_per_step": round(dt / args.steps * 1e3, 3),
                    "loader_wait_ms": round(ring.consumer_wait_ms - w0, 2) if ring is not None else None,

@@ -65,7 +65,7 @@ void stem_pool_bn_bwd(int pass, const void* idx, const void* g1, const void* g2,
 void mbv2_stem(const uint8_t* x, const float* w, const float* scale, const float* shift, void* out, int N, int H, int W,
                int ldc, float mul, float add, cudaStream_t s);
 void dwconv3x3(const void* x, const float* w, const float* scale, const float* shift, void* out, int N, int H, int W, int C,
-               int stride, cudaStream_t s);
+               int stride, int tile_w, cudaStream_t s);
 void preprocess_u8(const uint8_t* x, void* out, int64_t npix, int cpad, float mul, float add, cudaStream_t s);
 void resize_bilinear_u8(const uint8_t* x, uint8_t* out, int N, int H, int W, int OH, int OW, bool planar, cudaStream_t s);
 void weight_prep(const float* w, void* wf, void* wd, int taps, int cout, int cin, cudaStream_t s);

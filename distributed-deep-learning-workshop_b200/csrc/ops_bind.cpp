@@ -289,19 +289,19 @@ void mbv2_stem(Tensor x, Tensor w, Tensor scale, Tensor shift, Tensor out, doubl
   after();
 }
 // depthwise 3x3 (pad 1, stride 1 / 2) + folded BatchNorm + ReLU6;  x bf16 [N,H,W,C], w fp32 [9, C], out bf16 [N,Ho,Wo,C]
-void dwconv3x3(Tensor x, Tensor w, Tensor scale, Tensor shift, Tensor out, int64_t stride) {
+void dwconv3x3(Tensor x, Tensor w, Tensor scale, Tensor shift, Tensor out, int64_t stride, int64_t tile_w) {
   chk(x, at::kBFloat16, "x");
   chk(w, at::kFloat, "w");
   chk(scale, at::kFloat, "scale");
   chk(shift, at::kFloat, "shift");
   chk(out, at::kBFloat16, "out");
-  TORCH_CHECK(stride == 1 || stride == 2);
+  TORCH_CHECK((stride == 1 || stride == 2) && (tile_w == 1 || tile_w == 4));
   const int C = (int)x.size(3), H = (int)x.size(1), W = (int)x.size(2);
   TORCH_CHECK(x.dim() == 4 && C % 8 == 0 && w.numel() == 9 * C && scale.numel() == C && shift.numel() == C);
   TORCH_CHECK(out.dim() == 4 && out.size(0) == x.size(0) && out.size(3) == C && out.size(1) == (H - 1) / stride + 1 &&
               out.size(2) == (W - 1) / stride + 1, "dwconv3x3 output shape");
   b200::dwconv3x3(x.data_ptr(), w.data_ptr<float>(), scale.data_ptr<float>(), shift.data_ptr<float>(), out.data_ptr(),
-                  (int)x.size(0), H, W, C, (int)stride, cur());
+                  (int)x.size(0), H, W, C, (int)stride, (int)tile_w, cur());
   after();
 }
 void preprocess_u8(Tensor x, Tensor out, double mul, double add) {
@@ -400,7 +400,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("cC") = c10::nullopt, py::arg("dy") = c10::nullopt, py::arg("sum_dz"), py::arg("sum_dzy"));
   m.def("zero_", &zero_);
   m.def("mbv2_stem", &mbv2_stem);
-  m.def("dwconv3x3", &dwconv3x3);
+  m.def("dwconv3x3", &dwconv3x3, pybind11::arg("x"), pybind11::arg("w"), pybind11::arg("scale"), pybind11::arg("shift"),
+        pybind11::arg("out"), pybind11::arg("stride"), pybind11::arg("tile_w") = 4);
   m.def("preprocess_u8", &preprocess_u8);
   m.def("resize_bilinear_u8", &resize_bilinear_u8, py::arg("x"), py::arg("out"), py::arg("planar") = false);
   m.def("weight_prep", &weight_prep);

@@ -93,7 +93,7 @@ class _TableDataset(RingDataset):
     decode (PIL releases the GIL) runs outside it in `workers_count` threads."""
 
     def __init__(self, files, total_rows, batch_size, image_size, device, cur_shard, shard_count, num_epochs,
-                 workers_count, shuffle, seed):
+                 workers_count, shuffle, seed, decode_processes: int = 0):
         super().__init__(batch_size, image_size, device, num_slots=max(4, workers_count + 2))
         self.files = files
         self.total_rows = int(total_rows)
@@ -107,7 +107,20 @@ class _TableDataset(RingDataset):
         self._lock = threading.Lock()
         self._row_iter = self._rows()
         self._active_workers = max(1, workers_count)
-        self._threads = [threading.Thread(target=self._worker, daemon=True) for _ in range(max(1, workers_count))]
+        self._error: Optional[BaseException] = None
+        # decode PROCESSES (loader/_decode_worker.py): every filler thread owns an equal share of them, splits its batch
+        # over its share and receives the decoded pixels straight into the pinned slot (`recv_bytes_into`)
+        self._pools = None
+        if decode_processes and decode_processes > 0:
+            from ..utils.procpool import start_script_workers
+
+            nthreads = max(1, workers_count)
+            per = max(1, int(decode_processes) // nthreads)
+            script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_decode_worker.py")
+            procs = start_script_workers(script, per * nthreads, env={"OMP_NUM_THREADS": "1"})
+            self._pools = [procs[k * per:(k + 1) * per] for k in range(nthreads)]
+        self.decode_processes = sum(len(p) for p in self._pools) if self._pools else 0
+        self._threads = [threading.Thread(target=self._worker, args=(k,), daemon=True) for k in range(max(1, workers_count))]
         for t in self._threads:
             t.start()
 
@@ -159,9 +172,17 @@ class _TableDataset(RingDataset):
                     yield contents, labels, int(j)
             epoch += 1
 
-    def _worker(self):
+    def _worker(self, k: int = 0):
         try:
-            self._produce()
+            if self._pools is not None:
+                self._produce_with_processes(self._pools[k])
+            else:
+                self._produce()
+        except BaseException as ex:  # a dead decode process, a corrupt row ...: end the stream and re-raise in __next__
+            if not self._stop.is_set():
+                self._error = ex
+                self._stop.set()      # the other fillers stop after their batch in flight ...
+                self.ring.finish()    # ... and the consumer gets the error once the committed batches are drained
         finally:
             # the LAST worker to run out of rows ends the stream: the consumer drains what is committed and then gets
             # StopIteration (without this a `for batch in ds:` over a finite dataset blocked forever)
@@ -173,13 +194,7 @@ class _TableDataset(RingDataset):
 
     def _produce(self):
         while not self._stop.is_set():
-            with self._lock:
-                batch = []
-                try:
-                    for _ in range(self.batch_size):
-                        batch.append(next(self._row_iter))
-                except StopIteration:
-                    pass
+            batch = self._take_batch()
             if len(batch) < self.batch_size:
                 return  # finite epochs exhausted (drop the tail batch, like steps_per_epoch = n // batch)
             slot = self.ring.acquire_fill()
@@ -193,17 +208,94 @@ class _TableDataset(RingDataset):
                 lab[i] = labels[j]
             self.ring.commit(slot)
 
+    def _take_batch(self):
+        with self._lock:
+            batch = []
+            try:
+                for _ in range(self.batch_size):
+                    batch.append(next(self._row_iter))
+            except StopIteration:
+                pass
+        return batch
+
+    def _produce_with_processes(self, pool):
+        row = self.h * self.w * 3
+        P = len(pool)
+        per = -(-self.batch_size // P)
+        while not self._stop.is_set():
+            batch = self._take_batch()
+            if len(batch) < self.batch_size:
+                return
+            slot = self.ring.acquire_fill()
+            if slot < 0:
+                return
+            img, lab = self.ring.slot_tensors(slot)
+            dst = memoryview(img.numpy().reshape(-1))
+            lab = lab.numpy()
+            sent = []
+            for k, (_, conn) in enumerate(pool):
+                rows = batch[k * per:(k + 1) * per]
+                if not rows:
+                    break
+                payloads = [contents[j].as_buffer() for contents, _, j in rows]
+                head = np.array([self.h, self.w, len(rows)] + [len(b) for b in payloads], dtype=np.int32).tobytes()
+                conn.send_bytes(b"".join([head] + [memoryview(b) for b in payloads]))
+                sent.append((conn, k * per, len(rows)))
+            for conn, first, n in sent:   # blocking socket reads release the GIL; pixels land in the pinned slot directly
+                got = conn.recv_bytes_into(dst[first * row:(first + n) * row])
+                if got != n * row:
+                    raise RuntimeError(f"decode worker returned {got} bytes for {n} images")
+            for i, (_, labels, j) in enumerate(batch):
+                lab[i] = labels[j]
+            self.ring.commit(slot)
+
+    def __next__(self):
+        try:
+            return super().__next__()
+        except StopIteration:
+            if self._error is not None:
+                raise RuntimeError(f"the loader's decode pipeline failed: {self._error!r}") from self._error
+            raise
+
     def close(self) -> None:
         self._stop.set()
         super().close()
+        if self._pools:
+            # the filler threads own the connections: let them finish the batch in flight before the exit frames are sent
+            # (two writers on one socket would interleave their frames)
+            for t in self._threads:
+                if t is not threading.current_thread():
+                    t.join(timeout=20)
+            for pool in self._pools:
+                for proc, conn in pool:
+                    try:
+                        conn.send_bytes(b"")
+                        conn.close()
+                    except Exception:
+                        pass
+            for pool in self._pools:
+                for proc, _ in pool:
+                    try:
+                        proc.wait(timeout=5)
+                    except Exception:
+                        proc.kill()
+            self._pools = None
 
 
 class _GpuDecodeDataset:
-    """`make_dataset(decode='gpu')`: JPEG payloads are decoded ON THE GPU (nvJPEG through `torchvision.io.decode_jpeg`, a
-    library call - the reference's tf.io.decode_jpeg, P1/03:182-189) and resized by OUR bilinear kernel
-    (csrc/elementwise.cu resize_bilinear_u8, planar input -> HWC output) straight into the uint8 device batch; only the
-    compressed bytes cross PCIe.  Rows that are not JPEG (PNG, raw tensors) take the CPU decoder.  Same sharding / shuffle /
-    epoch semantics as the pinned-ring dataset (it reuses its row planner); yields (images uint8 [B,H,W,3], labels int64 [B])."""
+    """`make_dataset(decode='gpu')`: only the COMPRESSED bytes cross PCIe; the JPEG payloads are decoded on the GPU and resized
+    by our kernel straight into the uint8 device batch (the reference's tf.io.decode_jpeg + resize, P1/03:182-189).
+
+    Native path (`csrc/jpeg_decode.cpp`, extension `_b200_jpeg`): nvJPEG (library) batched decode - HARDWARE backend (the
+    NVJPG engines: no SM time, no CPU Huffman decode) when the GPU has it, else GPU-hybrid - into one scratch buffer, then ONE
+    launch of our batched anti-aliased resize kernel (`csrc/jpeg_resize.cu`, PIL's BILINEAR filter).  Batch k+1 is decoded on a
+    side stream while the model trains on batch k (three device buffers, event-chained both ways; no host synchronisation).
+    Fallbacks: `torchvision.io.decode_jpeg(device=cuda)` + `resize_bilinear_u8` when the native decoder cannot be created
+    (`B200DDL_JPEG_BACKEND=torchvision` forces it; `=hardware|gpu_hybrid|hybrid` pins a backend); rows that are not JPEG
+    (PNG, raw tensors) take the CPU decoder.  Same sharding / shuffle / epoch semantics as the pinned-ring dataset (it reuses
+    its row planner); yields (images uint8 [B,H,W,3], labels int64 [B])."""
+
+    _BUFFERS = 3
 
     def __init__(self, files, total_rows, batch_size, image_size, device, cur_shard, shard_count, num_epochs, shuffle, seed):
         import types
@@ -222,12 +314,36 @@ class _GpuDecodeDataset:
         self._src.row_lo, self._src.row_hi = (n * cur_shard) // k, (n * (cur_shard + 1)) // k
         self._src._plan = lambda: _TableDataset._plan(self._src)
         self._rows = _TableDataset._rows(self._src)
-        self._out = [torch.empty(batch_size, self.h, self.w, 3, device=self.device, dtype=torch.uint8) for _ in range(2)]
-        self._lab = [torch.empty(batch_size, device=self.device, dtype=torch.int64) for _ in range(2)]
-        self._k = 0
+        R = self._BUFFERS
+        self._out = [torch.empty(batch_size, self.h, self.w, 3, device=self.device, dtype=torch.uint8) for _ in range(R)]
+        self._lab = [torch.empty(batch_size, device=self.device, dtype=torch.int64) for _ in range(R)]
+        self._lab_host = [torch.empty(batch_size, dtype=torch.int64).pin_memory() for _ in range(R)]
+        self._done = [None] * R          # event on the decode stream: buffer r holds a finished batch
+        self._keep = [None] * R          # the Arrow buffers whose addresses nvJPEG was given (alive until the buffer is reused)
+        self._stream = torch.cuda.Stream(device=self.device)
+        self._entry_events = []          # events recorded on the consumer's stream at the entry of __next__ (oldest first)
+        self._k = 0                      # batches handed out
+        self._issued = 0                 # batches whose decode has been enqueued
+        self._exhausted = False
         self.compressed_bytes = 0
         self.gpu_decoded = 0
         self.cpu_decoded = 0
+        self.backend = "torchvision"
+        self.backend_errors = []
+        self._dec = None
+        want = os.environ.get("B200DDL_JPEG_BACKEND", "")
+        if want != "torchvision":
+            try:
+                jpeg = ops.ext("_b200_jpeg")
+                for name in ([want] if want else ["hardware", "gpu_hybrid"]):
+                    try:
+                        self._dec = jpeg.JpegDecoder(batch_size, name, 4, self.device.index)
+                        self.backend = "nvjpeg:" + name
+                        break
+                    except Exception as ex:   # ARCH_MISMATCH: no hardware engine on this GPU, ...
+                        self.backend_errors.append(f"{name}: {str(ex).splitlines()[0][:160]}")
+            except Exception as ex:
+                self.backend_errors.append(f"_b200_jpeg: {str(ex).splitlines()[0][:160]}")
 
     def __len__(self) -> int:
         return (self._src.row_hi - self._src.row_lo) // self.batch_size
@@ -240,47 +356,103 @@ class _GpuDecodeDataset:
 
     def close(self) -> None:
         self._rows = iter(())
+        self._exhausted = True
+        torch.cuda.synchronize(self.device)   # nothing may still read the bitstreams / write the buffers we drop
+        self._keep = [None] * self._BUFFERS
 
     def __iter__(self):
         return self
 
-    def __next__(self):
-        import warnings
-
-        import torchvision
-
+    def _take(self):
         batch = []
         try:
             for _ in range(self.batch_size):
                 batch.append(next(self._rows))
         except StopIteration:
             pass
-        if len(batch) < self.batch_size:
-            raise StopIteration
-        out, lab = self._out[self._k & 1], self._lab[self._k & 1]
-        self._k += 1
-        jpeg_idx, jpeg_data, labels = [], [], []
+        return batch if len(batch) == self.batch_size else None
+
+    def _issue(self, wait_event) -> bool:
+        """Enqueue the decode of the next batch into buffer `issued % R` on the decode stream.  `wait_event`: consumer-stream
+        event after which that buffer is no longer read."""
+        import warnings
+
+        batch = self._take()
+        if batch is None:
+            self._exhausted = True
+            return False
+        r = self._issued % self._BUFFERS
+        out, lab, lab_host = self._out[r], self._lab[r], self._lab_host[r]
+        ptrs, lens, keep, jpeg_idx, other = [], [], [], [], []
         for i, (contents, lbls, j) in enumerate(batch):
             buf = contents[j].as_buffer()
-            labels.append(int(lbls[j]))
-            head = bytes(buf[:3])
-            if head == b"\xff\xd8\xff":
-                with warnings.catch_warnings():
-                    warnings.simplefilter("ignore")  # read-only buffer: decode_jpeg does not write to it
-                    jpeg_data.append(torch.from_numpy(np.frombuffer(buf, dtype=np.uint8)))  # zero-copy view of the Arrow buffer
+            lab_host[i] = int(lbls[j])
+            if buf.size >= 3 and bytes(buf[:3]) == b"\xff\xd8\xff":
+                ptrs.append(buf.address)
+                lens.append(buf.size)
+                keep.append(buf)
                 jpeg_idx.append(i)
                 self.compressed_bytes += buf.size
             else:
-                out[i].copy_(torch.from_numpy(np.ascontiguousarray(decode_image(contents[j].as_py(), (self.h, self.w)))),
-                             non_blocking=False)
+                other.append((i, contents[j].as_py()))
+        st = self._stream
+        if wait_event is not None:
+            st.wait_event(wait_event)
+        with torch.cuda.stream(st):
+            if jpeg_idx:
+                contiguous = jpeg_idx == list(range(len(jpeg_idx)))
+                if self._dec is not None:
+                    try:
+                        if contiguous and len(jpeg_idx) == self.batch_size:
+                            self._dec.decode_resize(ptrs, lens, out)
+                        else:   # mixed batch: decode the JPEG rows into a temporary and scatter them
+                            tmp = torch.empty(len(jpeg_idx), self.h, self.w, 3, device=self.device, dtype=torch.uint8)
+                            self._dec.decode_resize(ptrs, lens, tmp)
+                            out[torch.tensor(jpeg_idx, device=self.device)] = tmp
+                    except RuntimeError as ex:
+                        # e.g. a progressive JPEG the hardware engine does not take: this and all later batches go the library way
+                        self.backend_errors.append(f"{self.backend}: {str(ex).splitlines()[0][:160]}")
+                        self._dec, self.backend = None, "torchvision"
+                if self._dec is None:
+                    import torchvision
+
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")  # read-only buffers: decode_jpeg does not write to them
+                        data = [torch.from_numpy(np.frombuffer(b, dtype=np.uint8)) for b in keep]
+                    imgs = torchvision.io.decode_jpeg(data, device=self.device, mode=torchvision.io.ImageReadMode.RGB)
+                    for i, img in zip(jpeg_idx, imgs):
+                        self._e.resize_bilinear_u8(img.unsqueeze(0), out[i:i + 1], True)  # [1,3,h,w] planar -> [1,H,W,3]
+                self.gpu_decoded += len(jpeg_idx)
+            for i, payload in other:
+                out[i].copy_(torch.from_numpy(np.ascontiguousarray(decode_image(payload, (self.h, self.w)))))
                 self.cpu_decoded += 1
-        if jpeg_data:
-            imgs = torchvision.io.decode_jpeg(jpeg_data, device=self.device, mode=torchvision.io.ImageReadMode.RGB)
-            for i, img in zip(jpeg_idx, imgs):
-                self._e.resize_bilinear_u8(img.unsqueeze(0), out[i:i + 1], True)  # [1,3,h,w] planar -> [1,H,W,3]
-            self.gpu_decoded += len(jpeg_data)
-        lab.copy_(torch.tensor(labels, dtype=torch.int64), non_blocking=False)
-        return out, lab
+            lab.copy_(lab_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self._done[r] = ev
+        self._keep[r] = keep
+        self._issued += 1
+        return True
+
+    def __next__(self):
+        cur = torch.cuda.current_stream(self.device)
+        entry = torch.cuda.Event()
+        entry.record(cur)            # everything the consumer enqueued so far (incl. its reads of the batch handed out last)
+        self._entry_events.append(entry)
+        if len(self._entry_events) > 2:
+            self._entry_events.pop(0)
+        if self._issued == self._k and not self._exhausted:
+            self._issue(None)        # first call: nothing has been prefetched yet
+        if self._issued == self._k:
+            raise StopIteration
+        # prefetch the batch after this one: it overwrites the buffer handed out two calls ago, whose reads the consumer
+        # enqueued before the PREVIOUS call's entry event
+        if not self._exhausted and self._issued - self._k < 2:
+            self._issue(self._entry_events[0] if len(self._entry_events) == 2 else None)
+        r = self._k % self._BUFFERS
+        cur.wait_event(self._done[r])
+        self._k += 1
+        return self._out[r], self._lab[r]
 
 
 class Converter:
@@ -305,8 +477,10 @@ class Converter:
 
     def make_dataset(self, batch_size: int = 32, cur_shard: Optional[int] = None, shard_count: Optional[int] = None,
                      num_epochs: Optional[int] = None, workers_count: int = 4, image_size=(IMG_HEIGHT, IMG_WIDTH),
-                     device=None, shuffle: bool = False, seed: int = 0, decode: str = "cpu"):
-        """``decode='cpu'``: PIL decode + resize in `workers_count` threads into the pinned ring (default);
+                     device=None, shuffle: bool = False, seed: int = 0, decode: str = "cpu", decode_processes=None):
+        """``decode='cpu'``: PIL decode + resize into the pinned ring - in `workers_count` threads (default), or, with
+        ``decode_processes=N`` (or ``'auto'``: the host's cores divided by the ranks of this node, at most 96; the default
+        on a GPU for datasets of >= 4096 rows; 0 = threads only), in N decode PROCESSES driven by those threads (threads of one process stop scaling at ~4.6 k images/s, see _decode_worker.py);
         ``decode='gpu'``: nvJPEG decode + our resize kernel on the device (`_GpuDecodeDataset`)."""
         if (cur_shard is None) != (shard_count is None):
             raise ValueError("cur_shard and shard_count must be given together")
@@ -317,8 +491,17 @@ class Converter:
             return _GpuDecodeDataset(self.files, self._n, batch_size, image_size, device, cs, sc, num_epochs, shuffle, seed)
         if decode != "cpu":
             raise ValueError("decode must be 'cpu' or 'gpu'")
+        if decode_processes is None:
+            # default: processes when a GPU consumes a dataset big enough to amortise starting them
+            on_gpu = _device_index(device) >= 0
+            decode_processes = "auto" if (on_gpu and self._n >= 4096) else 0
+        if decode_processes == "auto":
+            lws = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            decode_processes = max(0, min(96, ((os.cpu_count() or 1) - 2 * lws) // lws))
+            if decode_processes < 4:
+                decode_processes = 0
         return _TableDataset(self.files, self._n, batch_size, image_size, device, cs, sc, num_epochs, workers_count,
-                             shuffle, seed)
+                             shuffle, seed, decode_processes=int(decode_processes or 0))
 
     # reference spelling
     make_tf_dataset = make_dataset

@@ -37,6 +37,11 @@ EXTENSIONS: Dict[str, List[str]] = {
     "_b200_ops": ["elementwise.cu", "head_stem.cu", "mobilenet.cu", "optim.cu", "ops_bind.cpp"],
     "_b200_comm": ["allreduce.cu", "comm_bind.cpp"],
     "_b200_loader": ["ring_loader.cpp"],
+    "_b200_jpeg": ["jpeg_decode.cpp", "jpeg_resize.cu"],   # nvJPEG (library) decode + our batched resize kernel
+}
+# extra linker flags per extension
+LDFLAGS: Dict[str, List[str]] = {
+    "_b200_jpeg": ["-L/usr/local/cuda/lib64", "-lnvjpeg"],
 }
 # headers each extension actually includes (hashed with its sources): editing one extension's header must not
 # mark the others stale
@@ -46,6 +51,7 @@ HEADERS: Dict[str, List[str]] = {
     "_b200_ops": ["ops_api.h"],
     "_b200_comm": ["comm_api.h"],
     "_b200_loader": [],
+    "_b200_jpeg": [],
 }
 
 _loaded: Dict[str, object] = {}
@@ -60,7 +66,7 @@ def _hash(name: str) -> str:
             with open(p, "rb") as f:
                 h.update(rel.encode())
                 h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS + CXX_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + CXX_FLAGS + LDFLAGS.get(name, [])).encode())
     import torch
 
     h.update(torch.__version__.encode())
@@ -93,6 +99,7 @@ def build(name: str, verbose: bool = False) -> str:
         extra_cflags=CXX_FLAGS,
         extra_cuda_cflags=NVCC_FLAGS,
         extra_include_paths=[CSRC],
+        extra_ldflags=list(LDFLAGS.get(name, [])),   # a copy: cpp_extension appends the torch libraries in place
         build_directory=out_dir,
         with_cuda=True,
         is_python_module=False,  # we import by path ourselves (a CPU-only box cannot always dlopen)

@@ -157,7 +157,39 @@ def test_gpu_jpeg_decode_dataset_matches_cpu_decode(tmp_path):
             assert diff.mean() < 3.0 and diff.max() < 48.0, (float(diff.mean()), float(diff.max()))
             n += 1
         assert n == 4 and gpu_ds.gpu_decoded == 64 and gpu_ds.cpu_decoded == 0 and gpu_ds.compressed_bytes > 0
+        print("GPU JPEG backend:", gpu_ds.backend, gpu_ds.backend_errors)
+        assert gpu_ds.backend.startswith("nvjpeg:"), (gpu_ds.backend, gpu_ds.backend_errors)   # the native decoder, not the fallback
     conv.delete()
+
+
+def test_batched_resize_kernel_matches_pil_bilinear():
+    """csrc/jpeg_resize.cu: one launch resizes images of DIFFERENT sizes; the filter is PIL's BILINEAR (support stretched by
+    the down-scale factor), so it must agree with `Image.resize(..., BILINEAR)` to within rounding for shrink and enlarge."""
+    import numpy as np
+    from PIL import Image
+
+    from b200ddl import ops
+
+    jpeg = ops.ext("_b200_jpeg")
+    rng = np.random.default_rng(0)
+    sizes = [(375, 500), (96, 80), (224, 224), (100, 300), (600, 800), (50, 60)]
+    imgs, table, off = [], [], 0
+    for h, w in sizes:
+        base = rng.integers(0, 255, (h // 8 + 1, w // 8 + 1, 3)).astype(np.uint8)
+        img = np.asarray(Image.fromarray(base).resize((w, h), Image.BICUBIC)).astype(np.int32)
+        img = np.clip(img + rng.integers(-20, 20, img.shape), 0, 255).astype(np.uint8)
+        imgs.append(img)
+        table += [off, w, h, w * 3]
+        off += (h * w * 3 + 255) // 256 * 256
+    src = torch.zeros(off, dtype=torch.uint8)
+    for img, o in zip(imgs, table[0::4]):
+        src[o:o + img.size] = torch.from_numpy(img.reshape(-1))
+    out = torch.empty(len(sizes), 224, 224, 3, device="cuda", dtype=torch.uint8)
+    jpeg.resize_batched(src.cuda(), torch.tensor(table, dtype=torch.int64, device="cuda"), out)
+    for i, img in enumerate(imgs):
+        ref = np.asarray(Image.fromarray(img).resize((224, 224), Image.BILINEAR)).astype(np.int32)
+        d = np.abs(out[i].cpu().numpy().astype(np.int32) - ref)
+        assert d.max() <= 2 and d.mean() < 0.4, (sizes[i], int(d.max()), float(d.mean()))
 
 
 def test_smoke_entry():

@@ -250,3 +250,33 @@ def test_shard_udf_over_lazy_scan_pool_warmup_and_stats(session):
         assert all(w["wall_s"] >= w["predict_s"] * 0.5 for w in s3["per_worker"]) and len(s3["per_worker"]) == 2
     finally:
         udf.close()
+
+
+def test_decode_processes_match_decode_threads_and_surface_worker_death(session):
+    """`make_dataset(decode_processes=N)`: the decode runs in N torch-free worker processes whose output lands directly in
+    the ring's slots - same batches, bit for bit, as the thread path; a decode process that dies ends the stream with an
+    error instead of a hang."""
+    data = _tables(session, 64)
+    conv = make_converter(data.select(["content", "label_idx"]), session.cache_dir)
+    with conv.make_dataset(batch_size=16, num_epochs=1, workers_count=1, image_size=(IMG, IMG), device="cpu") as a, \
+         conv.make_dataset(batch_size=16, num_epochs=1, workers_count=1, image_size=(IMG, IMG), device="cpu",
+                           decode_processes=3) as b:
+        assert b.decode_processes == 3 and a.decode_processes == 0
+        n = 0
+        for (xa, ya), (xb, yb) in zip(a, b):
+            assert torch.equal(xa, xb) and torch.equal(ya, yb)
+            n += 1
+        assert n == 4
+    # two filler threads x two processes each, infinite epochs, shuffled: every batch is complete and the labels are valid
+    with conv.make_dataset(batch_size=8, workers_count=2, image_size=(IMG, IMG), device="cpu", shuffle=True, seed=3,
+                           decode_processes=4) as ds:
+        it = iter(ds)
+        for _ in range(12):
+            x, y = next(it)
+            assert x.shape == (8, IMG, IMG, 3) and int(y.min()) >= 0 and int(y.max()) < 5 and float(x.float().std()) > 1.0
+        # kill one decode process: the stream must end with an error, not block
+        ds._pools[0][0][0].kill()
+        with pytest.raises(RuntimeError, match="decode pipeline failed"):
+            for _ in range(64):
+                next(it)
+    conv.delete()
