@@ -94,7 +94,12 @@ class _TableDataset(RingDataset):
 
     def __init__(self, files, total_rows, batch_size, image_size, device, cur_shard, shard_count, num_epochs,
                  workers_count, shuffle, seed, decode_processes: int = 0):
-        super().__init__(batch_size, image_size, device, num_slots=max(4, workers_count + 2))
+        nproc = int(decode_processes or 0)
+        self._chunk = 16 if batch_size >= 64 else max(1, batch_size // 4)   # images per decode request
+        chunks_per_batch = -(-batch_size // self._chunk)
+        # process mode: enough slots that every decode process can hold a chunk of SOME slot while others are being consumed
+        slots = max(4, workers_count + 2) if nproc <= 0 else max(6, -(-nproc // chunks_per_batch) + 4)
+        super().__init__(batch_size, image_size, device, num_slots=slots)
         self.files = files
         self.total_rows = int(total_rows)
         self.cur_shard, self.shard_count = cur_shard, shard_count
@@ -108,19 +113,32 @@ class _TableDataset(RingDataset):
         self._row_iter = self._rows()
         self._active_workers = max(1, workers_count)
         self._error: Optional[BaseException] = None
-        # decode PROCESSES (loader/_decode_worker.py): every filler thread owns an equal share of them, splits its batch
-        # over its share and receives the decoded pixels straight into the pinned slot (`recv_bytes_into`)
+        # decode PROCESSES (loader/_decode_worker.py).  `workers_count` PLANNER threads cut batches into chunks of
+        # `self._chunk` rows and queue them; ONE light driver thread per process takes a chunk, ships the compressed bytes and
+        # receives the decoded pixels straight into the chunk's rows of the pinned slot (`recv_bytes_into`; the socket reads
+        # release the GIL).  A slot is committed by whichever driver finishes its last chunk.
         self._pools = None
-        if decode_processes and decode_processes > 0:
+        if nproc > 0:
+            import queue
+
             from ..utils.procpool import start_script_workers
 
-            nthreads = max(1, workers_count)
-            per = max(1, int(decode_processes) // nthreads)
             script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_decode_worker.py")
-            procs = start_script_workers(script, per * nthreads, env={"OMP_NUM_THREADS": "1"})
-            self._pools = [procs[k * per:(k + 1) * per] for k in range(nthreads)]
-        self.decode_processes = sum(len(p) for p in self._pools) if self._pools else 0
-        self._threads = [threading.Thread(target=self._worker, args=(k,), daemon=True) for k in range(max(1, workers_count))]
+            self._pools = start_script_workers(script, nproc, env={"OMP_NUM_THREADS": "1"})
+            self._work = queue.Queue(maxsize=4 * nproc)
+            self._plan_lock = threading.Lock()
+            self._pending = {}               # slot -> chunks still being decoded
+            self._seq_next = 0               # batches are numbered in the order they are cut from the row stream ...
+            self._seq_commit = 0             # ... and committed in that order (reorder buffer): the batch sequence is
+            self._seq_done = {}              # deterministic for a given seed, however the decode processes race
+            self._slot_seq = {}
+            self._planners_left = min(max(1, workers_count), 4)
+            self._drivers_left = nproc
+            self._threads = [threading.Thread(target=self._planner, daemon=True) for _ in range(self._planners_left)]
+            self._threads += [threading.Thread(target=self._driver, args=(k,), daemon=True) for k in range(nproc)]
+        else:
+            self._threads = [threading.Thread(target=self._worker, daemon=True) for _ in range(max(1, workers_count))]
+        self.decode_processes = nproc
         for t in self._threads:
             t.start()
 
@@ -172,17 +190,18 @@ class _TableDataset(RingDataset):
                     yield contents, labels, int(j)
             epoch += 1
 
-    def _worker(self, k: int = 0):
+    def _fail(self, ex: BaseException) -> None:
+        """A dead decode process, a corrupt row ...: end the stream; `__next__` re-raises once the committed batches are drained."""
+        if not self._stop.is_set():
+            self._error = ex
+            self._stop.set()
+            self.ring.finish()
+
+    def _worker(self):
         try:
-            if self._pools is not None:
-                self._produce_with_processes(self._pools[k])
-            else:
-                self._produce()
-        except BaseException as ex:  # a dead decode process, a corrupt row ...: end the stream and re-raise in __next__
-            if not self._stop.is_set():
-                self._error = ex
-                self._stop.set()      # the other fillers stop after their batch in flight ...
-                self.ring.finish()    # ... and the consumer gets the error once the committed batches are drained
+            self._produce()
+        except BaseException as ex:
+            self._fail(ex)
         finally:
             # the LAST worker to run out of rows ends the stream: the consumer drains what is committed and then gets
             # StopIteration (without this a `for batch in ds:` over a finite dataset blocked forever)
@@ -218,36 +237,93 @@ class _TableDataset(RingDataset):
                 pass
         return batch
 
-    def _produce_with_processes(self, pool):
-        row = self.h * self.w * 3
-        P = len(pool)
-        per = -(-self.batch_size // P)
-        while not self._stop.is_set():
-            batch = self._take_batch()
-            if len(batch) < self.batch_size:
-                return
-            slot = self.ring.acquire_fill()
-            if slot < 0:
-                return
-            img, lab = self.ring.slot_tensors(slot)
-            dst = memoryview(img.numpy().reshape(-1))
-            lab = lab.numpy()
-            sent = []
-            for k, (_, conn) in enumerate(pool):
-                rows = batch[k * per:(k + 1) * per]
-                if not rows:
+    def _planner(self):
+        """Process mode: batch -> slot -> chunks on the work queue."""
+        import queue
+
+        try:
+            while not self._stop.is_set():
+                # slot first, then the batch and its sequence number in one critical section: slots are acquired in
+                # sequence order too, so the oldest uncommitted batch always owns a slot (no reorder-buffer deadlock)
+                slot = self.ring.acquire_fill()
+                if slot < 0:
                     break
+                with self._plan_lock:
+                    batch = self._take_batch()
+                    seq = self._seq_next
+                    if len(batch) == self.batch_size:
+                        self._seq_next += 1
+                if len(batch) < self.batch_size:
+                    break
+                img, lab = self.ring.slot_tensors(slot)
+                dst = memoryview(img.numpy().reshape(-1))
+                lab = lab.numpy()
+                for i, (_, labels, j) in enumerate(batch):
+                    lab[i] = labels[j]
+                chunks = [(slot, dst, first, batch[first:first + self._chunk]) for first in range(0, self.batch_size, self._chunk)]
+                with self._lock:
+                    self._pending[slot] = len(chunks)
+                    self._slot_seq[slot] = seq
+                for item in chunks:
+                    while not self._stop.is_set():
+                        try:
+                            self._work.put(item, timeout=0.5)
+                            break
+                        except queue.Full:
+                            continue
+        except BaseException as ex:
+            self._fail(ex)
+        finally:
+            with self._lock:
+                self._planners_left -= 1
+                last = self._planners_left == 0
+            if last:   # every chunk is queued: one sentinel per driver, behind the last real item
+                for _ in range(self.decode_processes):
+                    while True:
+                        try:
+                            self._work.put(None, timeout=0.5)
+                            break
+                        except queue.Full:
+                            if self._stop.is_set():
+                                break
+
+    def _driver(self, k: int):
+        """Process mode: the thread that talks to decode process k."""
+        import queue
+
+        conn = self._pools[k][1]
+        row = self.h * self.w * 3
+        try:
+            while not self._stop.is_set():
+                try:
+                    item = self._work.get(timeout=0.5)
+                except queue.Empty:
+                    continue
+                if item is None:
+                    break
+                slot, dst, first, rows = item
                 payloads = [contents[j].as_buffer() for contents, _, j in rows]
                 head = np.array([self.h, self.w, len(rows)] + [len(b) for b in payloads], dtype=np.int32).tobytes()
                 conn.send_bytes(b"".join([head] + [memoryview(b) for b in payloads]))
-                sent.append((conn, k * per, len(rows)))
-            for conn, first, n in sent:   # blocking socket reads release the GIL; pixels land in the pinned slot directly
-                got = conn.recv_bytes_into(dst[first * row:(first + n) * row])
-                if got != n * row:
-                    raise RuntimeError(f"decode worker returned {got} bytes for {n} images")
-            for i, (_, labels, j) in enumerate(batch):
-                lab[i] = labels[j]
-            self.ring.commit(slot)
+                got = conn.recv_bytes_into(dst[first * row:(first + len(rows)) * row])   # pixels land in the pinned slot
+                if got != len(rows) * row:
+                    raise RuntimeError(f"decode worker {k} returned {got} bytes for {len(rows)} images")
+                with self._lock:
+                    self._pending[slot] -= 1
+                    if self._pending[slot] == 0:
+                        del self._pending[slot]
+                        self._seq_done[self._slot_seq.pop(slot)] = slot
+                        while self._seq_commit in self._seq_done:      # commit in sequence order
+                            self.ring.commit(self._seq_done.pop(self._seq_commit))
+                            self._seq_commit += 1
+        except BaseException as ex:
+            self._fail(ex)
+        finally:
+            with self._lock:
+                self._drivers_left -= 1
+                last = self._drivers_left == 0
+            if last and not self._stop.is_set():
+                self.ring.finish()   # finite epochs: everything decoded has been committed
 
     def __next__(self):
         try:
@@ -261,24 +337,22 @@ class _TableDataset(RingDataset):
         self._stop.set()
         super().close()
         if self._pools:
-            # the filler threads own the connections: let them finish the batch in flight before the exit frames are sent
+            # the driver threads own the connections: let them finish the chunk in flight before the exit frames are sent
             # (two writers on one socket would interleave their frames)
             for t in self._threads:
                 if t is not threading.current_thread():
                     t.join(timeout=20)
-            for pool in self._pools:
-                for proc, conn in pool:
-                    try:
-                        conn.send_bytes(b"")
-                        conn.close()
-                    except Exception:
-                        pass
-            for pool in self._pools:
-                for proc, _ in pool:
-                    try:
-                        proc.wait(timeout=5)
-                    except Exception:
-                        proc.kill()
+            for proc, conn in self._pools:
+                try:
+                    conn.send_bytes(b"")
+                    conn.close()
+                except Exception:
+                    pass
+            for proc, _ in self._pools:
+                try:
+                    proc.wait(timeout=5)
+                except Exception:
+                    proc.kill()
             self._pools = None
 
 

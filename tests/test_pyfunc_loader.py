@@ -275,7 +275,7 @@ def test_decode_processes_match_decode_threads_and_surface_worker_death(session)
             x, y = next(it)
             assert x.shape == (8, IMG, IMG, 3) and int(y.min()) >= 0 and int(y.max()) < 5 and float(x.float().std()) > 1.0
         # kill one decode process: the stream must end with an error, not block
-        ds._pools[0][0][0].kill()
+        ds._pools[0][0].kill()
         with pytest.raises(RuntimeError, match="decode pipeline failed"):
             for _ in range(64):
                 next(it)
