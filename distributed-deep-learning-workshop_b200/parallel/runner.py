@@ -20,6 +20,8 @@ import threading
 import time
 from typing import Any, Callable, List, Optional
 
+from ..utils.cpus import usable_cpus
+
 
 def _free_port() -> int:
     with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
@@ -84,7 +86,7 @@ class Runner:
         # N ranks with full-size OpenMP teams oversubscribe the host (measured: 50x slower CPU steps once the
         # spinning teams exceed the cores); like torchrun, give each rank its share unless the user chose.
         if not env.get("OMP_NUM_THREADS"):
-            env["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // self.np))
+            env["OMP_NUM_THREADS"] = str(max(1, usable_cpus() // self.np))   # the cgroup quota, not cpu_count
         return env
 
     def run(self, main: Callable[..., Any], **kwargs) -> Any:
