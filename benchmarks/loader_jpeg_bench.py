@@ -49,6 +49,16 @@ def main():
     ap.add_argument("--proc-threads", type=int, default=8, help="filler threads driving the decode processes")
     ap.add_argument("--modes", default="ring,cpu,procs,gpu")
     args = ap.parse_args()
+    # under torchrun (WORLD_SIZE > 1): data-parallel training, every rank reads ITS shard of the same cache and decodes it itself
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = 0
+    hvd = None
+    if world > 1:
+        import b200ddl.parallel as hvd
+
+        hvd.init()
+        rank = hvd.rank()
+        args.device = str(hvd.device())
     dev = torch.device(args.device)
     sw, sh = (int(v) for v in args.stored.split("x"))
     root = tempfile.mkdtemp(prefix="b200ddl_jpeg_")
@@ -67,18 +77,22 @@ def main():
     print(f"dataset: {args.images} JPEGs {sw}x{sh}, {jpeg_bytes / 1024:.1f} KB each, built in {time.time() - t0:.1f} s", flush=True)
 
     model = build_model(args.size, args.size, 3, len(CLASSES), arch=args.arch, batch_size=args.batch, freeze_base=False)
-    trainer = Trainer(model, device=args.device).compile(optimizer=optim.SGD(learning_rate=0.01, momentum=0.9),
-                                                         loss="sparse_categorical_crossentropy", metrics=["accuracy"])
+    opt = optim.SGD(learning_rate=0.01, momentum=0.9)
+    if world > 1:
+        opt = hvd.DistributedOptimizer(opt)
+    trainer = Trainer(model, device=args.device).compile(optimizer=opt, loss="sparse_categorical_crossentropy", metrics=["accuracy"])
+    shard = dict(cur_shard=rank, shard_count=world) if world > 1 else {}
 
     def make(mode):
         if mode == "ring":
             return SyntheticDataset(args.batch, num_classes=len(CLASSES), device=dev, threads=6, pool_images=2048, seed=3,
-                                    image_size=(args.size, args.size)) if dev.type == "cuda" else None
+                                    image_size=(args.size, args.size), **shard) if dev.type == "cuda" else None
         if mode == "procs":
             return conv.make_dataset(batch_size=args.batch, num_epochs=None, workers_count=args.proc_threads,
-                                     image_size=(args.size, args.size), device=dev, decode="cpu", decode_processes=args.procs)
+                                     image_size=(args.size, args.size), device=dev, decode="cpu",
+                                     decode_processes=max(1, args.procs // world), **shard)
         return conv.make_dataset(batch_size=args.batch, num_epochs=None, workers_count=args.workers,
-                                 image_size=(args.size, args.size), device=dev, decode=mode, decode_processes=0)
+                                 image_size=(args.size, args.size), device=dev, decode=mode, decode_processes=0, **shard)
 
     for mode in args.modes.split(","):
         if mode == "gpu" and dev.type != "cuda":
@@ -104,16 +118,23 @@ def main():
             hist = trainer.fit(ds, steps_per_epoch=args.steps, epochs=1, verbose=0)
             _sync(dev)
             dt = time.perf_counter() - t0
+            if world > 1:   # the job's rate: all ranks' images over the slowest rank's time
+                dt = max(hvd.allgather_object(dt))
+                loader_only = sum(hvd.allgather_object(loader_only))
             rec = {"mode": mode, "images": args.images, "stored": args.stored, "jpeg_kb": round(jpeg_bytes / 1024, 1),
                    "batch": args.batch, "steps": args.steps, "workers": args.workers if mode == "cpu" else (args.proc_threads if mode == "procs" else None),
                    "decode_processes": getattr(ds, "decode_processes", None),
-                   "loader_only_img_s": round(loader_only, 1), "train_img_s": round(args.batch * args.steps / dt, 1),
+                   "n_gpus": world, "loader_only_img_s": round(loader_only, 1), "train_img_s": round(world * args.batch * args.steps / dt, 1),
                    "train_ms_per_step": round(dt / args.steps * 1e3, 3),
                    "loader_wait_ms": round(ring.consumer_wait_ms - w0, 2) if ring is not None else None,
                    "gpu_decoded": getattr(ds, "gpu_decoded", None), "cpu_decoded": getattr(ds, "cpu_decoded", None),
                    "loss": hist.history["loss"][-1], "arch": args.arch, "cpus": os.cpu_count()}
-            print("LOADER_JPEG " + json.dumps(rec), flush=True)
+            if rank == 0:
+                print("LOADER_JPEG " + json.dumps(rec), flush=True)
     conv.delete()
+    if world > 1:
+        del trainer, model, opt
+        hvd.shutdown()
 
 
 if __name__ == "__main__":
