@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--stored", default="500x375")
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--backends", default="hardware,gpu_hybrid,hybrid,torchvision")
     args = ap.parse_args()
     sw, sh = (int(v) for v in args.stored.split("x"))
     pdf = synthetic_images(args.batch, size=(sh, sw), jpeg=True, seed=5).to_pandas()
@@ -64,7 +65,8 @@ def main():
             traceback.print_exc()
         print("JPEG_DECODE " + json.dumps(rec), flush=True)
 
-    for name in ("hardware", "gpu_hybrid", "hybrid"):
+    want = args.backends.split(",")
+    for name in [b for b in ("hardware", "gpu_hybrid", "hybrid") if b in want]:
         try:
             dec = jpeg.JpegDecoder(args.batch, name, 8, 0)
         except Exception as ex:
@@ -73,6 +75,8 @@ def main():
         report("nvjpeg:" + name, lambda: dec.decode_resize(ptrs, lens, out), {"hardware_info": dec.hardware_info()})
         del dec
 
+    if "torchvision" not in want:
+        return
     import torchvision
 
     data = [torch.from_numpy(b) for b in blobs]
