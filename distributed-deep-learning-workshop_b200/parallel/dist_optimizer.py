@@ -292,7 +292,8 @@ class DistributedOptimizer:
         every bucket; this makes every rank's state tensors complete (sum of the owners' slices), so that a checkpoint
         written by rank 0 can be resumed on any world size and `broadcast_parameters` does not overwrite live slices
         with rank 0's stale ones.  No-op without fused_update."""
-        if not self.fused_update or self.world == 1:
+        if not self.state_is_sharded or not self.buckets:
+            # no fused step has run since the state was last complete (fresh optimizer, just-loaded checkpoint, ...)
             self._state_complete = True
             return
         for name, v in self.opt.state.items():

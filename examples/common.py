@@ -29,5 +29,12 @@ def have_gpu() -> bool:
     return torch.cuda.is_available()
 
 
+def decode_mode() -> str:
+    """`WORKSHOP_DECODE=gpu`: JPEG rows are decoded on the GPU (nvJPEG + our resize kernel) instead of by CPU workers - the
+    path that scales with the number of GPUs per host (examples/part1/04_monitoring_and_optimization.md)."""
+    mode = os.environ.get("WORKSHOP_DECODE", "cpu")
+    return mode if (mode == "gpu" and have_gpu()) else "cpu"
+
+
 def default_arch() -> str:
     return "resnet50" if (have_gpu() and IMG_HEIGHT % 32 == 0 and not SMALL) else "mobilenetv2"

@@ -16,6 +16,7 @@ BATCH_SIZE = int(os.environ.get("BATCH_SIZE", "16" if SMALL else "256"))   # ref
 EPOCHS = 3                                                                  # reference :82
 HVD_NP = int(os.environ.get("HVD_NP", "2"))
 ARCH = default_arch()
+DECODE = decode_mode()   # WORKSHOP_DECODE=gpu: nvJPEG + our resize kernel instead of CPU decode workers
 
 cols_to_keep = ["content", "label_idx"]
 train_df = catalog.table(f"{database_name}.silver_train").select(cols_to_keep)
@@ -47,9 +48,9 @@ def train_and_evaluate_hvd():
     trainer = Trainer(model).compile(optimizer=optimizer, loss="sparse_categorical_crossentropy",
                                      metrics=["accuracy"])                                   # :325-328
     with converter_train.make_dataset(batch_size=BATCH_SIZE, cur_shard=hvd.rank(), shard_count=hvd.size(),
-                                      image_size=(IMG_HEIGHT, IMG_WIDTH)) as train_ds, \
+                                      image_size=(IMG_HEIGHT, IMG_WIDTH), decode=DECODE) as train_ds, \
          converter_val.make_dataset(batch_size=BATCH_SIZE, cur_shard=hvd.rank(), shard_count=hvd.size(),
-                                    image_size=(IMG_HEIGHT, IMG_WIDTH)) as val_ds:               # :332-337
+                                    image_size=(IMG_HEIGHT, IMG_WIDTH), decode=DECODE) as val_ds:               # :332-337
         steps_per_epoch = max(1, train_size // (BATCH_SIZE * hvd.size()))                    # :350
         validation_steps = max(1, val_size // (BATCH_SIZE * hvd.size()))                     # :351
         hist = trainer.fit(train_ds, steps_per_epoch=steps_per_epoch, epochs=EPOCHS, verbose=1,

@@ -18,6 +18,7 @@ EPOCHS = 1 if SMALL else 3                                                 # ref
 HVD_NUM_PROCESSES = int(os.environ.get("HVD_NP", "2"))                     # reference :70
 MAX_EVALS = int(os.environ.get("MAX_EVALS", "2" if SMALL else "4"))        # reference :357
 ARCH = default_arch()
+DECODE = decode_mode()   # WORKSHOP_DECODE=gpu: nvJPEG + our resize kernel instead of CPU decode workers
 checkpoint_dir = os.path.join(session.checkpoint_root, str(time.time()))   # reference :66-67
 os.makedirs(checkpoint_dir, exist_ok=True)
 
@@ -44,9 +45,9 @@ def train_and_evaluate_hvd(learning_rate=0.001, dropout=0.5, batch_size=32, chec
                                          save_weights_only=True))
     trainer = Trainer(model).compile(optimizer=optimizer, loss="sparse_categorical_crossentropy", metrics=["accuracy"])
     with converter_train.make_dataset(batch_size=batch_size, cur_shard=hvd.rank(), shard_count=hvd.size(),
-                                      image_size=(IMG_HEIGHT, IMG_WIDTH)) as train_ds, \
+                                      image_size=(IMG_HEIGHT, IMG_WIDTH), decode=DECODE) as train_ds, \
          converter_val.make_dataset(batch_size=batch_size, cur_shard=hvd.rank(), shard_count=hvd.size(),
-                                    image_size=(IMG_HEIGHT, IMG_WIDTH)) as val_ds:
+                                    image_size=(IMG_HEIGHT, IMG_WIDTH), decode=DECODE) as val_ds:
         steps_per_epoch = max(1, train_size // (batch_size * hvd.size()))
         validation_steps = max(1, val_size // (batch_size * hvd.size()))
         hist = trainer.fit(train_ds, steps_per_epoch=steps_per_epoch, epochs=EPOCHS, verbose=1,
