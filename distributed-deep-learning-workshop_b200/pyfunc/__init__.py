@@ -161,7 +161,8 @@ class _FragmentScorer:
         return t
 
     def score(self, frags_iter):
-        """Generator: yields (fragment position, predictions ndarray) for (position, fragment) pairs from `frags_iter`."""
+        """Generator: yields (fragment position, predictions as an Arrow array of the UDF's result type) for (position, fragment)
+        pairs from `frags_iter`."""
         import concurrent.futures as cf
         import time
 
@@ -397,7 +398,8 @@ class ShardUDF:
       Arrow batches) or generated (synthetic fragments) inside the worker that scores them;
     * workers are persistent - one process per GPU, model loaded once, reused by every later call of this UDF - and pull
       fragments from a shared queue (dynamic load balancing); each overlaps reading fragment k+1 with scoring fragment k;
-    * `stats` after a call: rows, workers, seconds, rows_per_sec, per-worker read / predict seconds."""
+    * `stats` after a call: rows, workers, fragments, seconds (scoring wall), rows_per_sec, startup_seconds (worker start + model
+      load + warm-up, one-off), prepare_seconds (fragment planning / IPC spill), per-worker read / predict / wall seconds."""
 
     def __init__(self, model_uri: str, result_type: str = "string", num_workers: Optional[int] = None,
                  batch_rows: int = 4096):
@@ -455,6 +457,7 @@ class ShardUDF:
         frags = self._fragments_of(table, column)
         n = sum(f.rows for f in frags)
         workers = min(self._workers(), max(1, len(frags)))
+        prepare_s = time.time() - t0   # fragment descriptors; for an in-memory table also the one-off Arrow IPC spill
         per_worker: List[dict] = []
         try:
             startup_s = 0.0
@@ -468,7 +471,8 @@ class ShardUDF:
                     self._local_sig = _frag_sig(frags[0])
                 t0 = time.time()
                 res = dict(self._local.score(enumerate(frags)))
-                per_worker = [{"worker": 0, "read_s": self._local.read_s, "predict_s": self._local.predict_s}]
+                per_worker = [{"worker": 0, "read_s": self._local.read_s, "predict_s": self._local.predict_s,
+                               "wall_s": self._local.wall_s}]
             else:
                 if (self._pool is None or self._pool.column != column or len(self._pool.procs) != workers
                         or self._pool.result_type != self.result_type):
@@ -490,7 +494,8 @@ class ShardUDF:
         arrays = [res[i] for i in range(len(frags))]   # Arrow arrays built by the workers: concatenation moves no elements
         dt = time.time() - t0
         self.stats = {"rows": n, "workers": workers, "fragments": len(frags), "seconds": dt,
-                      "rows_per_sec": n / max(dt, 1e-9), "startup_seconds": startup_s, "per_worker": per_worker}
+                      "rows_per_sec": n / max(dt, 1e-9), "startup_seconds": startup_s, "prepare_seconds": prepare_s,
+                      "per_worker": per_worker}
         return pa.chunked_array(arrays, type=typ)
 
     def close(self) -> None:

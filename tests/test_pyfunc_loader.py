@@ -280,3 +280,59 @@ def test_decode_processes_match_decode_threads_and_surface_worker_death(session)
             for _ in range(64):
                 next(it)
     conv.delete()
+
+
+def _planner_ns(files, total, shard, count, shuffle=False, seed=0, num_epochs=1):
+    """The row planner of the table datasets without a ring / decode threads (what `_GpuDecodeDataset` borrows too)."""
+    import types
+
+    from b200ddl.loader import _TableDataset
+
+    ns = types.SimpleNamespace(files=files, total_rows=total, cur_shard=shard, shard_count=count, num_epochs=num_epochs,
+                               shuffle=shuffle, seed=seed, row_groups_read=0, batch_size=1)
+    ns.row_lo, ns.row_hi = (total * shard) // count, (total * (shard + 1)) // count
+    ns._plan = lambda: _TableDataset._plan(ns)
+    return ns, _TableDataset._rows(ns)
+
+
+def test_loader_sharding_properties(tmp_path):
+    """Property test: for arbitrary file / row-group layouts and shard counts, the shards are
+    disjoint, together cover every row exactly once, differ in size by at most one row, open only row groups they own rows
+    of, and `shuffle` yields a seed-determined permutation of exactly the shard's rows that changes from epoch to epoch."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from hypothesis import given, settings, strategies as st
+
+    counter = [0]
+
+    @settings(max_examples=20, deadline=None)
+    @given(files=st.lists(st.tuples(st.integers(1, 40), st.integers(1, 17)), min_size=1, max_size=3),
+           shards=st.integers(1, 7), seed=st.integers(0, 1000))
+    def check(files, shards, seed):
+        counter[0] += 1
+        paths, base = [], 0
+        for k, (rows, rg) in enumerate(files):
+            p = tmp_path / f"c{counter[0]}_{k}.parquet"
+            ids = list(range(base, base + rows))
+            pq.write_table(pa.table({"content": [i.to_bytes(4, "little") for i in ids], "label_idx": ids}), p, row_group_size=rg)
+            paths.append((str(p), base))
+            base += rows
+        total = base
+        seen, sizes = [], []
+        for s in range(shards):
+            ns, rows = _planner_ns(paths, total, s, shards)
+            got = [int(labels[j]) for _, labels, j in rows]
+            assert got == list(range(ns.row_lo, ns.row_hi))                      # contiguous range, file order
+            groups_owned = sum(1 for (fi, rg, skip, cnt) in ns._plan())
+            assert ns.row_groups_read == groups_owned                             # no read amplification
+            seen += got
+            sizes.append(len(got))
+            ns1, r1 = _planner_ns(paths, total, s, shards, shuffle=True, seed=seed, num_epochs=2)
+            ns2, r2 = _planner_ns(paths, total, s, shards, shuffle=True, seed=seed, num_epochs=2)
+            a = [int(l[j]) for _, l, j in r1]
+            b = [int(l[j]) for _, l, j in r2]
+            assert a == b and len(a) == 2 * len(got)                              # deterministic for a seed, two epochs
+            assert sorted(a[:len(got)]) == got and sorted(a[len(got):]) == got    # every epoch = a permutation of the shard
+        assert sorted(seen) == list(range(total)) and max(sizes) - min(sizes) <= 1
+
+    check()
