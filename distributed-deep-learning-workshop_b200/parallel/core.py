@@ -9,7 +9,6 @@ from __future__ import annotations
 
 import datetime
 import os
-import pickle
 from typing import Any, List, Optional
 
 import torch
