@@ -306,7 +306,8 @@ def main():
                    "api": "b200ddl.train.Trainer.fit over loader.SyntheticDataset (pinned ring, side-stream H2D)",
                    "loader_wait_ms": ds.ring.consumer_wait_ms, "final_loss": hist.history["loss"][-1]}
 
-    cfg_flags = {"fuse_block_grad": bool(engine.fuse_block_grad), "fuse_stem_bwd": bool(engine.fuse_stem_bwd)}
+    cfg_flags = {"fuse_block_grad": bool(engine.fuse_block_grad), "fuse_stem_bwd": bool(engine.fuse_stem_bwd),
+                 "bn_rows_unroll": int(engine._e.get_bn_rows_unroll()) if hasattr(engine._e, "get_bn_rows_unroll") else 1}
     # ---------------------------------------------------------------- same-lease baseline (torch + cuDNN + NCCL)
     baseline = None
     algo_used = getattr(opt, "algo", "none") if world > 1 else "none"

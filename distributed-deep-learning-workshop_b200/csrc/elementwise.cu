@@ -134,8 +134,12 @@ __device__ __forceinline__ void bn_bwd_coeffs8(const BnBwdFuse& f, int c0, bool 
 // out = [relu]( y*scale + shift  [+ res | + res*res_scale + res_shift] )
 // Column-resident: a thread owns one 8-channel column vector and walks down the rows, so the per-channel
 // parameters are loaded into registers once instead of once per element (L1 traffic was 5x the payload).
-template <bool RELU, int RES, bool FUSED = false>  // RES: 0 none, 1 identity residual, 2 residual with its own BN
-__global__ void __launch_bounds__(256)
+// U: rows per loop iteration.  All loads of the U rows are issued before the first is consumed: with one row per iteration a
+// thread has one or two 16-byte loads in flight and the kernel sits at ~64 % of the measured copy bandwidth (ncu: bn_bwd_apply
+// 4.2 of 6.57 TB/s at 34 % occupancy - too few bytes in flight for HBM3e's latency); the per-element arithmetic and its order
+// are unchanged, so every U produces bit-identical results.
+template <bool RELU, int RES, bool FUSED = false, int U = 1>  // RES: 0 none, 1 identity residual, 2 residual with its own BN
+__global__ void __launch_bounds__(256, U > 1 ? 3 : 1)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                 const float* __restrict__ res_scale, const float* __restrict__ res_shift,
@@ -161,15 +165,29 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
         ldf8(res_shift + cv * 8, rh);
       }
     }
-    for (int64_t r = (int64_t)blockIdx.x * rpb + ry; r < M; r += (int64_t)gridDim.x * rpb) {
+    const int64_t rstep = (int64_t)gridDim.x * rpb;
+    for (int64_t r0 = (int64_t)blockIdx.x * rpb + ry; r0 < M; r0 += rstep * U) {
+      bf16x8 yraw[U], rraw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + u * rstep;
+        if (r < M) {
+          yraw[u] = ld8(y + r * C + cv * 8);
+          if (RES >= 1) rraw[u] = ld8(res + r * C + cv * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * rstep;
+      if (r >= M) break;
       const int64_t off = r * C + cv * 8;
       float f[8];
-      unpack8(ld8(y + off), f);
+      unpack8(yraw[u], f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
       if (RES >= 1) {
         float q[8];
-        unpack8(ld8(res + off), q);
+        unpack8(rraw[u], q);
         if (RES == 2) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) q[k] = fmaf(q[k], rs[k], rh[k]);
@@ -188,9 +206,15 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
         for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
       }
       st8(out + off, pack8(f));
+      }
     }
   }
 }
+
+// rows per loop iteration of the BatchNorm apply / backward-apply kernels (1, 2 or 4); see bn_apply_kernel
+static int g_bn_rows_unroll = 1;
+void set_bn_rows_unroll(int u) { g_bn_rows_unroll = (u == 2 || u == 4) ? u : 1; }
+int get_bn_rows_unroll() { return g_bn_rows_unroll; }
 
 static inline int rows_grid(int64_t M, int C, int threads) {
   const int cvec = C / 8;
@@ -212,7 +236,15 @@ void bn_apply(const void* y, const float* scale, const float* shift, const void*
   auto O = (__nv_bfloat16*)out;
   auto MK = (uint8_t*)mask;
   const int rmode = res == nullptr ? 0 : (res_scale == nullptr ? 1 : 2);
-#define LAUNCH(RL, RM) bn_apply_kernel<RL, RM><<<blocks, threads, 0, s>>>(Y, scale, shift, R, res_scale, res_shift, O, MK, M, C)
+#define LAUNCH(RL, RM)                                                                                               \
+  do {                                                                                                               \
+    if (g_bn_rows_unroll == 4)                                                                                       \
+      bn_apply_kernel<RL, RM, false, 4><<<blocks, threads, 0, s>>>(Y, scale, shift, R, res_scale, res_shift, O, MK, M, C); \
+    else if (g_bn_rows_unroll == 2)                                                                                  \
+      bn_apply_kernel<RL, RM, false, 2><<<blocks, threads, 0, s>>>(Y, scale, shift, R, res_scale, res_shift, O, MK, M, C); \
+    else                                                                                                             \
+      bn_apply_kernel<RL, RM><<<blocks, threads, 0, s>>>(Y, scale, shift, R, res_scale, res_shift, O, MK, M, C);     \
+  } while (0)
   if (relu) {
     if (rmode == 0) LAUNCH(true, 0); else if (rmode == 1) LAUNCH(true, 1); else LAUNCH(true, 2);
   } else {
@@ -402,8 +434,8 @@ void bn_bwd_coeffs(float* sum_dz, float* sum_dzy, const float* gamma, const floa
 
 // dy = A*dz + B*y + Cc  with dz either read as-is (MASK=false: stored dz / BN without ReLU) or recomputed as
 // g * (y*scale + shift > 0) (MASK=true).  Column-resident like bn_apply_kernel.
-template <bool MASK, bool FUSED = false>
-__global__ void __launch_bounds__(256)
+template <bool MASK, bool FUSED = false, int U = 1>   // U: rows per loop iteration (see bn_apply_kernel)
+__global__ void __launch_bounds__(256, U > 1 ? 3 : 1)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ cA, const float* __restrict__ cB,
@@ -428,18 +460,33 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
       ldf8(scale + cv * 8, sc);
       ldf8(shift + cv * 8, sh);
     }
-    for (int64_t r = (int64_t)blockIdx.x * rpb + ry; r < M; r += (int64_t)gridDim.x * rpb) {
-      const int64_t off = r * C + cv * 8;
-      float gg[8], yy[8];
-      unpack8(ld8(g + off), gg);
-      unpack8(ld8(y + off), yy);
-      if (MASK) {
+    const int64_t rstep = (int64_t)gridDim.x * rpb;
+    for (int64_t r0 = (int64_t)blockIdx.x * rpb + ry; r0 < M; r0 += rstep * U) {
+      bf16x8 graw[U], yraw[U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) gg[k] = fmaf(yy[k], sc[k], sh[k]) > 0.f ? gg[k] : 0.f;
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + u * rstep;
+        if (r < M) {
+          graw[u] = ld8(g + r * C + cv * 8);
+          yraw[u] = ld8(y + r * C + cv * 8);
+        }
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) gg[k] = fmaf(A[k], gg[k], fmaf(B[k], yy[k], Cc[k]));
-      st8(dy + off, pack8(gg));
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + u * rstep;
+        if (r >= M) break;
+        const int64_t off = r * C + cv * 8;
+        float gg[8], yy[8];
+        unpack8(graw[u], gg);
+        unpack8(yraw[u], yy);
+        if (MASK) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) gg[k] = fmaf(yy[k], sc[k], sh[k]) > 0.f ? gg[k] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gg[k] = fmaf(A[k], gg[k], fmaf(B[k], yy[k], Cc[k]));
+        st8(dy + off, pack8(gg));
+      }
     }
   }
 }
@@ -447,12 +494,23 @@ void bn_bwd_apply(const void* g, const void* y, const float* scale, const float*
                   const float* cB, const float* cC, void* dy, int64_t M, int C, cudaStream_t s) {
   const int threads = 256;
   const int blocks = rows_grid(M, C, threads);
+  auto G = (const __nv_bfloat16*)g;
+  auto Y = (const __nv_bfloat16*)y;
+  auto D = (__nv_bfloat16*)dy;
+#define LAUNCH_BWD(MK)                                                                                         \
+  do {                                                                                                         \
+    if (g_bn_rows_unroll == 4)                                                                                 \
+      bn_bwd_apply_kernel<MK, false, 4><<<blocks, threads, 0, s>>>(G, Y, scale, shift, cA, cB, cC, D, M, C);    \
+    else if (g_bn_rows_unroll == 2)                                                                            \
+      bn_bwd_apply_kernel<MK, false, 2><<<blocks, threads, 0, s>>>(G, Y, scale, shift, cA, cB, cC, D, M, C);    \
+    else                                                                                                       \
+      bn_bwd_apply_kernel<MK><<<blocks, threads, 0, s>>>(G, Y, scale, shift, cA, cB, cC, D, M, C);             \
+  } while (0)
   if (scale != nullptr)
-    bn_bwd_apply_kernel<true><<<blocks, threads, 0, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y, scale, shift,
-                                                         cA, cB, cC, (__nv_bfloat16*)dy, M, C);
+    LAUNCH_BWD(true);
   else
-    bn_bwd_apply_kernel<false><<<blocks, threads, 0, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y, scale,
-                                                          shift, cA, cB, cC, (__nv_bfloat16*)dy, M, C);
+    LAUNCH_BWD(false);
+#undef LAUNCH_BWD
 }
 
 void bn_bwd_apply_fused(const void* g, const void* y, const float* scale, const float* shift, const BnBwdFuse& f, void* dy,

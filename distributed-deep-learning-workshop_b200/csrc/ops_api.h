@@ -37,6 +37,9 @@ void bn_bwd_apply_fused(const void* g, const void* y, const float* scale, const 
 void bn_finalize(float* sum, float* sqsum, double count, const float* gamma, const float* beta, float* running_mean,
                  float* running_var, float momentum, float eps, float* mean, float* invstd, float* scale,
                  float* shift, int C, bool training, cudaStream_t s);
+// rows per loop iteration of the BatchNorm apply / backward-apply kernels: 1 (default), 2 or 4 - bit-identical results
+void set_bn_rows_unroll(int u);
+int get_bn_rows_unroll();
 void bn_apply(const void* y, const float* scale, const float* shift, const void* res, const float* res_scale,
               const float* res_shift, void* out, void* mask, int64_t M, int C, bool relu, cudaStream_t s);
 void channel_stats(const void* y, float* sum, float* sqsum, int64_t M, int C, cudaStream_t s);

@@ -399,6 +399,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("scale"), py::arg("shift"), py::arg("cA") = c10::nullopt, py::arg("cB") = c10::nullopt,
         py::arg("cC") = c10::nullopt, py::arg("dy") = c10::nullopt, py::arg("sum_dz"), py::arg("sum_dzy"));
   m.def("zero_", &zero_);
+  m.def("set_bn_rows_unroll", [](int64_t u) { b200::set_bn_rows_unroll((int)u); });
+  m.def("get_bn_rows_unroll", []() { return (int64_t)b200::get_bn_rows_unroll(); });
   m.def("mbv2_stem", &mbv2_stem);
   m.def("dwconv3x3", &dwconv3x3, pybind11::arg("x"), pybind11::arg("w"), pybind11::arg("scale"), pybind11::arg("shift"),
         pybind11::arg("out"), pybind11::arg("stride"), pybind11::arg("tile_w") = 4);
