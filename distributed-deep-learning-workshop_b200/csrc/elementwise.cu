@@ -213,7 +213,10 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
 
 // rows per loop iteration of the BatchNorm apply / backward-apply kernels (1, 2 or 4); see bn_apply_kernel
 static int g_bn_rows_unroll = 1;
-void set_bn_rows_unroll(int u) { g_bn_rows_unroll = (u == 2 || u == 4) ? u : 1; }
+// 3 = per-kernel choice from the measured table (profiles/r2_bn_unroll_check.txt): 4 rows for the forward apply without /
+// with an identity residual and for the mask-free backward apply, 2 rows for the backward apply that recomputes the ReLU mask,
+// 1 row for the apply with a second BatchNorm on the residual (more rows spill there)
+void set_bn_rows_unroll(int u) { g_bn_rows_unroll = (u == 2 || u == 3 || u == 4) ? u : 1; }
 int get_bn_rows_unroll() { return g_bn_rows_unroll; }
 
 static inline int rows_grid(int64_t M, int C, int threads) {
@@ -238,7 +241,7 @@ void bn_apply(const void* y, const float* scale, const float* shift, const void*
   const int rmode = res == nullptr ? 0 : (res_scale == nullptr ? 1 : 2);
 #define LAUNCH(RL, RM)                                                                                               \
   do {                                                                                                               \
-    if (g_bn_rows_unroll == 4)                                                                                       \
+    if (g_bn_rows_unroll == 4 || (g_bn_rows_unroll == 3 && RM != 2))                                                 \
       bn_apply_kernel<RL, RM, false, 4><<<blocks, threads, 0, s>>>(Y, scale, shift, R, res_scale, res_shift, O, MK, M, C); \
     else if (g_bn_rows_unroll == 2)                                                                                  \
       bn_apply_kernel<RL, RM, false, 2><<<blocks, threads, 0, s>>>(Y, scale, shift, R, res_scale, res_shift, O, MK, M, C); \
@@ -499,9 +502,9 @@ void bn_bwd_apply(const void* g, const void* y, const float* scale, const float*
   auto D = (__nv_bfloat16*)dy;
 #define LAUNCH_BWD(MK)                                                                                         \
   do {                                                                                                         \
-    if (g_bn_rows_unroll == 4)                                                                                 \
+    if (g_bn_rows_unroll == 4 || (g_bn_rows_unroll == 3 && !MK))                                               \
       bn_bwd_apply_kernel<MK, false, 4><<<blocks, threads, 0, s>>>(G, Y, scale, shift, cA, cB, cC, D, M, C);    \
-    else if (g_bn_rows_unroll == 2)                                                                            \
+    else if (g_bn_rows_unroll == 2 || (g_bn_rows_unroll == 3 && MK))                                           \
       bn_bwd_apply_kernel<MK, false, 2><<<blocks, threads, 0, s>>>(G, Y, scale, shift, cA, cB, cC, D, M, C);    \
     else                                                                                                       \
       bn_bwd_apply_kernel<MK><<<blocks, threads, 0, s>>>(G, Y, scale, shift, cA, cB, cC, D, M, C);             \
