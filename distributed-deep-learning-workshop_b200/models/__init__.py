@@ -30,6 +30,8 @@ def build_model(img_height: int = IMG_HEIGHT, img_width: int = IMG_WIDTH, img_ch
         raise ValueError("only 3-channel images are supported")
     if arch is None:
         arch = "resnet50" if (torch.cuda.is_available() and img_height == img_width and img_height % 32 == 0) else "mobilenetv2"
+    if arch == "mobilenetv2_head":   # SURVEY.md 7.1's spelling of the reference's model (frozen MobileNetV2 base + trainable head)
+        arch = "mobilenetv2"
     if arch == "resnet50":
         from .resnet_engine import ResNet50Engine
 
