@@ -235,3 +235,61 @@ def test_persistent_rank_pool_reuses_processes_and_process_group():
         assert "second job exploded" in str(ei.value)
         pid2, v2 = r.run(fn, offset=1.0)   # a fresh gang
         assert pid2 != pid0 and v2 == 3.0
+
+
+def test_consolidate_state_completes_rank_sharded_momentum_and_save_refuses_a_sharded_state(tmp_path):
+    """`fused_update` shards the momentum over ranks (csrc/allreduce.cu allreduce_sgd_nvls_kernel updates only the owner's
+    slice).  `consolidate_state()` must rebuild the complete tensor on every rank from the owners' slices, `Trainer.save`
+    must refuse an unconsolidated state, and `broadcast_parameters` must consolidate first.  The kernel needs NVLS; the
+    slice logic is exercised here on 2 CPU ranks by putting the optimizer into the sharded state by hand."""
+    ck = str(tmp_path / "ck.pt")
+
+    def fn(ck):
+        import torch
+        import b200ddl.parallel as hvd
+        from b200ddl import optim
+        from b200ddl.train import Trainer
+
+        hvd.init()
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+        opt = hvd.DistributedOptimizer(optim.SGD(0.1, momentum=0.9), bucket_mb=0.0001)
+        tr = Trainer(model, device="cpu").compile(optimizer=opt)
+        x = torch.randint(0, 255, (8, 8, 8, 3), dtype=torch.uint8)
+        y = torch.randint(0, 4, (8,))
+        tr.fit([(x, y)] * 2, steps_per_epoch=2, epochs=1, verbose=0)      # buckets exist, momentum is allocated
+        mom = opt.opt.state["momentum"]
+        truth = torch.arange(mom.numel(), dtype=torch.float32) * 0.5 + 1.0
+        # emulate the sharded state: a rank holds the truth on the ranges it owns and garbage everywhere else
+        opt.fused_update = True
+        opt._state_complete = False
+        mom.fill_(-777.0 - hvd.rank())
+        covered = torch.zeros(mom.numel(), dtype=torch.bool)
+        for b in opt.buckets:
+            a, e = opt.owned_range(b.lo, b.hi, hvd.rank(), hvd.size())
+            mom[a:e] = truth[a:e]
+            for r in range(hvd.size()):
+                a2, e2 = opt.owned_range(b.lo, b.hi, r, hvd.size())
+                covered[a2:e2] = True
+        refused = False
+        try:
+            tr.save(ck + f".{hvd.rank()}")
+        except RuntimeError as ex:
+            refused = "consolidate_state" in str(ex)
+        opt.consolidate_state()
+        ok = bool(torch.equal(mom[covered], truth[covered])) and not opt.state_is_sharded
+        tr.save(ck + f".{hvd.rank()}")                                     # complete state: accepted
+        # a later fused step shards it again; broadcast_parameters consolidates before it broadcasts
+        opt.begin_step()
+        sharded_again = opt.state_is_sharded
+        mom.fill_(-1.0)
+        for b in opt.buckets:
+            a, e = opt.owned_range(b.lo, b.hi, hvd.rank(), hvd.size())
+            mom[a:e] = truth[a:e] * 2
+        opt.broadcast_parameters(tr.backend.flat.params, 0)
+        ok2 = bool(torch.equal(mom[covered], truth[covered] * 2))
+        return {"refused": refused, "ok": ok, "sharded_again": sharded_again, "ok2": ok2, "n": int(covered.sum()), "buckets": len(opt.buckets)}
+
+    out = Runner(np=2, driver_log_verbosity="none", force_cpu=True).run(fn, ck=ck)
+    assert out["refused"] and out["ok"] and out["sharded_again"] and out["ok2"], out
+    assert out["buckets"] >= 2 and out["n"] > 0
