@@ -9,7 +9,9 @@ Reference usage (P1/03:137-144, 204-219, 332-348, 425-426)::
     converter.delete()                                        ->  conv.delete()
 
 `make_dataset` yields ``(images uint8 [B,H,W,3], labels int64 [B])`` forever (`num_epochs=None`, the reference's
-dead-lock avoidance for unequal shards, P1/03:199).  Rows are read from the parquet cache by `workers_count` decode
+dead-lock avoidance for unequal shards, P1/03:199).  On a GPU the yielded tensors are views of a small device-side
+staging ring (two buffers for the pinned-ring datasets, three for `decode='gpu'`): a batch is valid until the next-but-one
+`next()`; `Trainer.fit / evaluate` consume it immediately, anything that keeps batches around must `.clone()` them.  Rows are read from the parquet cache by `workers_count` decode
 threads (PIL releases the GIL), written straight into pinned host slots of the native `RingLoader`
 (csrc/ring_loader.cpp) and moved to the GPU with cudaMemcpyAsync on a side stream, double-buffered on the device.
 `SyntheticDataset` feeds the same ring from native gather threads (JPEG-shaped uint8 tensors; no network here).
@@ -368,7 +370,9 @@ class _GpuDecodeDataset:
     Fallbacks: `torchvision.io.decode_jpeg(device=cuda)` + `resize_bilinear_u8` when the native decoder cannot be created
     (`B200DDL_JPEG_BACKEND=torchvision` forces it; `=hardware|gpu_hybrid|hybrid` pins a backend); rows that are not JPEG
     (PNG, raw tensors) take the CPU decoder.  Same sharding / shuffle / epoch semantics as the pinned-ring dataset (it reuses
-    its row planner); yields (images uint8 [B,H,W,3], labels int64 [B])."""
+    its row planner); yields (images uint8 [B,H,W,3], labels int64 [B]).  The yielded tensors are views of a 3-deep device
+    ring: a batch stays valid until the SECOND `next()` after it (consume it - `fit` copies it into the engine's input right
+    away - or `.clone()` it)."""
 
     _BUFFERS = 3
 
